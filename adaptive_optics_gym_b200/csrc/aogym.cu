@@ -1,0 +1,689 @@
+// libaogym: C-ABI + host orchestration of the AO-v0 step path on B200 (sm_100a).
+// See include/aogym.h for the contract and the reference lines each entry point replaces.
+#include "common.cuh"
+#include "kernels_f64.cuh"
+#include "tensor_path.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+template <typename T>
+int dev_alloc(aog_env* env, T** p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) return AOG_OK;
+  AOG_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+  return AOG_OK;
+}
+
+int ensure_pinned(aog_env* env, size_t bytes) {
+  if (bytes <= env->h_pinned_cap) return AOG_OK;
+  if (env->h_pinned) cudaFreeHost(env->h_pinned);
+  env->h_pinned = nullptr;
+  env->h_pinned_cap = 0;
+  AOG_CUDA(cudaMallocHost(&env->h_pinned, bytes));
+  env->h_pinned_cap = bytes;
+  return AOG_OK;
+}
+
+bool tables_ready(aog_env* env) {
+  static const int need[] = {AOG_TABLE_APERTURE, AOG_TABLE_DM_MODES, AOG_TABLE_DM_GRAM, AOG_TABLE_MFT_FIB_1,
+                             AOG_TABLE_MFT_FIB_2, AOG_TABLE_MFT_OBS_1, AOG_TABLE_MFT_OBS_2, AOG_TABLE_LP_MODES_W,
+                             AOG_TABLE_LP_PHASE, AOG_TABLE_LP_GRAM};
+  for (int t : need)
+    if (!env->have[t]) { env->err = "table " + std::to_string(t) + " not set"; return false; }
+  if (env->cfg.atm_type == AOG_ATM_DYNAMIC && env->cfg.velocity != 0.0)
+    for (int t : {AOG_TABLE_AR_STENCIL, AOG_TABLE_AR_A, AOG_TABLE_AR_B})
+      if (!env->have[t]) { env->err = "AR table " + std::to_string(t) + " not set"; return false; }
+  return true;
+}
+
+int64_t center_px(const aog_env* env, int64_t timestep) {
+  // hcipy evolve_until: round(velocity * t / delta), np.round = round-half-even
+  const double t = (double)timestep * env->cfg.delta_t;
+  const double c = env->cfg.velocity * t;
+  return (int64_t)std::nearbyint(c / env->cfg.pupil_delta);
+}
+
+// ---- one column extrusion for all envs -------------------------------------------------
+int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long noise_stride, cudaStream_t st) {
+  const aog_config& c = env->cfg;
+  const int Np = c.num_pupil_pixels, Ns = c.num_stencil, B = c.num_envs;
+  const int flipped = positive ? 1 : 0;   // +x drift = hcipy 'right' = extrude on the rotated screen
+  const int org = (int)env->cnt.column_origin;
+  const int phys = positive ? org : (org - 1 + Np) % Np;
+  for (int e0 = 0; e0 < B; e0 += env->chunk) {
+    const int nB = std::min(env->chunk, B - e0);
+    dim3 g1(cdiv(Ns + Np, 256), nB);
+    k_ar_gather<<<g1, 256, 0, st>>>(env->screens, env->t_stencil, noise_dev, env->arZ, env->P, Np, Ns, e0, org,
+                                    flipped, c.sqrt_cn2, noise_stride, c.seed, (unsigned long long)c.env_id_base,
+                                    (unsigned long long)env->cnt.extrusions);
+    AOG_LAUNCH_CHECK();
+    dim3 g2(cdiv(Np, 64), cdiv(nB, 64));
+    k_dgemm<<<g2, 256, 0, st>>>(env->arZ, env->t_arW, env->arNew, nB, Np, Ns + Np, Ns + Np, Np, Np);
+    AOG_LAUNCH_CHECK();
+    dim3 g3(cdiv(Np, 128), nB);
+    k_ar_scatter<<<g3, 128, 0, st>>>(env->screens, env->arNew, env->P, Np, e0, phys, flipped);
+    AOG_LAUNCH_CHECK();
+  }
+  env->cnt.column_origin = positive ? (org + 1) % Np : phys;
+  env->cnt.extrusions++;
+  return AOG_OK;
+}
+
+int evolve_to(aog_env* env, int64_t new_timestep, int64_t old_timestep, const double* noise_dev, cudaStream_t st) {
+  if (env->cfg.velocity == 0.0) return AOG_OK;
+  const int64_t d = center_px(env, new_timestep) - center_px(env, old_timestep);
+  const int Np = env->cfg.num_pupil_pixels;
+  const int64_t n = d < 0 ? -d : d;
+  for (int64_t i = 0; i < n; ++i) {
+    const double* nz = noise_dev ? noise_dev + (size_t)i * Np : nullptr;
+    int rc = extrude_once(env, d > 0, nz, (long long)n * Np, st);
+    if (rc) return rc;
+  }
+  return AOG_OK;
+}
+
+// ---- optics chain for one chunk (FP64 path) ---------------------------------------------
+int optics_chunk_f64(aog_env* env, int e0, int nB, bool flat_dm, bool with_reward, const aog_outputs& out,
+                     cudaStream_t st) {
+  const aog_config& c = env->cfg;
+  const int Np = c.num_pupil_pixels, Nf = c.num_focal_pixels, n = c.obs_dim, K = c.num_modes, J = c.num_lp_modes;
+  const int P = env->P;
+  const bool strehl = with_reward && c.rew_type == AOG_REW_STREHL_RATIO;
+  constexpr int ET = 4;
+  {
+    dim3 g(env->strehl_blocks, cdiv(nB, ET));
+    k_field_f64<ET><<<g, 128, ET * K * sizeof(double), st>>>(
+        env->screens, env->act, env->t_modes, env->t_aperture, env->bufA, env->strehl_part, P, Np, K, e0, nB,
+        (int)env->cnt.column_origin, c.wavelength_wfs, c.wavelength_sci, c.amp_fiber, strehl ? 1 : 0,
+        flat_dm ? 1 : 0);
+    AOG_LAUNCH_CHECK();
+  }
+  if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev0, st)); }
+  {  // T = M1 . E    [Nf x Np] . [Np x Np]
+    dim3 g(cdiv(Np, 64), cdiv(Nf, 64), nB);
+    k_zgemm<<<g, 256, 0, st>>>(env->t_m1f, env->bufA, env->bufB, Nf, Np, Np, Np, Np, Np, 0, (long long)P,
+                               (long long)Nf * Np);
+    AOG_LAUNCH_CHECK();
+  }
+  {  // F = T . M2    [Nf x Np] . [Np x Nf]
+    dim3 g(cdiv(Nf, 64), cdiv(Nf, 64), nB);
+    k_zgemm<<<g, 256, 0, st>>>(env->bufB, env->t_m2f, env->bufC, Nf, Nf, Np, Np, Nf, Nf, (long long)Nf * Np, 0,
+                               (long long)env->NF2);
+    AOG_LAUNCH_CHECK();
+  }
+  if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev1, st)); env->ev_valid = true; }
+  const double2 norm = make_double2(c.mft_norm_re, c.mft_norm_im);
+  if (with_reward) {
+    k_fiber_f64<<<nB, 256, 0, st>>>(env->bufC, env->t_lpw, env->coef, env->NF2, J, (long long)env->NF2, norm);
+    AOG_LAUNCH_CHECK();
+  }
+  {
+    dim3 g(cdiv(Np, 8), nB);
+    k_obs_rows_f64<<<g, 256, 0, st>>>(env->bufA, env->t_m2o, env->bufR, Np, n, P);
+    AOG_LAUNCH_CHECK();
+  }
+  FinalizeArgs a{};
+  a.R = env->bufR; a.m1o = env->t_m1o; a.coef = env->coef; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
+  a.strehl_part = env->strehl_part; a.strehl_blocks = env->strehl_blocks;
+  a.Np = Np; a.n = n; a.J = J; a.rew_type = c.rew_type; a.has_thr = c.has_rew_threshold;
+  a.compute_reward = with_reward ? 1 : 0;
+  a.thr = c.rew_threshold; a.obs_weight = c.obs_weight; a.strehl_scale = c.strehl_scale; a.ssim_peak = c.ssim_ref_peak;
+  a.norm = norm;
+  const size_t n2 = (size_t)env->n2;
+  a.obs16 = out.obs_f16 ? out.obs_f16 + (size_t)e0 * n2 : nullptr;
+  a.obs64 = out.obs_f64 ? out.obs_f64 + (size_t)e0 * n2 : nullptr;
+  a.reward = out.reward ? out.reward + e0 : nullptr;
+  a.power = out.power ? out.power + e0 : nullptr;
+  a.strehl = out.strehl ? out.strehl + e0 : nullptr;
+  a.ssim = out.ssim ? out.ssim + e0 : nullptr;
+  k_finalize<<<nB, 64, 0, st>>>(a);
+  AOG_LAUNCH_CHECK();
+  return AOG_OK;
+}
+
+int optics_all(aog_env* env, bool flat_dm, bool with_reward, const aog_outputs& out, cudaStream_t st) {
+  const int B = env->cfg.num_envs;
+  if (env->cfg.precision == AOG_PRECISION_TENSOR) return aog_tensor_optics(env, flat_dm, with_reward, out, st);
+  for (int e0 = 0; e0 < B; e0 += env->chunk) {
+    int rc = optics_chunk_f64(env, e0, std::min(env->chunk, B - e0), flat_dm, with_reward, out, st);
+    if (rc) return rc;
+  }
+  return AOG_OK;
+}
+
+int alloc_host_outputs(aog_env* env) {
+  const size_t B = env->cfg.num_envs, n2 = env->n2;
+  if (env->o_obs16) return AOG_OK;
+  int rc;
+  if ((rc = dev_alloc(env, &env->o_obs16, B * n2))) return rc;
+  if ((rc = dev_alloc(env, &env->o_obs64, B * n2))) return rc;
+  if ((rc = dev_alloc(env, &env->o_reward, B))) return rc;
+  if ((rc = dev_alloc(env, &env->o_power, B))) return rc;
+  if ((rc = dev_alloc(env, &env->o_strehl, B))) return rc;
+  if ((rc = dev_alloc(env, &env->o_ssim, B))) return rc;
+  AOG_CUDA(cudaMemset(env->o_strehl, 0, B * sizeof(double)));
+  AOG_CUDA(cudaMemset(env->o_ssim, 0, B * sizeof(double)));
+  return AOG_OK;
+}
+
+// D2H of the outputs the caller asked for, through one pinned staging block.
+int copy_outputs_to_host(aog_env* env, const aog_outputs* out, cudaStream_t st) {
+  const size_t B = env->cfg.num_envs, n2 = env->n2;
+  if (!out) { AOG_CUDA(cudaStreamSynchronize(st)); return AOG_OK; }
+  const size_t bytes = B * n2 * (sizeof(uint16_t) + sizeof(double)) + 4 * B * sizeof(double) + 64;
+  int rc = ensure_pinned(env, bytes);
+  if (rc) return rc;
+  char* h = (char*)env->h_pinned;
+  size_t off = 0;
+  struct Item { void* dst; const void* src; size_t bytes; size_t off; };
+  std::vector<Item> items;
+  auto add = [&](void* dst, const void* src, size_t b) {
+    if (!dst) return;
+    items.push_back({dst, src, b, off});
+    off += (b + 15) & ~size_t(15);
+  };
+  add(out->obs_f64, env->o_obs64, B * n2 * sizeof(double));
+  add(out->reward, env->o_reward, B * sizeof(double));
+  add(out->power, env->o_power, B * sizeof(double));
+  add(out->strehl, env->o_strehl, B * sizeof(double));
+  add(out->ssim, env->o_ssim, B * sizeof(double));
+  add(out->obs_f16, env->o_obs16, B * n2 * sizeof(uint16_t));
+  for (auto& it : items) AOG_CUDA(cudaMemcpyAsync(h + it.off, it.src, it.bytes, cudaMemcpyDeviceToHost, st));
+  AOG_CUDA(cudaStreamSynchronize(st));
+  for (auto& it : items) std::memcpy(it.dst, h + it.off, it.bytes);
+  return AOG_OK;
+}
+
+aog_outputs device_outputs(aog_env* env) {
+  aog_outputs o{};
+  o.obs_f16 = env->o_obs16; o.obs_f64 = env->o_obs64; o.reward = env->o_reward; o.power = env->o_power;
+  o.strehl = env->o_strehl; o.ssim = env->o_ssim;
+  return o;
+}
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" {
+
+const char* aog_version(void) { return "aogym-b200 0.1 (sm_100a)"; }
+
+const char* aog_last_error(const aog_env* env) { return env ? env->err.c_str() : "null handle"; }
+
+int aog_create(const aog_config* cfg, aog_env** out) {
+  if (!cfg || !out) return AOG_ERR_INVALID;
+  *out = nullptr;
+  aog_env* env = new (std::nothrow) aog_env();
+  if (!env) return AOG_ERR_INVALID;
+  *out = env;   // returned even on failure so the caller can read aog_last_error, then destroy
+  env->cfg = *cfg;
+  const aog_config& c = env->cfg;
+  if (c.abi_version != AOG_ABI_VERSION) AOG_FAIL(AOG_ERR_INVALID, "abi_version mismatch");
+  if (c.num_envs < 1 || c.num_pupil_pixels < 8 || c.num_focal_pixels < 8 || c.num_modes < 1)
+    AOG_FAIL(AOG_ERR_INVALID, "bad sizes");
+  if (c.obs_dim < 1 || c.obs_dim > AOG_MAX_OBS) AOG_FAIL(AOG_ERR_INVALID, "obs_dim must be in [1, 16]");
+  if (c.num_lp_modes < 1 || c.num_lp_modes > AOG_MAX_LP) AOG_FAIL(AOG_ERR_INVALID, "num_lp_modes must be in [1, 8]");
+  if (c.rew_type == AOG_REW_SMF_SSIM && c.obs_dim * c.obs_dim < 7)
+    AOG_FAIL(AOG_ERR_INVALID, "smf_ssim needs obs_dim^2 >= 7 (SSIM window)");
+  int ndev = 0;
+  AOG_CUDA(cudaGetDeviceCount(&ndev));
+  if (c.device < 0 || c.device >= ndev) AOG_FAIL(AOG_ERR_INVALID, "no such CUDA device");
+  AOG_CUDA(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  AOG_CUDA(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10) AOG_FAIL(AOG_ERR_UNSUPPORTED, "libaogym is built for sm_100a (Blackwell B200) only");
+  const int Np = c.num_pupil_pixels, Nf = c.num_focal_pixels, K = c.num_modes, J = c.num_lp_modes, n = c.obs_dim;
+  env->P = Np * Np;
+  env->NF2 = Nf * Nf;
+  env->n2 = n * n;
+  const size_t P = env->P, B = c.num_envs;
+  int rc;
+#define A(expr) if ((rc = (expr))) return rc
+  A(dev_alloc(env, &env->t_aperture, P));
+  A(dev_alloc(env, &env->t_modes, (size_t)K * P));
+  A(dev_alloc(env, &env->t_gram, (size_t)K * K));
+  A(dev_alloc(env, &env->t_m1f, (size_t)Nf * Np));
+  A(dev_alloc(env, &env->t_m2f, (size_t)Np * Nf));
+  A(dev_alloc(env, &env->t_m1o, (size_t)n * Np));
+  A(dev_alloc(env, &env->t_m2o, (size_t)Np * n));
+  A(dev_alloc(env, &env->t_lpw, (size_t)J * env->NF2));
+  A(dev_alloc(env, &env->t_lpphase, (size_t)J));
+  A(dev_alloc(env, &env->t_lpgram, (size_t)J * J));
+  if (c.num_stencil > 0) {
+    A(dev_alloc(env, &env->t_stencil, (size_t)c.num_stencil));
+    A(dev_alloc(env, &env->t_arA, (size_t)Np * c.num_stencil));
+    A(dev_alloc(env, &env->t_arB, (size_t)Np * Np));
+    A(dev_alloc(env, &env->t_arW, (size_t)(c.num_stencil + Np) * Np));
+  }
+  if (c.num_screen_fine > 0) {
+    const size_t N2 = c.num_screen_fine;
+    A(dev_alloc(env, &env->t_scrC1, P));
+    A(dev_alloc(env, &env->t_scrW1, P));
+    A(dev_alloc(env, &env->t_scrW1T, P));
+    A(dev_alloc(env, &env->t_scrC2, N2 * N2));
+    A(dev_alloc(env, &env->t_scrW2, (size_t)Np * N2));
+    A(dev_alloc(env, &env->t_scrW2T, (size_t)Np * N2));
+  }
+  A(dev_alloc(env, &env->screens, B * P));
+  AOG_CUDA(cudaMemset(env->screens, 0, B * P * sizeof(double)));
+  A(dev_alloc(env, &env->act, B * K));
+  AOG_CUDA(cudaMemset(env->act, 0, B * K * sizeof(double)));
+  A(dev_alloc(env, (double**)&env->act_in, B * K));
+  env->chunk = (int)std::min<size_t>(B, 4096);
+  env->strehl_blocks = cdiv(env->P, 128);
+  const size_t ch = env->chunk;
+  if (c.precision == AOG_PRECISION_F64 || c.num_screen_fine > 0) {
+    A(dev_alloc(env, &env->bufA, ch * P));
+    A(dev_alloc(env, &env->bufB, ch * (size_t)Np * std::max(Nf, Np)));
+    A(dev_alloc(env, &env->bufC, ch * std::max<size_t>(env->NF2, P)));
+  }
+  A(dev_alloc(env, &env->bufR, ch * (size_t)Np * n));
+  A(dev_alloc(env, &env->coef, ch * (size_t)J));
+  A(dev_alloc(env, &env->strehl_part, ch * (size_t)env->strehl_blocks));
+  if (c.num_stencil > 0) {
+    A(dev_alloc(env, &env->arZ, ch * (size_t)(c.num_stencil + Np)));
+    A(dev_alloc(env, &env->arNew, ch * (size_t)Np));
+  }
+  A(alloc_host_outputs(env));
+  if (c.precision == AOG_PRECISION_TENSOR) A(aog_tensor_create(env));
+#undef A
+  AOG_CUDA(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
+  AOG_CUDA(cudaEventCreate(&env->ev0));
+  AOG_CUDA(cudaEventCreate(&env->ev1));
+  return AOG_OK;
+}
+
+void aog_destroy(aog_env* env) {
+  if (!env) return;
+  cudaSetDevice(env->cfg.device);
+  cudaDeviceSynchronize();
+  aog_tensor_destroy(env);
+  void* ptrs[] = {env->t_aperture, env->t_modes, env->t_gram, env->t_m1f, env->t_m2f, env->t_m1o, env->t_m2o,
+                  env->t_lpw, env->t_lpphase, env->t_lpgram, env->t_stencil, env->t_arA, env->t_arB, env->t_arW,
+                  env->t_scrC1, env->t_scrW1, env->t_scrW1T, env->t_scrC2, env->t_scrW2, env->t_scrW2T,
+                  env->screens, env->act, env->bufA, env->bufB, env->bufC, env->bufR, env->coef,
+                  env->strehl_part, env->arZ, env->arNew, env->act_in, env->noise_in, env->o_obs16, env->o_obs64,
+                  env->o_reward, env->o_power, env->o_strehl, env->o_ssim};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (env->h_pinned) cudaFreeHost(env->h_pinned);
+  if (env->own_stream) cudaStreamDestroy(env->own_stream);
+  if (env->ev0) cudaEventDestroy(env->ev0);
+  if (env->ev1) cudaEventDestroy(env->ev1);
+  delete env;
+}
+
+int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
+  if (!env || !host) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  AOG_CUDA(cudaSetDevice(c.device));
+  const size_t Np = c.num_pupil_pixels, Nf = c.num_focal_pixels, K = c.num_modes, J = c.num_lp_modes, n = c.obs_dim;
+  const size_t P = env->P, Ns = c.num_stencil, N2 = c.num_screen_fine;
+  void* dst = nullptr;
+  size_t want = 0, esz = sizeof(double);
+  switch (which) {
+    case AOG_TABLE_APERTURE: dst = env->t_aperture; want = P; break;
+    case AOG_TABLE_DM_MODES: dst = env->t_modes; want = K * P; break;
+    case AOG_TABLE_DM_GRAM: dst = env->t_gram; want = K * K; break;
+    case AOG_TABLE_MFT_FIB_1: dst = env->t_m1f; want = Nf * Np; esz = sizeof(double2); break;
+    case AOG_TABLE_MFT_FIB_2: dst = env->t_m2f; want = Np * Nf; esz = sizeof(double2); break;
+    case AOG_TABLE_MFT_OBS_1: dst = env->t_m1o; want = n * Np; esz = sizeof(double2); break;
+    case AOG_TABLE_MFT_OBS_2: dst = env->t_m2o; want = Np * n; esz = sizeof(double2); break;
+    case AOG_TABLE_LP_MODES_W: dst = env->t_lpw; want = J * env->NF2; break;
+    case AOG_TABLE_LP_PHASE: dst = env->t_lpphase; want = J; esz = sizeof(double2); break;
+    case AOG_TABLE_LP_GRAM: dst = env->t_lpgram; want = J * J; break;
+    case AOG_TABLE_AR_STENCIL: dst = env->t_stencil; want = Ns; esz = sizeof(int32_t); break;
+    case AOG_TABLE_AR_A: dst = env->t_arA; want = Np * Ns; break;
+    case AOG_TABLE_AR_B: dst = env->t_arB; want = Np * Np; break;
+    case AOG_TABLE_SCR_C1: dst = env->t_scrC1; want = P; break;
+    case AOG_TABLE_SCR_W1: dst = env->t_scrW1; want = P; esz = sizeof(double2); break;
+    case AOG_TABLE_SCR_C2: dst = env->t_scrC2; want = N2 * N2; break;
+    case AOG_TABLE_SCR_W2: dst = env->t_scrW2; want = Np * N2; esz = sizeof(double2); break;
+    default: AOG_FAIL(AOG_ERR_INVALID, "unknown table id");
+  }
+  if (!dst || want == 0) AOG_FAIL(AOG_ERR_INVALID, "table not configured for this handle");
+  if (count != want)
+    AOG_FAIL(AOG_ERR_INVALID, "table " + std::to_string(which) + ": expected " + std::to_string(want) +
+                                  " elements, got " + std::to_string(count));
+  AOG_CUDA(cudaMemcpy(dst, host, want * esz, cudaMemcpyHostToDevice));
+  env->have[which] = true;
+  if ((which == AOG_TABLE_AR_A || which == AOG_TABLE_AR_B) && env->have[AOG_TABLE_AR_A] && env->have[AOG_TABLE_AR_B]) {
+    const int tot = (int)((Ns + Np) * Np);
+    k_build_arW<<<cdiv(tot, 256), 256>>>(env->t_arA, env->t_arB, env->t_arW, (int)Np, (int)Ns);
+    AOG_LAUNCH_CHECK();
+  }
+  if (which == AOG_TABLE_SCR_W1) {
+    k_transpose_z<<<cdiv((int)P, 256), 256>>>(env->t_scrW1, env->t_scrW1T, (int)Np, (int)Np);
+    AOG_LAUNCH_CHECK();
+  }
+  if (which == AOG_TABLE_SCR_W2) {
+    k_transpose_z<<<cdiv((int)(Np * N2), 256), 256>>>(env->t_scrW2, env->t_scrW2T, (int)Np, (int)N2);
+    AOG_LAUNCH_CHECK();
+  }
+  if (c.precision == AOG_PRECISION_TENSOR) {
+    int rc = aog_tensor_table_updated(env, which, host);
+    if (rc) return rc;
+  }
+  AOG_CUDA(cudaDeviceSynchronize());
+  return AOG_OK;
+}
+
+int aog_set_screens(aog_env* env, const void* src, int dtype, int src_on_device, int first_env, int count) {
+  if (!env || !src) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  if (first_env < 0 || count < 1 || first_env + count > c.num_envs) AOG_FAIL(AOG_ERR_INVALID, "env range");
+  AOG_CUDA(cudaSetDevice(c.device));
+  const size_t nel = (size_t)count * env->P;
+  double* dst = env->screens + (size_t)first_env * env->P;
+  if (env->cnt.column_origin != 0) AOG_FAIL(AOG_ERR_STATE, "set_screens after extrusions: reset counters first");
+  if (dtype == AOG_DTYPE_F64) {
+    AOG_CUDA(cudaMemcpy(dst, src, nel * sizeof(double), src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  } else if (dtype == AOG_DTYPE_F32) {
+    const float* s = (const float*)src;
+    float* tmp = nullptr;
+    if (!src_on_device) {
+      AOG_CUDA(cudaMalloc((void**)&tmp, nel * sizeof(float)));
+      cudaError_t e = cudaMemcpy(tmp, src, nel * sizeof(float), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { cudaFree(tmp); env->err = cudaGetErrorString(e); return AOG_ERR_CUDA; }
+      s = tmp;
+    }
+    k_f32_to_f64<<<(unsigned)((nel + 255) / 256), 256>>>(s, dst, nel);
+    env->launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (tmp) cudaFree(tmp);
+    if (e != cudaSuccess) { env->err = cudaGetErrorString(e); return AOG_ERR_CUDA; }
+  } else {
+    AOG_FAIL(AOG_ERR_INVALID, "dtype");
+  }
+  if (c.precision == AOG_PRECISION_TENSOR) return aog_tensor_screens_updated(env);
+  return AOG_OK;
+}
+
+int aog_get_screens(aog_env* env, double* host_out, int first_env, int count) {
+  if (!env || !host_out) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  if (first_env < 0 || count < 1 || first_env + count > c.num_envs) AOG_FAIL(AOG_ERR_INVALID, "env range");
+  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_CUDA(cudaDeviceSynchronize());
+  const int Np = c.num_pupil_pixels, org = (int)env->cnt.column_origin;
+  std::vector<double> tmp((size_t)count * env->P);
+  AOG_CUDA(cudaMemcpy(tmp.data(), env->screens + (size_t)first_env * env->P, tmp.size() * sizeof(double),
+                      cudaMemcpyDeviceToHost));
+  for (int b = 0; b < count; ++b)
+    for (int y = 0; y < Np; ++y)
+      for (int x = 0; x < Np; ++x)
+        host_out[(size_t)b * env->P + (size_t)y * Np + x] = tmp[(size_t)b * env->P + (size_t)y * Np + (x + org) % Np];
+  return AOG_OK;
+}
+
+int aog_generate_screens(aog_env* env, void* stream) {
+  if (!env) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  if (c.num_screen_fine <= 0 || !env->have[AOG_TABLE_SCR_C1] || !env->have[AOG_TABLE_SCR_W1] ||
+      !env->have[AOG_TABLE_SCR_C2] || !env->have[AOG_TABLE_SCR_W2])
+    AOG_FAIL(AOG_ERR_STATE, "screen synthesis tables not set");
+  AOG_CUDA(cudaSetDevice(c.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : env->own_stream;
+  const int Np = c.num_pupil_pixels, N2 = c.num_screen_fine, P = env->P, B = c.num_envs;
+  // independent Philox domain from the extrusion noise: offset the seed
+  const unsigned long long seed = c.seed ^ 0x9E3779B97F4A7C15ull;
+  const unsigned long long per = (unsigned long long)P + (unsigned long long)N2 * N2;
+  const unsigned long long base = (unsigned long long)env->cnt.episode_no * per;
+  const long long sB = (long long)Np * std::max(c.num_focal_pixels, Np);
+  const long long sC = (long long)std::max<size_t>(env->NF2, P);
+  for (int e0 = 0; e0 < B; e0 += env->chunk) {
+    const int nB = std::min(env->chunk, B - e0);
+    // scale 1: X1 [Np x Np] -> W1 X1 W1^T
+    k_scr_noise<<<dim3(cdiv(P, 256), nB), 256, 0, st>>>(env->t_scrC1, env->bufA, P, (long long)P, e0, seed,
+                                                        (unsigned long long)c.env_id_base, base);
+    AOG_LAUNCH_CHECK();
+    k_zgemm<<<dim3(cdiv(Np, 64), cdiv(Np, 64), nB), 256, 0, st>>>(env->t_scrW1, env->bufA, env->bufB, Np, Np, Np, Np,
+                                                                   Np, Np, 0, (long long)P, sB);
+    AOG_LAUNCH_CHECK();
+    k_zgemm<<<dim3(cdiv(Np, 64), cdiv(Np, 64), nB), 256, 0, st>>>(env->bufB, env->t_scrW1T, env->bufC, Np, Np, Np, Np,
+                                                                   Np, Np, sB, 0, sC);
+    AOG_LAUNCH_CHECK();
+    k_scr_combine<<<dim3(cdiv(P, 256), nB), 256, 0, st>>>(env->screens, env->bufC, P, sC, e0, c.sqrt_cn2, 0);
+    AOG_LAUNCH_CHECK();
+    // scale 2: X2 [N2 x N2] -> W2 X2 W2^T
+    k_scr_noise<<<dim3(cdiv(N2 * N2, 256), nB), 256, 0, st>>>(env->t_scrC2, env->bufA, N2 * N2, (long long)P, e0, seed,
+                                                              (unsigned long long)c.env_id_base, base + P);
+    AOG_LAUNCH_CHECK();
+    k_zgemm<<<dim3(cdiv(N2, 64), cdiv(Np, 64), nB), 256, 0, st>>>(env->t_scrW2, env->bufA, env->bufB, Np, N2, N2, N2,
+                                                                   N2, N2, 0, (long long)P, sB);
+    AOG_LAUNCH_CHECK();
+    k_zgemm<<<dim3(cdiv(Np, 64), cdiv(Np, 64), nB), 256, 0, st>>>(env->bufB, env->t_scrW2T, env->bufC, Np, Np, N2, N2,
+                                                                   Np, Np, sB, 0, sC);
+    AOG_LAUNCH_CHECK();
+    k_scr_combine<<<dim3(cdiv(P, 256), nB), 256, 0, st>>>(env->screens, env->bufC, P, sC, e0, c.sqrt_cn2, 1);
+    AOG_LAUNCH_CHECK();
+  }
+  env->cnt.column_origin = 0;
+  if (c.precision == AOG_PRECISION_TENSOR) return aog_tensor_screens_updated(env);
+  return AOG_OK;
+}
+
+int aog_next_extrusions(const aog_env* env) {
+  if (!env) return AOG_ERR_INVALID;
+  if (env->cfg.velocity == 0.0) return 0;
+  const int64_t d = center_px(env, env->cnt.timestep + 1) - center_px(env, env->cnt.timestep);
+  return (int)(d < 0 ? -d : d);
+}
+
+int aog_reset(aog_env* env, const aog_outputs* out_dev, void* stream) {
+  if (!env) return AOG_ERR_INVALID;
+  if (!tables_ready(env)) return AOG_ERR_STATE;
+  const aog_config& c = env->cfg;
+  AOG_CUDA(cudaSetDevice(c.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : env->own_stream;
+  int rc;
+  // AO_env.py:76-77 -- semi_dynamic draws a fresh screen per episode
+  if (c.atm_type == AOG_ATM_SEMI_DYNAMIC && c.num_screen_fine > 0)
+    if ((rc = aog_generate_screens(env, st))) return rc;
+  // AO_env.py:79-80
+  if (c.flat_mirror_start) AOG_CUDA(cudaMemsetAsync(env->act, 0, (size_t)c.num_envs * c.num_modes * sizeof(double), st));
+  env->cnt.timestep_render = 0;           // AO_env.py:83
+  // AO_env.py:84: layer.t = timestep * delta_t -- same time as the last step: no extrusion
+  aog_outputs o{};
+  if (out_dev) o = *out_dev;
+  o.reward = nullptr; o.power = nullptr; o.strehl = nullptr; o.ssim = nullptr;
+  return optics_all(env, false, false, o, st);
+}
+
+int aog_reset_host(aog_env* env, const aog_outputs* out_host) {
+  if (!env) return AOG_ERR_INVALID;
+  aog_outputs d = device_outputs(env);
+  int rc = aog_reset(env, &d, env->own_stream);
+  if (rc) return rc;
+  aog_outputs h{};
+  if (out_host) { h.obs_f16 = out_host->obs_f16; h.obs_f64 = out_host->obs_f64; }
+  return copy_outputs_to_host(env, &h, env->own_stream);
+}
+
+int aog_step(aog_env* env, const void* actions_dev, int act_dtype, const double* noise_dev,
+             const aog_outputs* out_dev, int32_t* done_out, void* stream) {
+  if (!env || !actions_dev) return AOG_ERR_INVALID;
+  if (!tables_ready(env)) return AOG_ERR_STATE;
+  const aog_config& c = env->cfg;
+  AOG_CUDA(cudaSetDevice(c.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : env->own_stream;
+  const int B = c.num_envs, K = c.num_modes;
+  // AO_env.py:115-120
+  const size_t shm = (size_t)(K + 32) * sizeof(double);
+  const double target = 0.1 * c.wavelength_sci;
+  if (act_dtype == AOG_DTYPE_F32)
+    k_actuators<float><<<B, 128, shm, st>>>((const float*)actions_dev, env->t_gram, env->act, K, c.sh_operation, target);
+  else if (act_dtype == AOG_DTYPE_F64)
+    k_actuators<double><<<B, 128, shm, st>>>((const double*)actions_dev, env->t_gram, env->act, K, c.sh_operation, target);
+  else
+    AOG_FAIL(AOG_ERR_INVALID, "act_dtype");
+  AOG_LAUNCH_CHECK();
+  // AO_env.py:123-125
+  const int64_t old_t = env->cnt.timestep;
+  env->cnt.timestep += 1;
+  env->cnt.timestep_render += 1;
+  int rc = evolve_to(env, env->cnt.timestep, old_t, noise_dev, st);
+  if (rc) return rc;
+  // AO_env.py:132-144
+  aog_outputs o{};
+  if (out_dev) o = *out_dev;
+  rc = optics_all(env, false, true, o, st);
+  if (rc) return rc;
+  // AO_env.py:147-151
+  int done = 0;
+  if (env->cnt.timestep_render == c.max_steps) { done = 1; env->cnt.episode_no += 1; }
+  if (done_out) *done_out = done;
+  return AOG_OK;
+}
+
+int aog_step_host(aog_env* env, const void* actions_host, int act_dtype, const double* noise_host,
+                  const aog_outputs* out_host, int32_t* done_out) {
+  if (!env || !actions_host) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  AOG_CUDA(cudaSetDevice(c.device));
+  cudaStream_t st = env->own_stream;
+  const size_t esz = act_dtype == AOG_DTYPE_F32 ? sizeof(float) : sizeof(double);
+  const size_t abytes = (size_t)c.num_envs * c.num_modes * esz;
+  AOG_CUDA(cudaMemcpyAsync(env->act_in, actions_host, abytes, cudaMemcpyHostToDevice, st));
+  const double* nz = nullptr;
+  if (noise_host) {
+    const int n_ext = aog_next_extrusions(env);
+    const size_t cnt = (size_t)c.num_envs * n_ext * c.num_pupil_pixels;
+    if (cnt > 0) {
+      if (cnt > env->noise_in_cap) {
+        int rc = dev_alloc(env, &env->noise_in, cnt);
+        if (rc) return rc;
+        env->noise_in_cap = cnt;
+      }
+      AOG_CUDA(cudaMemcpyAsync(env->noise_in, noise_host, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+      nz = env->noise_in;
+    }
+  }
+  aog_outputs d = device_outputs(env);
+  int rc = aog_step(env, env->act_in, act_dtype, nz, &d, done_out, st);
+  if (rc) return rc;
+  return copy_outputs_to_host(env, out_host, st);
+}
+
+int aog_get_counters(const aog_env* env, aog_counters* out) {
+  if (!env || !out) return AOG_ERR_INVALID;
+  *out = env->cnt;
+  return AOG_OK;
+}
+
+int aog_set_counters(aog_env* env, const aog_counters* in) {
+  if (!env || !in) return AOG_ERR_INVALID;
+  env->cnt = *in;
+  return AOG_OK;
+}
+
+int aog_get_actuators(aog_env* env, double* host_out) {
+  if (!env || !host_out) return AOG_ERR_INVALID;
+  AOG_CUDA(cudaSetDevice(env->cfg.device));
+  AOG_CUDA(cudaDeviceSynchronize());
+  AOG_CUDA(cudaMemcpy(host_out, env->act, (size_t)env->cfg.num_envs * env->cfg.num_modes * sizeof(double),
+                      cudaMemcpyDeviceToHost));
+  return AOG_OK;
+}
+
+int aog_set_actuators(aog_env* env, const double* host_in) {
+  if (!env || !host_in) return AOG_ERR_INVALID;
+  AOG_CUDA(cudaSetDevice(env->cfg.device));
+  AOG_CUDA(cudaDeviceSynchronize());
+  AOG_CUDA(cudaMemcpy(env->act, host_in, (size_t)env->cfg.num_envs * env->cfg.num_modes * sizeof(double),
+                      cudaMemcpyHostToDevice));
+  return AOG_OK;
+}
+
+int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size_t count) {
+  if (!env || !host_out) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  if (env_index < 0 || env_index >= c.num_envs) AOG_FAIL(AOG_ERR_INVALID, "env_index");
+  if (!tables_ready(env)) return AOG_ERR_STATE;
+  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_CUDA(cudaDeviceSynchronize());
+  const size_t P = env->P;
+  if (which == AOG_FIELD_SCREEN) {
+    if (count != P) AOG_FAIL(AOG_ERR_INVALID, "count");
+    return aog_get_screens(env, host_out, env_index, 1);
+  }
+  if (which == AOG_FIELD_ACTUATORS) {
+    if (count != (size_t)c.num_modes) AOG_FAIL(AOG_ERR_INVALID, "count");
+    AOG_CUDA(cudaMemcpy(host_out, env->act + (size_t)env_index * c.num_modes, count * sizeof(double),
+                        cudaMemcpyDeviceToHost));
+    return AOG_OK;
+  }
+  // optical fields: recompute the FP64 chain for that one env from the current state
+  if (!env->bufA) {
+    int rc;
+    const size_t ch = env->chunk;
+    if ((rc = dev_alloc(env, &env->bufA, ch * P))) return rc;
+    if ((rc = dev_alloc(env, &env->bufB, ch * (size_t)c.num_pupil_pixels * std::max(c.num_focal_pixels, c.num_pupil_pixels)))) return rc;
+    if ((rc = dev_alloc(env, &env->bufC, ch * std::max<size_t>(env->NF2, P)))) return rc;
+  }
+  aog_outputs d = device_outputs(env);
+  aog_outputs none{};
+  none.obs_f64 = d.obs_f64;   // optics_chunk_f64 applies the env offset itself
+  const bool timing = env->timing;
+  env->timing = false;
+  int rc = optics_chunk_f64(env, env_index, 1, false, false, none, env->own_stream);
+  env->timing = timing;
+  if (rc) return rc;
+  AOG_CUDA(cudaStreamSynchronize(env->own_stream));
+  if (which == AOG_FIELD_PUPIL) {
+    if (count != 2 * P) AOG_FAIL(AOG_ERR_INVALID, "count");
+    AOG_CUDA(cudaMemcpy(host_out, env->bufA, count * sizeof(double), cudaMemcpyDeviceToHost));
+  } else if (which == AOG_FIELD_FOCAL || which == AOG_FIELD_FOCAL_POWER) {
+    const size_t nf2 = env->NF2;
+    std::vector<double> f(2 * nf2);
+    AOG_CUDA(cudaMemcpy(f.data(), env->bufC, 2 * nf2 * sizeof(double), cudaMemcpyDeviceToHost));
+    const double nr = c.mft_norm_re, ni = c.mft_norm_im;
+    const double w = (c.obs_weight * c.obs_dim * c.obs_dim) / (double)nf2;   // same window, Nf^2 pixels
+    if (which == AOG_FIELD_FOCAL) {
+      if (count != 2 * nf2) AOG_FAIL(AOG_ERR_INVALID, "count");
+      for (size_t i = 0; i < nf2; ++i) {
+        host_out[2 * i] = f[2 * i] * nr - f[2 * i + 1] * ni;
+        host_out[2 * i + 1] = f[2 * i] * ni + f[2 * i + 1] * nr;
+      }
+    } else {
+      if (count != nf2) AOG_FAIL(AOG_ERR_INVALID, "count");
+      for (size_t i = 0; i < nf2; ++i) {
+        const double fr = f[2 * i] * nr - f[2 * i + 1] * ni, fi = f[2 * i] * ni + f[2 * i + 1] * nr;
+        host_out[i] = (fr * fr + fi * fi) * w;
+      }
+    }
+  } else if (which == AOG_FIELD_OBS_POWER) {
+    if (count != (size_t)env->n2) AOG_FAIL(AOG_ERR_INVALID, "count");
+    AOG_CUDA(cudaMemcpy(host_out, d.obs_f64 + (size_t)env_index * env->n2, count * sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    AOG_FAIL(AOG_ERR_INVALID, "unknown field");
+  }
+  return AOG_OK;
+}
+
+int64_t aog_launch_count(const aog_env* env) { return env ? env->launches : -1; }
+
+int aog_chunk_size(const aog_env* env) { return env ? env->chunk : AOG_ERR_INVALID; }
+
+int aog_set_timing(aog_env* env, int enabled) {
+  if (!env) return AOG_ERR_INVALID;
+  env->timing = enabled != 0;
+  env->ev_valid = false;
+  return AOG_OK;
+}
+
+double aog_last_mft_ms(aog_env* env) {
+  if (!env || !env->ev_valid) return -1.0;
+  if (cudaEventSynchronize(env->ev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, env->ev0, env->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Shared declarations of libaogym (sm_100a).  See include/aogym.h for the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+#include "aogym.h"
+
+#define AOG_MAX_LP 8       // guided fibre modes kept in registers (reference config: 3)
+#define AOG_MAX_OBS 16     // obs_dim upper bound (reference uses 2..5)
+
+struct aog_env {
+  aog_config cfg{};
+  int P = 0, NF2 = 0, n2 = 0;
+  std::string err;
+  bool have[AOG_TABLE_COUNT] = {};
+
+  // ---- tables (device) ----
+  double* t_aperture = nullptr;    // [P]
+  double* t_modes = nullptr;       // [K][P]
+  double* t_gram = nullptr;        // [K][K]
+  double2* t_m1f = nullptr;        // [Nf][Np]
+  double2* t_m2f = nullptr;        // [Np][Nf]
+  double2* t_m1o = nullptr;        // [n][Np]
+  double2* t_m2o = nullptr;        // [Np][n]
+  double* t_lpw = nullptr;         // [J][Nf*Nf]
+  double2* t_lpphase = nullptr;    // [J]
+  double* t_lpgram = nullptr;      // [J][J]
+  int* t_stencil = nullptr;        // [Ns]
+  double* t_arA = nullptr;         // [Np][Ns] as uploaded
+  double* t_arB = nullptr;         // [Np][Np] as uploaded
+  double* t_arW = nullptr;         // [(Ns+Np)][Np] = [A^T ; B^T]  (GEMM operand)
+  double* t_scrC1 = nullptr;       // [Np][Np]
+  double2* t_scrW1 = nullptr;      // [Np][Np]
+  double2* t_scrW1T = nullptr;     // transpose
+  double* t_scrC2 = nullptr;       // [N2][N2]
+  double2* t_scrW2 = nullptr;      // [Np][N2]
+  double2* t_scrW2T = nullptr;     // [N2][Np]
+
+  // ---- per-env state (device) ----
+  double* screens = nullptr;       // [B][P], ring-buffered along x (column_origin)
+  double* act = nullptr;           // [B][K] DM actuators (after normalisation)
+
+  // ---- scratch for one chunk of envs ----
+  int chunk = 0;
+  double2* bufA = nullptr;         // [chunk][P]              pupil field E
+  double2* bufB = nullptr;         // [chunk][Np*max(Nf,Np)]  stage-1 product T
+  double2* bufC = nullptr;         // [chunk][max(Nf*Nf,P)]   focal field F
+  double2* bufR = nullptr;         // [chunk][Np*n]           obs-arm row products
+  double2* coef = nullptr;         // [chunk][J]              fibre-mode coefficients
+  double2* strehl_part = nullptr;  // [chunk][strehl_blocks]
+  int strehl_blocks = 0;
+  double* arZ = nullptr;           // [chunk][Ns+Np]
+  double* arNew = nullptr;         // [chunk][Np]
+  void* act_in = nullptr;          // [B][K] staging of raw actions (f64-sized)
+  double* noise_in = nullptr;      // staging for injected noise
+  size_t noise_in_cap = 0;
+  // device-side outputs used by the *_host variants
+  uint16_t* o_obs16 = nullptr; double* o_obs64 = nullptr; double* o_reward = nullptr;
+  double* o_power = nullptr; double* o_strehl = nullptr; double* o_ssim = nullptr;
+  // pinned host staging
+  void* h_pinned = nullptr; size_t h_pinned_cap = 0;
+
+  // ---- counters (host; all envs run in lock-step) ----
+  aog_counters cnt{};
+  int64_t launches = 0;
+  cudaStream_t own_stream = nullptr;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+};
+
+#define AOG_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      env->err = std::string(#call) + ": " + cudaGetErrorString(_e);                    \
+      return AOG_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define AOG_FAIL(code, msg) \
+  do { env->err = (msg); return (code); } while (0)
+
+#define AOG_LAUNCH_CHECK()                                   \
+  do {                                                       \
+    env->launches++;                                         \
+    AOG_CUDA(cudaGetLastError());                            \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

@@ -1,0 +1,451 @@
+// FP64 (exact) kernels of the AO-v0 step path.  This is the guaranteed-parity arithmetic
+// (AOG_PRECISION_F64) and the on-device checker for the tensor-core path.
+#pragma once
+#include "common.cuh"
+#include <curand_kernel.h>
+
+// --------------------------------------------------------------------------------------
+// Action normalisation (reference AO_env.py:115-120):
+//   a = action / (arange(K) + 10);  a *= 0.1 lambda_sci / std(M a),  std^2 = a^T G a
+// One block per env.
+// --------------------------------------------------------------------------------------
+template <typename ActT>
+__global__ void k_actuators(const ActT* __restrict__ actions, const double* __restrict__ gram,
+                            double* __restrict__ act, int K, int sh_operation, double target_rms) {
+  extern __shared__ double sh_a[];   // [K] + [32] reduction scratch
+  double* red = sh_a + K;
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double a = (double)actions[(size_t)b * K + k];
+    sh_a[k] = sh_operation ? a : a / (double)(k + 10);
+  }
+  __syncthreads();
+  if (sh_operation) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) act[(size_t)b * K + k] = sh_a[k];
+    return;
+  }
+  double part = 0.0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    double r = 0.0;
+    for (int j = 0; j < K; ++j) r += gram[(size_t)i * K + j] * sh_a[j];
+    part += sh_a[i] * r;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const double scale = target_rms / sqrt(red[0]);   // var == 0 -> inf -> 0 * inf = NaN (reference semantics)
+  for (int k = threadIdx.x; k < K; k += blockDim.x) act[(size_t)b * K + k] = sh_a[k] * scale;
+}
+
+// --------------------------------------------------------------------------------------
+// DM surface + pupil field + Strehl partial sums (AO_env.py:132-135, 479-483):
+//   s = M a;  E = amp A exp(i (S / l_wfs + 2 s k_wfs));  sum_ap exp(i (S / l_sci + 2 s k_sci))
+// Thread = one pixel for ET envs (the mode value is loaded once and reused ET times).
+// grid (ceil(P/128), ceil(nB/ET)), block 128.
+// --------------------------------------------------------------------------------------
+template <int ET>
+__global__ void k_field_f64(const double* __restrict__ screens, const double* __restrict__ act,
+                            const double* __restrict__ modes, const double* __restrict__ aperture,
+                            double2* __restrict__ E, double2* __restrict__ strehl_part, int P, int Np, int K,
+                            int env0, int nB, int col_origin, double l_wfs, double l_sci, double amp,
+                            int do_strehl, int flat_dm) {
+  extern __shared__ double sh_act[];   // [ET][K]
+  __shared__ double2 red[ET][4];
+  const int e0 = blockIdx.y * ET;
+  for (int i = threadIdx.x; i < ET * K; i += blockDim.x) {
+    int e = i / K, k = i - e * K;
+    sh_act[i] = (e0 + e < nB && !flat_dm) ? act[(size_t)(env0 + e0 + e) * K + k] : 0.0;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = p < P;
+  double s[ET];
+#pragma unroll
+  for (int e = 0; e < ET; ++e) s[e] = 0.0;
+  if (valid && !flat_dm) {
+    for (int k = 0; k < K; ++k) {
+      const double m = modes[(size_t)k * P + p];
+#pragma unroll
+      for (int e = 0; e < ET; ++e) s[e] = fma(m, sh_act[e * K + k], s[e]);
+    }
+  }
+  const double ap = valid ? aperture[p] : 0.0;
+  int y = 0, xp = 0;
+  if (valid) {
+    y = p / Np;
+    xp = p - y * Np + col_origin;
+    if (xp >= Np) xp -= Np;
+  }
+  const double kw = 6.283185307179586476925286766559 / l_wfs;
+  const double ks = 6.283185307179586476925286766559 / l_sci;
+#pragma unroll
+  for (int e = 0; e < ET; ++e) {
+    double2 st = make_double2(0.0, 0.0);
+    if (valid && e0 + e < nB) {
+      const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)y * Np + xp];
+      double sn, cs;
+      sincos(S / l_wfs + 2.0 * s[e] * kw, &sn, &cs);
+      E[(size_t)(e0 + e) * P + p] = make_double2(amp * ap * cs, amp * ap * sn);
+      if (do_strehl) {
+        sincos(S / l_sci + 2.0 * s[e] * ks, &sn, &cs);
+        st = make_double2(ap * cs, ap * sn);
+      }
+    }
+    if (do_strehl) {
+      st.x = warp_sum(st.x);
+      st.y = warp_sum(st.y);
+      if ((threadIdx.x & 31) == 0) red[e][threadIdx.x >> 5] = st;
+    }
+  }
+  if (do_strehl) {
+    __syncthreads();
+    if (threadIdx.x < ET && e0 + threadIdx.x < nB) {
+      double2 a = red[threadIdx.x][0];
+      for (int w = 1; w < 4; ++w) { a.x += red[threadIdx.x][w].x; a.y += red[threadIdx.x][w].y; }
+      strehl_part[(size_t)(e0 + threadIdx.x) * gridDim.x + blockIdx.x] = a;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Batched complex FP64 GEMM  C[b] = A[b] (M x Kd) . B[b] (Kd x N), row-major, stride 0 = shared.
+// 64x64x16 tiles, 256 threads, 4x4 complex accumulators per thread.
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_zgemm(const double2* __restrict__ A, const double2* __restrict__ B,
+                                               double2* __restrict__ C, int M, int N, int Kd, int lda, int ldb,
+                                               int ldc, long long sA, long long sB, long long sC) {
+  __shared__ double2 As[16][65];
+  __shared__ double2 Bs[16][64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  A += (size_t)blockIdx.z * sA;
+  B += (size_t)blockIdx.z * sB;
+  C += (size_t)blockIdx.z * sC;
+  double2 acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = make_double2(0.0, 0.0);
+  const double2 zero = make_double2(0.0, 0.0);
+  for (int k0 = 0; k0 < Kd; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = threadIdx.x & 15, m = (threadIdx.x >> 4) + 16 * i;
+      As[k][m] = (m0 + m < M && k0 + k < Kd) ? A[(size_t)(m0 + m) * lda + k0 + k] : zero;
+      const int n = threadIdx.x & 63, kb = (threadIdx.x >> 6) + 4 * i;
+      Bs[kb][n] = (n0 + n < N && k0 + kb < Kd) ? B[(size_t)(k0 + kb) * ldb + n0 + n] : zero;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double2 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j].x = fma(a[i].x, b[j].x, acc[i][j].x);
+          acc[i][j].x = fma(-a[i].y, b[j].y, acc[i][j].x);
+          acc[i][j].y = fma(a[i].x, b[j].y, acc[i][j].y);
+          acc[i][j].y = fma(a[i].y, b[j].x, acc[i][j].y);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+      if (m < M && n < N) C[(size_t)m * ldc + n] = acc[i][j];
+    }
+}
+
+// Real FP64 GEMM C (M x N) = A (M x Kd) . B (Kd x N), same tiling (AR extrusion over envs).
+__global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, const double* __restrict__ B,
+                                               double* __restrict__ C, int M, int N, int Kd, int lda, int ldb,
+                                               int ldc) {
+  __shared__ double As[16][65];
+  __shared__ double Bs[16][64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < Kd; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = threadIdx.x & 15, m = (threadIdx.x >> 4) + 16 * i;
+      As[k][m] = (m0 + m < M && k0 + k < Kd) ? A[(size_t)(m0 + m) * lda + k0 + k] : 0.0;
+      const int n = threadIdx.x & 63, kb = (threadIdx.x >> 6) + 4 * i;
+      Bs[kb][n] = (n0 + n < N && k0 + kb < Kd) ? B[(size_t)(k0 + kb) * ldb + n0 + n] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+      if (m < M && n < N) C[(size_t)m * ldc + n] = acc[i][j];
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// Fibre-mode projection (AO_env.py:471): c_j = norm * sum_q F[q] (mode_j w)[q].  Block per env.
+// --------------------------------------------------------------------------------------
+__global__ void k_fiber_f64(const double2* __restrict__ F, const double* __restrict__ lpw,
+                            double2* __restrict__ coef, int NF2, int J, long long strideF, double2 norm) {
+  __shared__ double2 red[AOG_MAX_LP][8];
+  const int b = blockIdx.x;
+  const double2* f = F + (size_t)b * strideF;
+  double2 acc[AOG_MAX_LP];
+#pragma unroll
+  for (int j = 0; j < AOG_MAX_LP; ++j) acc[j] = make_double2(0.0, 0.0);
+  for (int q = threadIdx.x; q < NF2; q += blockDim.x) {
+    const double2 v = f[q];
+#pragma unroll
+    for (int j = 0; j < AOG_MAX_LP; ++j)
+      if (j < J) {
+        const double w = lpw[(size_t)j * NF2 + q];
+        acc[j].x = fma(v.x, w, acc[j].x);
+        acc[j].y = fma(v.y, w, acc[j].y);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < AOG_MAX_LP; ++j)
+    if (j < J) {
+      acc[j].x = warp_sum(acc[j].x);
+      acc[j].y = warp_sum(acc[j].y);
+      if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = acc[j];
+    }
+  __syncthreads();
+  if (threadIdx.x < J) {
+    double2 a = make_double2(0.0, 0.0);
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a.x += red[threadIdx.x][w].x; a.y += red[threadIdx.x][w].y; }
+    coef[(size_t)b * J + threadIdx.x] = make_double2(a.x * norm.x - a.y * norm.y, a.x * norm.y + a.y * norm.x);
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Photodetector arm, first contraction (AO_env.py:139): R[y][u] = sum_x E[y][x] M2o[x][u].
+// Warp per pupil row; grid (ceil(Np/8), nB), block 256.
+// --------------------------------------------------------------------------------------
+__global__ void k_obs_rows_f64(const double2* __restrict__ E, const double2* __restrict__ m2o,
+                               double2* __restrict__ R, int Np, int n, int P) {
+  const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (y >= Np) return;
+  const double2* row = E + (size_t)blockIdx.y * P + (size_t)y * Np;
+  for (int u = 0; u < n; ++u) {
+    double re = 0.0, im = 0.0;
+    for (int x = lane; x < Np; x += 32) {
+      const double2 e = row[x], m = m2o[(size_t)x * n + u];
+      re += e.x * m.x - e.y * m.y;
+      im += e.x * m.y + e.y * m.x;
+    }
+    re = warp_sum(re);
+    im = warp_sum(im);
+    if (lane == 0) R[((size_t)blockIdx.y * Np + y) * n + u] = make_double2(re, im);
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Per-env epilogue: obs power (second contraction + |.|^2 w), fibre power, Strehl, SSIM,
+// reward, threshold (AO_env.py:142-153, 468-503).  Block per env.
+// --------------------------------------------------------------------------------------
+struct FinalizeArgs {
+  const double2* R; const double2* m1o; const double2* coef; const double2* lpphase; const double* lpgram;
+  const double2* strehl_part; int strehl_blocks;
+  int Np, n, J, rew_type, has_thr, compute_reward;
+  double thr, obs_weight, strehl_scale, ssim_peak;
+  double2 norm;
+  uint16_t* obs16; double* obs64; double* reward; double* power; double* strehl; double* ssim;
+};
+
+__device__ __forceinline__ double ssim_1d(const double* x, int len, int ref_idx, double peak) {
+  // skimage.metrics.structural_similarity 0.22 on 1-D data against peak * onehot(ref_idx):
+  // win 7, uniform filter, sample covariance, K1 = .01, K2 = .03, crop 3, mean.
+  const double C1 = (0.01 * peak) * (0.01 * peak), C2 = (0.03 * peak) * (0.03 * peak);
+  const double cov_norm = 7.0 / 6.0;
+  double tot = 0.0;
+  for (int c = 3; c < len - 3; ++c) {
+    double sx = 0, sxx = 0, sy = 0, syy = 0, sxy = 0;
+    for (int i = c - 3; i <= c + 3; ++i) {
+      const double a = x[i], r = (i == ref_idx) ? peak : 0.0;
+      sx += a; sxx += a * a; sy += r; syy += r * r; sxy += a * r;
+    }
+    const double ux = sx / 7, uy = sy / 7, uxx = sxx / 7, uyy = syy / 7, uxy = sxy / 7;
+    const double vx = cov_norm * (uxx - ux * ux), vy = cov_norm * (uyy - uy * uy), vxy = cov_norm * (uxy - ux * uy);
+    tot += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+  }
+  return tot / (double)(len - 6);
+}
+
+__global__ void k_finalize(FinalizeArgs a) {
+  __shared__ double obs[AOG_MAX_OBS * AOG_MAX_OBS];
+  const int b = blockIdx.x;
+  const int n2 = a.n * a.n;
+  for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+    const int v = t / a.n, u = t - v * a.n;
+    double re = 0.0, im = 0.0;
+    const double2* r = a.R + (size_t)b * a.Np * a.n;
+    for (int y = 0; y < a.Np; ++y) {
+      const double2 m = a.m1o[(size_t)v * a.Np + y], e = r[(size_t)y * a.n + u];
+      re += m.x * e.x - m.y * e.y;
+      im += m.x * e.y + m.y * e.x;
+    }
+    const double fr = re * a.norm.x - im * a.norm.y, fi = re * a.norm.y + im * a.norm.x;
+    const double pw = (fr * fr + fi * fi) * a.obs_weight;
+    obs[t] = pw;
+    if (a.obs64) a.obs64[(size_t)b * n2 + t] = pw;
+    if (a.obs16) a.obs16[(size_t)b * n2 + t] = __half_as_ushort(__double2half(pw));
+  }
+  __syncthreads();
+  if (threadIdx.x != 0 || !a.compute_reward) return;
+  // fibre: out = M (c e^{i beta L});  total power = c'^H G c'
+  double2 c[AOG_MAX_LP];
+  for (int j = 0; j < a.J; ++j) {
+    const double2 cj = a.coef[(size_t)b * a.J + j], ph = a.lpphase[j];
+    c[j] = make_double2(cj.x * ph.x - cj.y * ph.y, cj.x * ph.y + cj.y * ph.x);
+  }
+  double power = 0.0;
+  for (int j = 0; j < a.J; ++j)
+    for (int k = 0; k < a.J; ++k)
+      power += a.lpgram[j * a.J + k] * (c[j].x * c[k].x + c[j].y * c[k].y);
+  double reward;
+  if (a.rew_type == AOG_REW_STREHL_RATIO) {
+    double sr = 0.0, si = 0.0;
+    const double2* sp = a.strehl_part + (size_t)b * a.strehl_blocks;
+    for (int i = 0; i < a.strehl_blocks; ++i) { sr += sp[i].x; si += sp[i].y; }
+    const double strehl = a.strehl_scale * (sr * sr + si * si);
+    if (a.strehl) a.strehl[b] = strehl;
+    reward = -(100.0 - strehl);
+  } else {
+    const double s = ssim_1d(obs, n2, n2 / 2, a.ssim_peak);
+    if (a.ssim) a.ssim[b] = s;
+    reward = 0.8 * power + (1.0 - 0.8) * s;
+  }
+  if (a.has_thr && reward < a.thr) reward = -1.0;
+  if (a.reward) a.reward[b] = reward;
+  if (a.power) a.power[b] = power;
+}
+
+// --------------------------------------------------------------------------------------
+// Autoregressive column extrusion (hcipy InfiniteAtmosphericLayer._extrude; AO_env.py:125).
+// gather: Z[b] = [ screen[stencil] (on the 180-degree rotated screen when moving +x) ,
+//                  sqrt(Cn2) xi ];  GEMM: new = Z . [A^T ; B^T];  scatter: ring slot.
+// --------------------------------------------------------------------------------------
+__global__ void k_ar_gather(const double* __restrict__ screens, const int* __restrict__ stencil,
+                            const double* __restrict__ noise, double* __restrict__ Z, int P, int Np, int Ns,
+                            int env0, int col_origin, int flipped, double sqrt_cn2, long long noise_stride,
+                            unsigned long long seed, unsigned long long env_id_base, unsigned long long draw_index) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Ns + Np) return;
+  double v;
+  if (j < Ns) {
+    int q = stencil[j];
+    int y = q / Np, x = q - y * Np;
+    if (flipped) { y = Np - 1 - y; x = Np - 1 - x; }
+    x += col_origin;
+    if (x >= Np) x -= Np;
+    v = screens[(size_t)(env0 + b) * P + (size_t)y * Np + x];
+  } else {
+    const int i = j - Ns;
+    double xi;
+    if (noise) {
+      xi = noise[(size_t)(env0 + b) * noise_stride + i];
+    } else {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seed, env_id_base + env0 + b, (draw_index * (unsigned long long)Np + i) * 4ull, &st);
+      xi = curand_normal_double(&st);
+    }
+    v = sqrt_cn2 * xi;
+  }
+  Z[(size_t)b * (Ns + Np) + j] = v;
+}
+
+__global__ void k_ar_scatter(double* __restrict__ screens, const double* __restrict__ newcol, int P, int Np,
+                             int env0, int phys_col, int flipped) {
+  const int b = blockIdx.y;
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= Np) return;
+  const int src = flipped ? (Np - 1 - y) : y;
+  screens[(size_t)(env0 + b) * P + (size_t)y * Np + phys_col] = newcol[(size_t)b * Np + src];
+}
+
+// --------------------------------------------------------------------------------------
+// von-Karman screen synthesis (semi_dynamic reset; AO_env.py:76-77): spectral noise
+// X = C . (xi_r + i xi_i), then screen = Re[W X W^T] through the batched complex GEMM.
+// --------------------------------------------------------------------------------------
+__global__ void k_scr_noise(const double* __restrict__ C, double2* __restrict__ X, int count, long long strideX,
+                            int env0, unsigned long long seed, unsigned long long env_id_base,
+                            unsigned long long draw_base) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, env_id_base + env0 + b, (draw_base + (unsigned long long)i) * 4ull, &st);
+  const double2 z = curand_normal2_double(&st);
+  const double c = C[i];
+  X[(size_t)b * strideX + i] = make_double2(c * z.x, c * z.y);
+}
+
+__global__ void k_scr_combine(double* __restrict__ screens, const double2* __restrict__ Y, int P, long long strideY,
+                              int env0, double scale, int accumulate) {
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double v = scale * Y[(size_t)b * strideY + p].x;
+  double* s = screens + (size_t)(env0 + b) * P + p;
+  *s = accumulate ? (*s + v) : v;
+}
+
+// misc ---------------------------------------------------------------------------------
+__global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+
+__global__ void k_transpose_z(const double2* __restrict__ in, double2* __restrict__ out, int rows, int cols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) { int r = i / cols, c = i - r * cols; out[(size_t)c * rows + r] = in[i]; }
+}
+
+__global__ void k_build_arW(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ W,
+                            int Np, int Ns) {
+  // W[j][y] = A[y][j] (j < Ns);  W[Ns + j][y] = B[y][j]
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (Ns + Np) * Np) return;
+  int j = i / Np, y = i - j * Np;
+  W[i] = (j < Ns) ? A[(size_t)y * Ns + j] : Bm[(size_t)y * Np + (j - Ns)];
+}
+
+__global__ void k_focal_power(const double2* __restrict__ F, double* __restrict__ out, int n, double2 norm, double w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 f = F[i];
+  const double fr = f.x * norm.x - f.y * norm.y, fi = f.x * norm.y + f.y * norm.x;
+  out[i] = (fr * fr + fi * fi) * w;
+}

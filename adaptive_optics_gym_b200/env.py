@@ -1,0 +1,332 @@
+"""``AOEnv`` / ``AOVecEnv`` -- the ``AO-v0`` boundary of the reference on B200 CUDA kernels.
+
+``AOEnv`` mirrors ``gym_AO.envs.AO_env.AOEnv`` of the reference (constructor kwargs
+``AO_env.py:17-29``; ``reset`` ``:74-103``; ``step`` ``:106-153``; ``SH_step`` ``:254-290``;
+``render`` ``:156-194``): same names, argument meaning, return types and error behaviour, so
+``main.py`` / ``algorithm.py`` / ``eval_policy.py`` run unchanged against it.  ``AOVecEnv`` is the
+vectorised N-environment variant (not in the reference): the same kwargs plus ``num_envs``, torch
+CUDA tensors in and out, all environments in lock-step.
+
+All arithmetic of reset/step runs in ``libaogym.so`` (hand-written sm_100a CUDA behind the C-ABI
+of ``include/aogym.h``); this file only builds the set-up tables and marshals buffers.  There is
+no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._gym_compat import Env, spaces
+from .tables import AOConfig, build_tables, synthesize_screens
+
+
+def _coerce_velocity(atm_type, velocity_value):
+    """Reference AO_env.py:200-208 (including its two prints)."""
+    if (atm_type == 'quasi_static' or atm_type == 'semi_dynamic') and velocity_value != 0:
+        print('In ' + atm_type + ' atmospheric condition, the velocity value should be zero.')
+        print('therefore velocity value is changed to zero')
+        velocity_value = 0
+    elif atm_type == 'dynamic' and velocity_value == 0:
+        print('In ' + atm_type + ' atmospheric condition, the velocity value cannot be zero.')
+        print('therefore velocity value is changed to 1 m/s')
+        velocity_value = 1
+    return velocity_value
+
+
+class _AOCore:
+    """Shared construction: config -> tables -> device handle -> initial screens."""
+
+    def _setup(self, *, atm_type, atm_vel, atm_fried, act_type, act_dim, obs_dim, rew_type, rew_threshold,
+               timesteps_per_episode, flat_mirror_start_per_episode, SH_operation, num_envs, device, seed,
+               precision, tables, initial_screens, num_pupil_pixels, num_focal_pixels_fiber, env_id_base):
+        if atm_type not in _lib.ATM:
+            raise ValueError(f'atm_type must be one of {list(_lib.ATM)}')
+        self.atm_type = atm_type
+        self.rew_type = rew_type
+        self.act_type = act_type
+        self.flat_mirror_start_per_episode = flat_mirror_start_per_episode
+        self.rew_threshold = rew_threshold
+        self.SH_operation = SH_operation
+        self.num_envs = int(num_envs)
+        velocity = _coerce_velocity(atm_type, atm_vel)
+        cfg = AOConfig(atm_type=atm_type, velocity=float(velocity), fried_parameter=float(atm_fried),
+                       act_type=act_type, num_modes=int(act_dim), obs_dim=int(obs_dim), rew_type=rew_type,
+                       max_steps=int(timesteps_per_episode), num_pupil_pixels=int(num_pupil_pixels),
+                       num_focal_pixels_fiber=int(num_focal_pixels_fiber))
+        self.config = cfg
+        # reference attribute names (AO_env.py:249-251 assigns every parameter onto self)
+        for k in ('telescope_diameter', 'num_pupil_pixels', 'wavelength_wfs', 'wavelength_sci', 'num_modes',
+                  'delta_t', 'max_steps', 'velocity', 'fried_parameter', 'outer_scale',
+                  'singlemode_fiber_core_radius', 'multimode_fiber_core_radius'):
+            setattr(self, k, getattr(cfg, k))
+        self.num_focal_pixels_fiber = cfg.num_focal_pixels_fiber
+        self.num_focal_pixels_fiber_subsample = cfg.obs_dim
+        self._seed = 0 if seed is None else int(seed)
+        rng = np.random.default_rng(self._seed)
+        self.tables = build_tables(cfg, rng=rng, overrides=tables)
+        t = self.tables
+
+        # skimage raises ValueError from step() when obs_dim^2 < 7 (AO_env.py:495); keep that
+        # behaviour at the boundary and give the device a configuration it accepts.
+        self._ssim_too_small = rew_type == 'smf_ssim' and cfg.obs_dim ** 2 < 7
+        if rew_type not in _lib.REW:
+            raise ValueError(f'rew_type must be one of {list(_lib.REW)}')
+
+        c = _lib.AogConfig()
+        c.abi_version = _lib.ABI_VERSION
+        c.device = int(device)
+        c.num_envs = self.num_envs
+        c.num_pupil_pixels = cfg.num_pupil_pixels
+        c.num_focal_pixels = cfg.num_focal_pixels_fiber
+        c.obs_dim = cfg.obs_dim
+        c.num_modes = cfg.num_modes
+        c.num_lp_modes = int(t['lp_phase'].size)
+        c.num_stencil = int(t['ar_stencil'].size) if 'ar_stencil' in t.arrays else 0
+        c.num_screen_fine = int(t['scr_C2'].shape[0])
+        c.atm_type = _lib.ATM[atm_type]
+        c.rew_type = _lib.REW['strehl_ratio'] if self._ssim_too_small else _lib.REW[rew_type]
+        c.sh_operation = int(bool(SH_operation))
+        c.flat_mirror_start = int(bool(flat_mirror_start_per_episode))
+        c.max_steps = cfg.max_steps
+        c.has_rew_threshold = int(rew_threshold is not None)
+        c.rew_threshold = float(rew_threshold) if rew_threshold is not None else 0.0
+        c.precision = _lib.PRECISION[precision]
+        c.env_id_base = int(env_id_base)
+        c.wavelength_wfs = cfg.wavelength_wfs
+        c.wavelength_sci = cfg.wavelength_sci
+        c.delta_t = cfg.delta_t
+        c.velocity = cfg.velocity
+        c.pupil_delta = t['pupil_delta']
+        c.amp_fiber = t['amp_fiber']
+        c.sqrt_cn2 = float(np.sqrt(t['cn2']))
+        c.strehl_scale = t['strehl_scale']
+        c.obs_weight = t['obs_weight']
+        c.ssim_ref_peak = cfg.ssim_ref_peak
+        c.mft_norm_re = float(np.real(t['mft_fib_norm']))
+        c.mft_norm_im = float(np.imag(t['mft_fib_norm']))
+        c.seed = self._seed
+        self._h = _lib.Handle(c)
+        for name in _lib.TABLE_IDS:
+            if name in t.arrays:
+                self._h.set_table(name, t.arrays[name])
+        # initial screen(s) (hcipy draws one at construction; AO_env.py:370)
+        if initial_screens is not None:
+            s = np.asarray(initial_screens)
+            s = s.reshape(-1, cfg.num_pupil_pixels ** 2)
+            if s.shape[0] == 1 and self.num_envs > 1:
+                s = np.repeat(s, self.num_envs, axis=0)
+            if s.shape[0] != self.num_envs:
+                raise ValueError('initial_screens must hold one screen per env')
+            self._h.set_screens(s)
+        else:
+            self._h.generate_screens()
+        self.timestep = 0
+        self.episode_no = 0
+        self.timestep_render = 0
+
+    # ---- state shared by both front ends
+    def _sync_counters(self):
+        c = self._h.counters()
+        self.timestep, self.timestep_render, self.episode_no = c.timestep, c.timestep_render, c.episode_no
+
+    def get_state(self):
+        """Environment state (absent in the reference): screens, DM actuators, counters."""
+        c = self._h.counters()
+        return dict(screens=self._h.get_screens(), actuators=self._h.get_actuators(),
+                    timestep=c.timestep, timestep_render=c.timestep_render, episode_no=c.episode_no,
+                    extrusions=c.extrusions)
+
+    def set_state(self, state):
+        self._h.set_counters(column_origin=0)
+        self._h.set_screens(state['screens'])
+        self._h.set_actuators(state['actuators'])
+        self._h.set_counters(timestep=state['timestep'], timestep_render=state['timestep_render'],
+                             episode_no=state['episode_no'], extrusions=state['extrusions'], column_origin=0)
+        self._sync_counters()
+
+    def close(self):
+        self._h.close()
+
+
+class AOEnv(_AOCore, Env):
+    """Single ``AO-v0`` environment, NumPy in / NumPy out (reference ``AO_env.py:16-503``).
+
+    Extra optional kwargs (defaults = reference constants): ``device``, ``seed``, ``precision``
+    ('f64' exact arithmetic | 'tensor' split-fp16 tcgen05 MFT), ``tables`` (override any set-up
+    table), ``initial_screen``, ``num_pupil_pixels``, ``num_focal_pixels_fiber``.
+    """
+
+    metadata = {'render_modes': ['human']}
+
+    def __init__(self, atm_type='quasi_static', atm_vel=0, atm_fried=0.15, act_type='num_actuators', act_dim=64,
+                 obs_dim=2, rew_type='strehl_ratio', rew_threshold=None, timesteps_per_episode=20,
+                 flat_mirror_start_per_episode=True, SH_operation=False, *, device=0, seed=None,
+                 precision='f64', tables=None, initial_screen=None, num_pupil_pixels=240,
+                 num_focal_pixels_fiber=128):
+        super().__init__()
+        self._setup(atm_type=atm_type, atm_vel=atm_vel, atm_fried=atm_fried, act_type=act_type, act_dim=act_dim,
+                    obs_dim=obs_dim, rew_type=rew_type, rew_threshold=rew_threshold,
+                    timesteps_per_episode=timesteps_per_episode,
+                    flat_mirror_start_per_episode=flat_mirror_start_per_episode, SH_operation=SH_operation,
+                    num_envs=1, device=device, seed=seed, precision=precision, tables=tables,
+                    initial_screens=initial_screen, num_pupil_pixels=num_pupil_pixels,
+                    num_focal_pixels_fiber=num_focal_pixels_fiber, env_id_base=0)
+        # AO_env.py:45-46
+        self.observation_space = spaces.Box(low=-1, high=1, shape=(self.num_focal_pixels_fiber_subsample ** 2,),
+                                            dtype=np.float16)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(self.num_modes,), dtype=np.float16)
+        self.last_obs_f64 = None
+        self.last_strehl = None
+        self.last_ssim = None
+
+    def reset(self, seed=None, options=None):
+        """AO_env.py:74-103 -> (float16 obs [obs_dim^2], {}); seed/options ignored as in the reference."""
+        h = self._h.reset_host()
+        self._sync_counters()
+        self.last_obs_f64 = h['obs_f64'][0].copy()
+        return h['obs_f16'][0].copy(), {}
+
+    def step(self, action, extrusion_noise=None):
+        """AO_env.py:106-153 -> (float16 obs, reward, done, False, {"power": float})."""
+        if self._ssim_too_small:
+            raise ValueError('win_size exceeds image extent. Either ensure that your images are at least 7x7; '
+                             'or pass win_size explicitly in the function call, with an odd value less than or '
+                             'equal to the smaller side of your images.')
+        a = np.asarray(action)
+        if a.dtype != np.float32:
+            a = a.astype(np.float64)
+        h, done = self._h.step_host(a.reshape(1, -1), extrusion_noise)
+        self._sync_counters()
+        self.last_obs_f64 = h['obs_f64'][0].copy()
+        self.last_strehl = float(h['strehl'][0])
+        self.last_ssim = float(h['ssim'][0])
+        reward = np.float64(h['reward'][0])
+        return h['obs_f16'][0].copy(), reward, done, False, {"power": float(h['power'][0])}
+
+    def SH_step(self):
+        raise NotImplementedError('SH_step (AO_env.py:254-290) is not built yet; see DESIGN.md')
+
+    def render(self, close=False):
+        """AO_env.py:156-194.  Reads the three panels' fields back from the device; draws them when
+        matplotlib is importable, and always leaves them in ``self.last_render``."""
+        screen = self._h.get_field('screen')
+        opd = screen / self.wavelength_wfs * (self.wavelength_wfs / (2 * np.pi)) * 1e6
+        self.last_render = dict(phase_screen_opd=opd, focal_power=self._h.get_field('focal_power'),
+                                obs_power=self._h.get_field('obs_power'))
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError:
+            return
+        n, nf, no = self.num_pupil_pixels, self.num_focal_pixels_fiber, self.num_focal_pixels_fiber_subsample
+        plt.suptitle('episode %d - timestep %d / %d' % (self.episode_no + 1, self.timestep_render + 1, self.max_steps))
+        plt.subplots_adjust(wspace=1, hspace=1)
+        plt.subplot(2, 2, 1)
+        plt.title(r'Atmospheric phase screen $ [\mu m]$')
+        plt.imshow(opd.reshape(n, n), vmin=-6, vmax=6, cmap='RdBu', origin='lower')
+        plt.colorbar()
+        plt.subplot(2, 2, 3)
+        plt.title('Wavefront power on focal plane')
+        plt.imshow(self.last_render['focal_power'].reshape(nf, nf), vmin=0, origin='lower')
+        plt.colorbar()
+        plt.subplot(2, 2, 4)
+        plt.title('Wavefront power on photodetector')
+        plt.imshow(self.last_render['obs_power'].reshape(no, no), vmin=0, origin='lower')
+        plt.colorbar()
+        plt.show(block=False)
+        plt.pause(0.05)
+        plt.clf()
+
+
+class AOVecEnv(_AOCore):
+    """``num_envs`` lock-stepped ``AO-v0`` environments on one B200; torch CUDA tensors in/out.
+
+    ``reset() -> (obs [B, n^2] float16, {})``;
+    ``step(actions [B, K]) -> (obs, reward [B] f64, done [B] bool, trunc [B] bool, {"power": [B] f64})``.
+    Every env shares ``timesteps_per_episode`` so all terminate on the same step (the caller
+    resets after ``done``, as with the single env).  Sharding across GPUs: one instance per rank
+    with ``env_id_base = rank * num_envs`` (RNG stream = global env id); no collective on the
+    step path.
+    """
+
+    def __init__(self, num_envs, atm_type='quasi_static', atm_vel=0, atm_fried=0.15, act_type='num_actuators',
+                 act_dim=64, obs_dim=2, rew_type='strehl_ratio', rew_threshold=None, timesteps_per_episode=20,
+                 flat_mirror_start_per_episode=True, SH_operation=False, *, device=0, seed=None, precision='f64',
+                 tables=None, initial_screens=None, num_pupil_pixels=240, num_focal_pixels_fiber=128,
+                 env_id_base=0):
+        import torch
+        self._torch = torch
+        self.device = torch.device('cuda', int(device))
+        self._setup(atm_type=atm_type, atm_vel=atm_vel, atm_fried=atm_fried, act_type=act_type, act_dim=act_dim,
+                    obs_dim=obs_dim, rew_type=rew_type, rew_threshold=rew_threshold,
+                    timesteps_per_episode=timesteps_per_episode,
+                    flat_mirror_start_per_episode=flat_mirror_start_per_episode, SH_operation=SH_operation,
+                    num_envs=num_envs, device=device, seed=seed, precision=precision, tables=tables,
+                    initial_screens=initial_screens, num_pupil_pixels=num_pupil_pixels,
+                    num_focal_pixels_fiber=num_focal_pixels_fiber, env_id_base=env_id_base)
+        B, n2 = self.num_envs, self.config.obs_dim ** 2
+        self.single_observation_space = spaces.Box(low=-1, high=1, shape=(n2,), dtype=np.float16)
+        self.single_action_space = spaces.Box(low=-1, high=1, shape=(self.num_modes,), dtype=np.float16)
+        kw = dict(device=self.device)
+        self.obs = torch.empty((B, n2), dtype=torch.float16, **kw)
+        self.obs_f64 = torch.empty((B, n2), dtype=torch.float64, **kw)
+        self.reward = torch.empty(B, dtype=torch.float64, **kw)
+        self.power = torch.empty(B, dtype=torch.float64, **kw)
+        self.strehl = torch.zeros(B, dtype=torch.float64, **kw)
+        self.ssim = torch.zeros(B, dtype=torch.float64, **kw)
+        self._true = torch.ones(B, dtype=torch.bool, **kw)
+        self._false = torch.zeros(B, dtype=torch.bool, **kw)
+        o = _lib.AogOutputs()
+        o.obs_f16, o.obs_f64 = self.obs.data_ptr(), self.obs_f64.data_ptr()
+        o.reward, o.power = self.reward.data_ptr(), self.power.data_ptr()
+        o.strehl, o.ssim = self.strehl.data_ptr(), self.ssim.data_ptr()
+        self._out = o
+
+    def _stream(self):
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, seed=None, options=None):
+        self._h.reset_device(self._out, self._stream())
+        self._sync_counters()
+        return self.obs, {}
+
+    def step(self, actions, extrusion_noise=None):
+        torch = self._torch
+        if self._ssim_too_small:
+            raise ValueError('win_size exceeds image extent (smf_ssim needs obs_dim^2 >= 7)')
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions), device=self.device)
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        if actions.dtype not in (torch.float32, torch.float64):
+            actions = actions.to(torch.float64)
+        actions = actions.contiguous()
+        if actions.numel() != self.num_envs * self.num_modes:
+            raise ValueError(f'actions must be [{self.num_envs}, {self.num_modes}]')
+        nz_ptr = None
+        if extrusion_noise is not None:
+            nz = extrusion_noise
+            if not torch.is_tensor(nz):
+                nz = torch.as_tensor(np.asarray(nz, dtype=np.float64), device=self.device)
+            nz = nz.to(self.device, torch.float64).contiguous()
+            need = self.num_envs * self._h.next_extrusions() * self.num_pupil_pixels
+            if nz.numel() != need:
+                raise ValueError(f'extrusion_noise must have {need} elements')
+            nz_ptr = nz.data_ptr() if need else None
+        dt = _lib.DTYPE_F32 if actions.dtype == torch.float32 else _lib.DTYPE_F64
+        done = self._h.step_device(actions.data_ptr(), dt, self._out, nz_ptr, self._stream())
+        self._sync_counters()
+        return self.obs, self.reward, (self._true if done else self._false), self._false, {"power": self.power}
+
+    def set_screens(self, screens):
+        """[B, Np^2] torch (cuda, float32/float64) or NumPy array."""
+        torch = self._torch
+        if torch.is_tensor(screens) and screens.is_cuda:
+            s = screens.contiguous()
+            dt = _lib.DTYPE_F32 if s.dtype == torch.float32 else _lib.DTYPE_F64
+            if s.dtype not in (torch.float32, torch.float64):
+                raise ValueError('screens must be float32 or float64')
+            self._h.set_screens_device(s.data_ptr(), dt, 0, self.num_envs)
+        else:
+            self._h.set_screens(np.asarray(screens))

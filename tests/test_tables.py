@@ -1,0 +1,69 @@
+"""CPU: the product's set-up tables (adaptive_optics_gym_b200/tables.py) against the oracle's
+independently written hcipy restatement."""
+import numpy as np
+import pytest
+
+from adaptive_optics_gym_b200.tables import (AOConfig, ar_extrusion_tables, build_tables, disk_harmonic_orders,
+                                             synthesize_screens, zernike_noll)
+from oracle import ao_oracle as O
+
+
+@pytest.mark.parametrize('act_type,K,n', [('zernike', 6, 5), ('num_actuators', 64, 2), ('zernike', 21, 3)])
+def test_tables_match_oracle(act_type, K, n):
+    tb = build_tables(AOConfig(act_type=act_type, num_modes=K, obs_dim=n))
+    env = O.OracleAOEnv(act_type=act_type, act_dim=K, obs_dim=n, initial_screen=np.zeros(57600))
+    np.testing.assert_allclose(tb['dm_modes'], env.deformable_mirror.M.T, atol=5e-15)
+    np.testing.assert_array_equal(tb['aperture'], env.aperture)
+    a = np.random.default_rng(0).normal(size=K)
+    assert np.sqrt(a @ tb['dm_gram'] @ a) == pytest.approx(np.std(env.deformable_mirror.M @ a), rel=1e-12)
+    for prop, k1, k2 in ((env.propagator_fiber, 'mft_fib_1', 'mft_fib_2'),
+                         (env.propagator_fiber_subsample, 'mft_obs_1', 'mft_obs_2')):
+        M1, M2, norm = prop.matrices(env.pupil_grid, 1.5e-6)
+        np.testing.assert_allclose(tb[k1], M1, atol=1e-13 * np.abs(M1).max())
+        np.testing.assert_allclose(tb[k2], M2, atol=1e-13)
+        assert tb['mft_fib_norm'] == pytest.approx(norm, rel=1e-15)
+    fg = env.propagator_fiber.output_grid
+    L, beta = env.single_mode_fiber.instance(fg, 1.5e-6)
+    np.testing.assert_allclose(tb['lp_modes_w'], L.T * fg.weight, atol=1e-13 * np.abs(L).max() * fg.weight)
+    np.testing.assert_allclose(tb['lp_beta'], beta, rtol=1e-13)
+    np.testing.assert_allclose(tb['lp_phase'], np.exp(1j * beta * 10), atol=1e-6)
+    assert tb['amp_fiber'] == pytest.approx(env.wf_wfs_fiber.electric_field.real.max(), rel=1e-14)
+    assert tb['amp_flux'] == pytest.approx(env.wf_sci.electric_field.real.max(), rel=1e-14)
+    assert tb['sci_focal_index'] == int(np.argmax(env.unaberrated_PSF))
+    assert tb['obs_weight'] == pytest.approx(env.propagator_fiber_subsample.output_grid.weight, rel=1e-15)
+    # Strehl by single-pixel sum == the reference's full-plane route
+    scr = O.von_karman_screen(env.pupil_grid, tb['cn2'], 10.0, np.random.default_rng(1))
+    env.layer.achromatic_screen = scr
+    env.reset()
+    env.rew_type = 'strehl_ratio'
+    env.reward_function()
+    s = np.sum(env.aperture * np.exp(1j * scr / 2.2e-6))
+    assert tb['strehl_scale'] * abs(s) ** 2 == pytest.approx(env.last_strehl, rel=1e-11)
+
+
+def test_noll_and_disk_harmonic_ordering():
+    assert [zernike_noll(j) for j in range(1, 8)] == [O.hcipy_noll_to_zernike(j) for j in range(1, 8)]
+    assert zernike_noll(4) == (2, 0) and zernike_noll(2) == (1, 1) and zernike_noll(3) == (1, -1)
+    assert disk_harmonic_orders(64) == O.hcipy_disk_harmonic_orders_sorted(64)
+    assert disk_harmonic_orders(5) == [(1, 0), (1, -1), (1, 1), (1, -2), (1, 2)]
+
+
+def test_ar_tables_match_oracle_given_same_stencil():
+    g = O.hcipy_make_pupil_grid(48, 0.5 * 48 / 240)
+    lay = O.InfiniteAtmosphericLayer(g, 1e-13, 10.0, 5.0, np.random.default_rng(2))
+    st = np.flatnonzero(lay.stencil_left).reshape(48, 3)
+    idx, A, B = ar_extrusion_tables(48, g.delta[0], 10.0, None, extra_columns=st[:, 2] % 48)
+    np.testing.assert_array_equal(idx, np.flatnonzero(lay.stencil_left))
+    np.testing.assert_allclose(A, lay.A_horizontal, atol=1e-6)
+    np.testing.assert_allclose(B @ B.T, lay.B_horizontal @ lay.B_horizontal.T, atol=1e-4 * np.abs(B @ B.T).max())   # difference of near-equal covariances
+
+
+def test_host_screen_synthesis_statistics():
+    tb = build_tables(AOConfig(num_modes=4))
+    scr = synthesize_screens(tb, 96, tb['cn2'], np.random.default_rng(0)).reshape(-1, 240, 240)
+    r0 = O.hcipy_fried_parameter_from_Cn_squared(tb['cn2'], 1.0)
+    cov = O.hcipy_phase_covariance_von_karman(r0, 10.0)
+    for lag in (4, 16, 64):
+        th = 2 * (cov(np.array(0.0)) - cov(np.array(lag * 0.5 / 240)))
+        d = np.mean((scr[:, :, lag:] - scr[:, :, :-lag]) ** 2)
+        assert d / th == pytest.approx(1.0, abs=0.15)
