@@ -25,7 +25,8 @@ TABLE_IDS = {
     'mft_obs_2': 6, 'lp_modes_w': 7, 'lp_phase': 8, 'lp_gram': 9, 'ar_stencil': 10, 'ar_A': 11,
     'ar_B': 12, 'scr_C1': 13, 'scr_W1': 14, 'scr_C2': 15, 'scr_W2': 16,
 }
-FIELD_IDS = {'screen': 0, 'pupil': 1, 'focal': 2, 'focal_power': 3, 'obs_power': 4, 'actuators': 5}
+FIELD_IDS = {'screen': 0, 'pupil': 1, 'focal': 2, 'focal_power': 3, 'obs_power': 4, 'actuators': 5,
+             'tc_pupil': 6, 'tc_stage1': 7}
 
 
 class AogConfig(C.Structure):
@@ -197,10 +198,11 @@ class Handle:
         c = self.cfg
         P, nf2, n2 = c.num_pupil_pixels ** 2, c.num_focal_pixels ** 2, c.obs_dim ** 2
         size = {'screen': P, 'pupil': 2 * P, 'focal': 2 * nf2, 'focal_power': nf2, 'obs_power': n2,
-                'actuators': c.num_modes}[which]
+                'actuators': c.num_modes, 'tc_pupil': 2 * P,
+                'tc_stage1': 2 * c.num_focal_pixels * c.num_pupil_pixels}[which]
         out = np.empty(size)
         self.check(self.lib.aog_get_field(self._h, FIELD_IDS[which], env_index, _ptr(out), size), 'aog_get_field')
-        if which in ('pupil', 'focal'):
+        if which in ('pupil', 'focal', 'tc_pupil', 'tc_stage1'):
             return out.view(np.complex128)
         return out
 

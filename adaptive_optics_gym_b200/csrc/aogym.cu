@@ -70,6 +70,10 @@ int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long
     k_ar_scatter<<<g3, 128, 0, st>>>(env->screens, env->arNew, env->P, Np, e0, phys, flipped);
     AOG_LAUNCH_CHECK();
   }
+  if (c.precision == AOG_PRECISION_TENSOR) {
+    int rc = aog_tensor_column_updated(env, phys, st);
+    if (rc) return rc;
+  }
   env->cnt.column_origin = positive ? (org + 1) % Np : phys;
   env->cnt.extrusions++;
   return AOG_OK;
@@ -293,7 +297,7 @@ int aog_create(const aog_config* cfg, aog_env** out) {
   A(alloc_host_outputs(env));
   if (c.precision == AOG_PRECISION_TENSOR) A(aog_tensor_create(env));
 #undef A
-  AOG_CUDA(cudaStreamCreateWithFlags(&env->own_stream, cudaStreamNonBlocking));
+  AOG_CUDA(cudaStreamCreate(&env->own_stream));   // blocking: ordered with the default stream
   AOG_CUDA(cudaEventCreate(&env->ev0));
   AOG_CUDA(cudaEventCreate(&env->ev1));
   return AOG_OK;
@@ -429,12 +433,12 @@ int aog_generate_screens(aog_env* env, void* stream) {
       !env->have[AOG_TABLE_SCR_C2] || !env->have[AOG_TABLE_SCR_W2])
     AOG_FAIL(AOG_ERR_STATE, "screen synthesis tables not set");
   AOG_CUDA(cudaSetDevice(c.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : env->own_stream;
+  cudaStream_t st = (cudaStream_t)stream;
   const int Np = c.num_pupil_pixels, N2 = c.num_screen_fine, P = env->P, B = c.num_envs;
   // independent Philox domain from the extrusion noise: offset the seed
   const unsigned long long seed = c.seed ^ 0x9E3779B97F4A7C15ull;
   const unsigned long long per = (unsigned long long)P + (unsigned long long)N2 * N2;
-  const unsigned long long base = (unsigned long long)env->cnt.episode_no * per;
+  const unsigned long long base = (unsigned long long)(env->screen_draws++) * per;
   const long long sB = (long long)Np * std::max(c.num_focal_pixels, Np);
   const long long sC = (long long)std::max<size_t>(env->NF2, P);
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
@@ -481,7 +485,7 @@ int aog_reset(aog_env* env, const aog_outputs* out_dev, void* stream) {
   if (!tables_ready(env)) return AOG_ERR_STATE;
   const aog_config& c = env->cfg;
   AOG_CUDA(cudaSetDevice(c.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : env->own_stream;
+  cudaStream_t st = (cudaStream_t)stream;
   int rc;
   // AO_env.py:76-77 -- semi_dynamic draws a fresh screen per episode
   if (c.atm_type == AOG_ATM_SEMI_DYNAMIC && c.num_screen_fine > 0)
@@ -512,7 +516,7 @@ int aog_step(aog_env* env, const void* actions_dev, int act_dtype, const double*
   if (!tables_ready(env)) return AOG_ERR_STATE;
   const aog_config& c = env->cfg;
   AOG_CUDA(cudaSetDevice(c.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : env->own_stream;
+  cudaStream_t st = (cudaStream_t)stream;
   const int B = c.num_envs, K = c.num_modes;
   // AO_env.py:115-120
   const size_t shm = (size_t)(K + 32) * sizeof(double);
@@ -618,6 +622,10 @@ int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size
     AOG_CUDA(cudaMemcpy(host_out, env->act + (size_t)env_index * c.num_modes, count * sizeof(double),
                         cudaMemcpyDeviceToHost));
     return AOG_OK;
+  }
+  if (which == AOG_FIELD_TC_PUPIL || which == AOG_FIELD_TC_STAGE1) {
+    if (c.precision != AOG_PRECISION_TENSOR) AOG_FAIL(AOG_ERR_INVALID, "tensor-path field on an FP64 handle");
+    return aog_tensor_get_field(env, which, env_index % env->chunk, host_out, count);
   }
   // optical fields: recompute the FP64 chain for that one env from the current state
   if (!env->bufA) {

@@ -64,6 +64,8 @@ struct aog_env {
   // ---- counters (host; all envs run in lock-step) ----
   aog_counters cnt{};
   int64_t launches = 0;
+  int64_t screen_draws = 0;        // von-Karman syntheses so far (Philox offset domain)
+  void* tensor_state = nullptr;     // TensorState (tensor_path.cu) when precision == TENSOR
   cudaStream_t own_stream = nullptr;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -10,7 +10,7 @@
 // One block per env.
 // --------------------------------------------------------------------------------------
 template <typename ActT>
-__global__ void k_actuators(const ActT* __restrict__ actions, const double* __restrict__ gram,
+static __global__ void k_actuators(const ActT* __restrict__ actions, const double* __restrict__ gram,
                             double* __restrict__ act, int K, int sh_operation, double target_rms) {
   extern __shared__ double sh_a[];   // [K] + [32] reduction scratch
   double* red = sh_a + K;
@@ -50,7 +50,7 @@ __global__ void k_actuators(const ActT* __restrict__ actions, const double* __re
 // grid (ceil(P/128), ceil(nB/ET)), block 128.
 // --------------------------------------------------------------------------------------
 template <int ET>
-__global__ void k_field_f64(const double* __restrict__ screens, const double* __restrict__ act,
+static __global__ void k_field_f64(const double* __restrict__ screens, const double* __restrict__ act,
                             const double* __restrict__ modes, const double* __restrict__ aperture,
                             double2* __restrict__ E, double2* __restrict__ strehl_part, int P, int Np, int K,
                             int env0, int nB, int col_origin, double l_wfs, double l_sci, double amp,
@@ -117,7 +117,7 @@ __global__ void k_field_f64(const double* __restrict__ screens, const double* __
 // Batched complex FP64 GEMM  C[b] = A[b] (M x Kd) . B[b] (Kd x N), row-major, stride 0 = shared.
 // 64x64x16 tiles, 256 threads, 4x4 complex accumulators per thread.
 // --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_zgemm(const double2* __restrict__ A, const double2* __restrict__ B,
+static __global__ void __launch_bounds__(256) k_zgemm(const double2* __restrict__ A, const double2* __restrict__ B,
                                                double2* __restrict__ C, int M, int N, int Kd, int lda, int ldb,
                                                int ldc, long long sA, long long sB, long long sC) {
   __shared__ double2 As[16][65];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_zgemm(const double2* __restrict__ A, co
 }
 
 // Real FP64 GEMM C (M x N) = A (M x Kd) . B (Kd x N), same tiling (AR extrusion over envs).
-__global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, const double* __restrict__ B,
+static __global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, const double* __restrict__ B,
                                                double* __restrict__ C, int M, int N, int Kd, int lda, int ldb,
                                                int ldc) {
   __shared__ double As[16][65];
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) k_dgemm(const double* __restrict__ A, con
 // --------------------------------------------------------------------------------------
 // Fibre-mode projection (AO_env.py:471): c_j = norm * sum_q F[q] (mode_j w)[q].  Block per env.
 // --------------------------------------------------------------------------------------
-__global__ void k_fiber_f64(const double2* __restrict__ F, const double* __restrict__ lpw,
+static __global__ void k_fiber_f64(const double2* __restrict__ F, const double* __restrict__ lpw,
                             double2* __restrict__ coef, int NF2, int J, long long strideF, double2 norm) {
   __shared__ double2 red[AOG_MAX_LP][8];
   const int b = blockIdx.x;
@@ -251,7 +251,7 @@ __global__ void k_fiber_f64(const double2* __restrict__ F, const double* __restr
 // Photodetector arm, first contraction (AO_env.py:139): R[y][u] = sum_x E[y][x] M2o[x][u].
 // Warp per pupil row; grid (ceil(Np/8), nB), block 256.
 // --------------------------------------------------------------------------------------
-__global__ void k_obs_rows_f64(const double2* __restrict__ E, const double2* __restrict__ m2o,
+static __global__ void k_obs_rows_f64(const double2* __restrict__ E, const double2* __restrict__ m2o,
                                double2* __restrict__ R, int Np, int n, int P) {
   const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -278,6 +278,7 @@ struct FinalizeArgs {
   const double2* R; const double2* m1o; const double2* coef; const double2* lpphase; const double* lpgram;
   const double2* strehl_part; int strehl_blocks;
   int Np, n, J, rew_type, has_thr, compute_reward;
+  int transpose_out;   // R / table hold the transposed contraction: result (a, b) is obs pixel (v = b, u = a)
   double thr, obs_weight, strehl_scale, ssim_peak;
   double2 norm;
   uint16_t* obs16; double* obs64; double* reward; double* power; double* strehl; double* ssim;
@@ -302,7 +303,7 @@ __device__ __forceinline__ double ssim_1d(const double* x, int len, int ref_idx,
   return tot / (double)(len - 6);
 }
 
-__global__ void k_finalize(FinalizeArgs a) {
+static __global__ void k_finalize(FinalizeArgs a) {
   __shared__ double obs[AOG_MAX_OBS * AOG_MAX_OBS];
   const int b = blockIdx.x;
   const int n2 = a.n * a.n;
@@ -317,9 +318,10 @@ __global__ void k_finalize(FinalizeArgs a) {
     }
     const double fr = re * a.norm.x - im * a.norm.y, fi = re * a.norm.y + im * a.norm.x;
     const double pw = (fr * fr + fi * fi) * a.obs_weight;
-    obs[t] = pw;
-    if (a.obs64) a.obs64[(size_t)b * n2 + t] = pw;
-    if (a.obs16) a.obs16[(size_t)b * n2 + t] = __half_as_ushort(__double2half(pw));
+    const int to = a.transpose_out ? (u * a.n + v) : t;
+    obs[to] = pw;
+    if (a.obs64) a.obs64[(size_t)b * n2 + to] = pw;
+    if (a.obs16) a.obs16[(size_t)b * n2 + to] = __half_as_ushort(__double2half(pw));
   }
   __syncthreads();
   if (threadIdx.x != 0 || !a.compute_reward) return;
@@ -356,7 +358,7 @@ __global__ void k_finalize(FinalizeArgs a) {
 // gather: Z[b] = [ screen[stencil] (on the 180-degree rotated screen when moving +x) ,
 //                  sqrt(Cn2) xi ];  GEMM: new = Z . [A^T ; B^T];  scatter: ring slot.
 // --------------------------------------------------------------------------------------
-__global__ void k_ar_gather(const double* __restrict__ screens, const int* __restrict__ stencil,
+static __global__ void k_ar_gather(const double* __restrict__ screens, const int* __restrict__ stencil,
                             const double* __restrict__ noise, double* __restrict__ Z, int P, int Np, int Ns,
                             int env0, int col_origin, int flipped, double sqrt_cn2, long long noise_stride,
                             unsigned long long seed, unsigned long long env_id_base, unsigned long long draw_index) {
@@ -386,7 +388,7 @@ __global__ void k_ar_gather(const double* __restrict__ screens, const int* __res
   Z[(size_t)b * (Ns + Np) + j] = v;
 }
 
-__global__ void k_ar_scatter(double* __restrict__ screens, const double* __restrict__ newcol, int P, int Np,
+static __global__ void k_ar_scatter(double* __restrict__ screens, const double* __restrict__ newcol, int P, int Np,
                              int env0, int phys_col, int flipped) {
   const int b = blockIdx.y;
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,7 +401,7 @@ __global__ void k_ar_scatter(double* __restrict__ screens, const double* __restr
 // von-Karman screen synthesis (semi_dynamic reset; AO_env.py:76-77): spectral noise
 // X = C . (xi_r + i xi_i), then screen = Re[W X W^T] through the batched complex GEMM.
 // --------------------------------------------------------------------------------------
-__global__ void k_scr_noise(const double* __restrict__ C, double2* __restrict__ X, int count, long long strideX,
+static __global__ void k_scr_noise(const double* __restrict__ C, double2* __restrict__ X, int count, long long strideX,
                             int env0, unsigned long long seed, unsigned long long env_id_base,
                             unsigned long long draw_base) {
   const int b = blockIdx.y;
@@ -412,7 +414,7 @@ __global__ void k_scr_noise(const double* __restrict__ C, double2* __restrict__ 
   X[(size_t)b * strideX + i] = make_double2(c * z.x, c * z.y);
 }
 
-__global__ void k_scr_combine(double* __restrict__ screens, const double2* __restrict__ Y, int P, long long strideY,
+static __global__ void k_scr_combine(double* __restrict__ screens, const double2* __restrict__ Y, int P, long long strideY,
                               int env0, double scale, int accumulate) {
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -423,17 +425,17 @@ __global__ void k_scr_combine(double* __restrict__ screens, const double2* __res
 }
 
 // misc ---------------------------------------------------------------------------------
-__global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+static __global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (double)in[i];
 }
 
-__global__ void k_transpose_z(const double2* __restrict__ in, double2* __restrict__ out, int rows, int cols) {
+static __global__ void k_transpose_z(const double2* __restrict__ in, double2* __restrict__ out, int rows, int cols) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * cols) { int r = i / cols, c = i - r * cols; out[(size_t)c * rows + r] = in[i]; }
 }
 
-__global__ void k_build_arW(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ W,
+static __global__ void k_build_arW(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ W,
                             int Np, int Ns) {
   // W[j][y] = A[y][j] (j < Ns);  W[Ns + j][y] = B[y][j]
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -442,7 +444,7 @@ __global__ void k_build_arW(const double* __restrict__ A, const double* __restri
   W[i] = (j < Ns) ? A[(size_t)y * Ns + j] : Bm[(size_t)y * Np + (j - Ns)];
 }
 
-__global__ void k_focal_power(const double2* __restrict__ F, double* __restrict__ out, int n, double2 norm, double w) {
+static __global__ void k_focal_power(const double2* __restrict__ F, double* __restrict__ out, int n, double2 norm, double w) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double2 f = F[i];

@@ -20,7 +20,8 @@
  * Conventions: every function returns 0 on success or a negative aog_status; nothing throws
  * across the ABI; aog_last_error() gives the message of the last failure on that handle.
  * All arrays are dense, row-major, env-major ([num_envs][...]).  Complex tables are
- * interleaved (re, im) doubles.  `stream` is a cudaStream_t passed as void*; the `*_host`
+ * interleaved (re, im) doubles.  `stream` is a cudaStream_t passed as void*
+ * (NULL = the CUDA default stream); the `*_host`
  * variants take HOST pointers, do the host<->device copies themselves and synchronise.
  * A handle is not thread-safe.  There is no CPU fallback: every entry point needs the GPU.
  */
@@ -87,7 +88,10 @@ typedef enum aog_field {
   AOG_FIELD_FOCAL = 2,       /* [Nf*Nf] complex focal field on the fibre plane */
   AOG_FIELD_FOCAL_POWER = 3, /* [Nf*Nf] |E|^2 w   (render panel 3)  */
   AOG_FIELD_OBS_POWER = 4,   /* [n*n]   photodetector power (render panel 4) */
-  AOG_FIELD_ACTUATORS = 5    /* [K]     DM actuators after normalisation */
+  AOG_FIELD_ACTUATORS = 5,   /* [K]     DM actuators after normalisation */
+  /* tensor-path intermediates of the last step (tests / debugging), hi + lo recombined: */
+  AOG_FIELD_TC_PUPIL = 6,    /* [P]       complex, unit modulus x aperture */
+  AOG_FIELD_TC_STAGE1 = 7    /* [Nf*Np]   complex stage-1 product M1~ . E~ (unit-modulus twiddles) */
 } aog_field;
 
 typedef struct aog_config {
