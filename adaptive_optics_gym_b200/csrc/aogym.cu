@@ -146,7 +146,7 @@ int optics_chunk_f64(aog_env* env, int e0, int nB, bool flat_dm, bool with_rewar
   a.power = out.power ? out.power + e0 : nullptr;
   a.strehl = out.strehl ? out.strehl + e0 : nullptr;
   a.ssim = out.ssim ? out.ssim + e0 : nullptr;
-  k_finalize<<<nB, 64, 0, st>>>(a);
+  k_finalize<<<nB, 128, 0, st>>>(a);
   AOG_LAUNCH_CHECK();
   return AOG_OK;
 }

@@ -275,9 +275,10 @@ static __global__ void k_obs_rows_f64(const double2* __restrict__ E, const doubl
 // reward, threshold (AO_env.py:142-153, 468-503).  Block per env.
 // --------------------------------------------------------------------------------------
 struct FinalizeArgs {
-  const double2* R; const double2* m1o; const double2* coef; const double2* lpphase; const double* lpgram;
+  const double2* R; const float2* R4; const double2* m1o; const double2* coef; const double2* lpphase; const double* lpgram;
   const double2* strehl_part; int strehl_blocks;
   int Np, n, J, rew_type, has_thr, compute_reward;
+  int r4_parts;        // partial sums per contraction index in R4
   int transpose_out;   // R / table hold the transposed contraction: result (a, b) is obs pixel (v = b, u = a)
   double thr, obs_weight, strehl_scale, ssim_peak;
   double2 norm;
@@ -307,21 +308,42 @@ static __global__ void k_finalize(FinalizeArgs a) {
   __shared__ double obs[AOG_MAX_OBS * AOG_MAX_OBS];
   const int b = blockIdx.x;
   const int n2 = a.n * a.n;
-  for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+  // one warp per photodetector pixel, lanes split the contraction index, FP64 accumulation
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int t = warp; t < n2; t += nwarps) {
     const int v = t / a.n, u = t - v * a.n;
     double re = 0.0, im = 0.0;
-    const double2* r = a.R + (size_t)b * a.Np * a.n;
-    for (int y = 0; y < a.Np; ++y) {
-      const double2 m = a.m1o[(size_t)v * a.Np + y], e = r[(size_t)y * a.n + u];
-      re += m.x * e.x - m.y * e.y;
-      im += m.x * e.y + m.y * e.x;
+    if (a.R4) {   // tensor path: r4_parts FP32 partial sums per contraction index
+      const float2* r4 = a.R4 + (size_t)b * a.Np * a.r4_parts * a.n;
+      for (int y = lane; y < a.Np; y += 32) {
+        const double2 m = a.m1o[(size_t)v * a.Np + y];
+        double ex = 0.0, ey = 0.0;
+        for (int qq = 0; qq < a.r4_parts; ++qq) {
+          const float2 t4 = r4[((size_t)y * a.r4_parts + qq) * a.n + u];
+          ex += (double)t4.x;
+          ey += (double)t4.y;
+        }
+        re += m.x * ex - m.y * ey;
+        im += m.x * ey + m.y * ex;
+      }
+    } else {
+      const double2* r = a.R + (size_t)b * a.Np * a.n;
+      for (int y = lane; y < a.Np; y += 32) {
+        const double2 m = a.m1o[(size_t)v * a.Np + y], e = r[(size_t)y * a.n + u];
+        re += m.x * e.x - m.y * e.y;
+        im += m.x * e.y + m.y * e.x;
+      }
     }
-    const double fr = re * a.norm.x - im * a.norm.y, fi = re * a.norm.y + im * a.norm.x;
-    const double pw = (fr * fr + fi * fi) * a.obs_weight;
-    const int to = a.transpose_out ? (u * a.n + v) : t;
-    obs[to] = pw;
-    if (a.obs64) a.obs64[(size_t)b * n2 + to] = pw;
-    if (a.obs16) a.obs16[(size_t)b * n2 + to] = __half_as_ushort(__double2half(pw));
+    re = warp_sum(re);
+    im = warp_sum(im);
+    if (lane == 0) {
+      const double fr = re * a.norm.x - im * a.norm.y, fi = re * a.norm.y + im * a.norm.x;
+      const double pw = (fr * fr + fi * fi) * a.obs_weight;
+      const int to = a.transpose_out ? (u * a.n + v) : t;
+      obs[to] = pw;
+      if (a.obs64) a.obs64[(size_t)b * n2 + to] = pw;
+      if (a.obs16) a.obs16[(size_t)b * n2 + to] = __half_as_ushort(__double2half(pw));
+    }
   }
   __syncthreads();
   if (threadIdx.x != 0 || !a.compute_reward) return;

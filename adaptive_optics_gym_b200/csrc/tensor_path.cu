@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -43,16 +44,26 @@ struct TensorState {
   __half* E_hi = nullptr; __half* E_lo = nullptr;     // [chunk][240][480]  pupil field, x-major
   __half* T_hi = nullptr; __half* T_lo = nullptr;     // [chunk][128][480]  stage-1 product
   float* lpw = nullptr;                               // [J][128][128] fibre modes * weight / max
-  float* screensT = nullptr;                          // [B][Np][Np] FP32, x-major (transposed), ring-buffered
-  float* modesT = nullptr;                            // [K][Np][Np] FP32 transposed
-  float* apT = nullptr;                               // [Np][Np]
+  // atmospheric phase / pi reduced to [-1, 1], FP32, tiled for the field kernel's bulk prefetch:
+  // [env / 32][Np xp][Np / 16 chunks][2 = {lambda_wfs, lambda_sci}][32 envs][16 pixels], ring-buffered in xp,
+  // the four 16-byte pieces of each env row pre-swizzled (piece j at j ^ ((env >> 1) & 3)) so the
+  // shared-memory image is bank-conflict free.
+  float* hwt = nullptr;
+  __half* modesK_hi = nullptr; __half* modesK_lo = nullptr;   // [Np x][Np y][KPAD] DM modes, k contiguous (GEMM B operand)
+  __half* act_hi = nullptr; __half* act_lo = nullptr;         // [chunk rows padded to 128][KPAD] actuators * 4 / lambda_wfs
+  uint16_t* apmask = nullptr;                         // [Np x][Np / 16] aperture bits of each 16-pixel column chunk
+  float2* m1o32 = nullptr;                            // [n][Np] first obs-arm table in FP32
+  float2* R4 = nullptr;                               // [chunk][Np x][FK_PARTS][n] obs-arm column partial sums
+  int kpad = 64;
+  int act_rows = 128;
   double2* m2oT = nullptr;                            // [n][Np] transposed obs table
   int* err_flag = nullptr;                            // device flag set by a timed-out barrier wait
   CUtensorMap tmA1_hi, tmA1_lo, tmE_hi, tmE_lo, tmT_hi, tmT_lo, tmB2_hi, tmB2_lo;
+  CUtensorMap tmAct_hi, tmAct_lo, tmModes_hi, tmModes_lo;
   double pupil_weight = 0.0;                          // |M1| (grid weight folded in the table)
   double lpw_scale = 0.0;
   int num_sms = 148;
-  bool have_m1 = false, have_m2 = false, have_lp = false, have_modes = false, have_ap = false, have_m2o = false;
+  bool have_m1 = false, have_m2 = false, have_lp = false, have_modes = false, have_ap = false, have_m2o = false, have_m1o = false;
 };
 
 TensorState* TS(aog_env* env) { return reinterpret_cast<TensorState*>(env->tensor_state); }
@@ -81,11 +92,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (the launch fails, the GPU stays usable), never hang.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if (++spins > (1u << 24)) {            // seconds: a protocol bug, not a slow producer
       atomicExch(err_flag, code);
       __threadfence_system();
       asm volatile("trap;");
@@ -166,7 +179,7 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
   constexpr uint32_t IDESC = umma_idesc_f16(128, N_TILE);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint64_t* full = reinterpret_cast<uint64_t*>(base + NUM_STAGES * STAGE_BYTES);
   uint64_t* empty = full + NUM_STAGES;
   uint64_t* tmem_full = empty + NUM_STAGES;
@@ -264,7 +277,6 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
       tc_fence_after();
       if constexpr (MODE == 0) {
         // stage-1 product -> split fp16, row-major [v][k] with k = (x | 240 + x)
-        const size_t rbase = ((size_t)item * 128 + row) * TC_K;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
 #pragma unroll 1
@@ -281,12 +293,21 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
               hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
               lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
             }
-            uint4* dh = reinterpret_cast<uint4*>(p.T_hi + rbase + h * TC_NP + c * 16);
-            uint4* dl = reinterpret_cast<uint4*>(p.T_lo + rbase + h * TC_NP + c * 16);
-            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            // full-sector stores: lane pairs (rows v, v+1) swap halves so each instruction writes whole
+            // 32-byte sectors instead of two half-sector partial writes per row
+            const bool odd = lane & 1;
+            const size_t r_even = ((size_t)item * 128 + (row & ~1)) * TC_K + h * TC_NP + c * 16 + (odd ? 8 : 0);
+            const size_t r_odd = r_even + TC_K;
+            uint32_t xh[4], xl[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              xh[k] = __shfl_xor_sync(0xffffffffu, odd ? hi[k] : hi[4 + k], 1);
+              xl[k] = __shfl_xor_sync(0xffffffffu, odd ? lo[k] : lo[4 + k], 1);
+            }
+            *reinterpret_cast<uint4*>(p.T_hi + r_even) = odd ? make_uint4(xh[0], xh[1], xh[2], xh[3]) : make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(p.T_lo + r_even) = odd ? make_uint4(xl[0], xl[1], xl[2], xl[3]) : make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(p.T_hi + r_odd) = odd ? make_uint4(hi[4], hi[5], hi[6], hi[7]) : make_uint4(xh[0], xh[1], xh[2], xh[3]);
+            *reinterpret_cast<uint4*>(p.T_lo + r_odd) = odd ? make_uint4(lo[4], lo[5], lo[6], lo[7]) : make_uint4(xl[0], xl[1], xl[2], xl[3]);
           }
         }
         tc_fence_before();
@@ -365,162 +386,413 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
 }
 
 // ----------------------------------------------------------------------------- field kernel
-// DM surface + pupil field (unit modulus, split fp16, x-major) + Strehl partial sums + obs-arm
-// column products, FP32 phase / FP64 reductions.  Block = 4 pupil columns x 64 threads (60 active,
-// 4 consecutive y each) looping over ET envs, so each mode value is loaded once per ET envs.
-// grid (Np / 4, ceil(nB / ET)), block 256.
-template <int ET>
-__global__ void __launch_bounds__(256)
-k_field_tc(const float* __restrict__ screensT, const double* __restrict__ act, const float* __restrict__ modesT,
-           const float* __restrict__ apT, const double2* __restrict__ m1o, __half* __restrict__ E_hi,
-           __half* __restrict__ E_lo, double2* __restrict__ R, double2* __restrict__ strehl_part, int K, int n,
-           int env0, int nB, int col_origin, double turns_wfs_S, double turns_wfs_s, double turns_sci_S,
-           double turns_sci_s, int do_strehl) {
-  constexpr int Np = TC_NP;
-  extern __shared__ float sh_act[];                      // [ET][K]
-  __shared__ double red[ET][4][2][2 * AOG_MAX_OBS + 2];  // [env][column][warp of the column][obs re/im.., strehl re/im]
-  const int e0 = blockIdx.y * ET;
-  for (int i = threadIdx.x; i < ET * K; i += blockDim.x) {
-    const int e = i / K, k = i - e * K;
-    sh_act[i] = (e0 + e < nB) ? (float)act[(size_t)(env0 + e0 + e) * K + k] : 0.f;
-  }
-  __syncthreads();
-  const int colw = threadIdx.x >> 6;                     // 0..3 column within the block
-  const int t = threadIdx.x & 63;                        // 0..63, active < 60
-  const int x = blockIdx.x * 4 + colw;                   // logical pupil column
-  const int y0 = 4 * t;
-  const bool active = t < Np / 4;
-  int xp = x + col_origin;
-  if (xp >= Np) xp -= Np;
-  float4 ap = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) ap = *reinterpret_cast<const float4*>(apT + (size_t)x * Np + y0);
-  const bool lit = active && (ap.x + ap.y + ap.z + ap.w) > 0.f;
+// k_dm_field_tc: DM surface as a tensor-core GEMM with the whole field formation in its epilogue
+// (reference AO_env.py:119-120 surface, :132-135 atmosphere + DM phase, :139 obs arm, :479-483
+// Strehl sum).
+//
+//   D[env][y] (half-turns of DM phase at lambda_wfs) = act'[env][k] . modes[x][y][k]      per pupil column x
+//
+// A = 128 envs x KPAD (actuators scaled by 4 / lambda_wfs, split fp16), B = the 240 pixels of column x
+// (split fp16 modes, k contiguous), accumulator = 128 TMEM lanes (envs) x 240 columns (pixels), double
+// buffered (2 x 256 columns).  12 epilogue warps (3 per TMEM lane group, each a third of the column)
+// own ONE ENV PER THREAD: add the atmospheric half-turns, sincospif, apply the aperture, split to
+// fp16 hi/lo and store the stage-1 B operand E[env][x][y | 240 + y], accumulate the obs-arm column
+// products and the Strehl sum in registers -- no shuffles, no FP64 in the loop.
+// Work item = (block of 128 envs, column x); each CTA takes a contiguous range of items.
+constexpr int FK_STAGES = 1;                            // the double-buffered TMEM accumulator hides the operand load
+constexpr int FK_A_TILE = 128 * 64 * 2;                 // 16 KB: 128 env rows x 128 B
+constexpr int FK_B_TILE = 256 * 64 * 2;                 // 32 KB slot (240 rows used)
+constexpr int FK_STAGE_BYTES = 2 * FK_A_TILE + 2 * FK_B_TILE;   // 96 KB
+constexpr int FK_EPI_WARPS = 12;                        // 3 per TMEM lane group: 5 of the 15 column chunks each
+constexpr int FK_PARTS = FK_EPI_WARPS / 4;
+constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
+constexpr int FK_SLOTS = 16;                            // Strehl partial slots per env (>= CTAs touching an env block)
+constexpr int FK_MIN_ITEMS = 16;                        // items per CTA at least (bounds the slots)
+constexpr int FK_PF_TILE = 32 * 16 * 4;                 // 2 KB: 32 envs x 16 pixels of phase (one TMA box)
+constexpr int FK_PF_BYTES = FK_EPI_WARPS * 2 * 2 * FK_PF_TILE;   // per warp: 2 buffers x {wfs, sci}
+constexpr int FK_AUX_BAR = 256;
 
-  float s[ET][4];
-#pragma unroll
-  for (int e = 0; e < ET; ++e) s[e][0] = s[e][1] = s[e][2] = s[e][3] = 0.f;
-  if (lit) {
-    const float* mp = modesT + (size_t)x * Np + y0;
-    for (int k = 0; k < K; ++k) {
-      const float4 m = __ldg(reinterpret_cast<const float4*>(mp + (size_t)k * Np * Np));
-#pragma unroll
-      for (int e = 0; e < ET; ++e) {
-        const float a = sh_act[e * K + k];
-        s[e][0] = fmaf(m.x, a, s[e][0]);
-        s[e][1] = fmaf(m.y, a, s[e][1]);
-        s[e][2] = fmaf(m.z, a, s[e][2]);
-        s[e][3] = fmaf(m.w, a, s[e][3]);
-      }
-    }
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;   // 8 rows x 128 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;             // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+// sin / cos of pi * a for |a| up to a few half-turns: reduce to [-1/2, 1/2] turns exactly in FP32, then the
+// SFU (MUFU.SIN / MUFU.COS, abs error 2^-21.4 on [-pi, pi] -- below the FP32 phase rounding already present).
+__device__ __forceinline__ void fast_sincospi(float a, float* s, float* c) {
+  const float t = 0.5f * a;
+  const float x = (t - rintf(t)) * 6.283185307179586f;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(x));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(x));
+}
+
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+struct FieldParams {
+  int num_envs;          // envs in this chunk
+  int num_items;         // env blocks x 240 columns
+  int items_per_cta;
+  int nkb;               // KPAD / 64
+  int n;                 // obs_dim
+  int col_origin;
+  int do_strehl;
+  int env0;              // first env of the chunk (index into hw / hs)
+  int dbg;               // AOG_FK_DEBUG bits (tuning experiments only): 1 no E stores, 2 no prefetch, 4 no TMEM load, 8 no fence
+  float sci_ratio;       // lambda_wfs / lambda_sci
+  const float* hwt;     // tiled phase array (see TensorState::hwt)
+  const uint16_t* apmask;
+  const float2* m1o32;
+  __half* E_hi; __half* E_lo;
+  float2* R4;
+  double2* strehl_part;  // [env][FK_SLOTS]
+  int* err_flag;
+};
+
+template <bool STREHL, int NOBS>
+__global__ void __launch_bounds__(FK_THREADS, 1)
+k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constant__ CUtensorMap tmAct_lo,
+              const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
+              const FieldParams p) {
+  constexpr int Np = TC_NP;
+  constexpr uint32_t TX_BYTES = 2 * FK_A_TILE + 2 * Np * 64 * 2;
+  constexpr uint32_t IDESC = umma_idesc_f16(128, Np);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
+  uint8_t* pf = base + FK_STAGES * FK_STAGE_BYTES;                       // phase prefetch ring of the epilogue warps
+  uint8_t* aux = pf + FK_PF_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty = full + FK_STAGES;
+  uint64_t* tmem_full = empty + FK_STAGES;       // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint64_t* pfbar = tmem_empty + 2;              // [FK_EPI_WARPS][2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pfbar + 2 * FK_EPI_WARPS);
+  double2* sred = reinterpret_cast<double2*>(aux + FK_AUX_BAR);          // [FK_PARTS][128 envs]
+  float2* m1o_s = reinterpret_cast<float2*>(aux + FK_AUX_BAR + FK_PARTS * 128 * sizeof(double2));   // [n][Np]
+  uint16_t* apmask_s = reinterpret_cast<uint16_t*>(m1o_s + NOBS * Np);  // [Np][Np / 16]
+  uint8_t* run_s = reinterpret_cast<uint8_t*>(apmask_s + Np * (Np / 16));   // [Np][2]: first lit chunk, lit count
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item_lo = blockIdx.x * p.items_per_cta;
+  const int item_hi = min(p.num_items, item_lo + p.items_per_cta);
+
+  for (int i = threadIdx.x; i < NOBS * Np; i += blockDim.x) m1o_s[i] = p.m1o32[i];
+  for (int i = threadIdx.x; i < Np * (Np / 16); i += blockDim.x) apmask_s[i] = p.apmask[i];
+  for (int xx = threadIdx.x; xx < Np; xx += blockDim.x) {
+    int first = 0, cnt = 0;
+    for (int c = 0; c < Np / 16; ++c)
+      if (p.apmask[xx * (Np / 16) + c]) { if (!cnt) first = c; ++cnt; }
+    run_s[2 * xx] = (uint8_t)first;
+    run_s[2 * xx + 1] = (uint8_t)cnt;     // the aperture is convex: the lit chunks are contiguous
   }
-  // obs-arm table rows for this thread's 4 pixels: m1o[v][y0..y0+3]
-  const float apv[4] = {ap.x, ap.y, ap.z, ap.w};
-  const int wcol = (threadIdx.x >> 5) & 1;               // which of the column's two warps
-#pragma unroll
-  for (int e = 0; e < ET; ++e) {
-    const bool env_ok = e0 + e < nB;
-    float cs[4] = {0.f, 0.f, 0.f, 0.f}, sn[4] = {0.f, 0.f, 0.f, 0.f};
-    double st_re = 0.0, st_im = 0.0;
-    if (lit && env_ok) {
-      const float4 S4 = *reinterpret_cast<const float4*>(screensT + ((size_t)(env0 + e0 + e) * Np + xp) * Np + y0);
-      const float Sv[4] = {S4.x, S4.y, S4.z, S4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // phase in turns, reduced to [-1/2, 1/2] in FP64, then sin/cos(2 pi t) in FP32
-        double tw = (double)Sv[i] * turns_wfs_S + (double)s[e][i] * turns_wfs_s;
-        tw -= rint(tw);
-        float sv, cv;
-        sincospif((float)(2.0 * tw), &sv, &cv);
-        cs[i] = cv * apv[i];
-        sn[i] = sv * apv[i];
-        if (do_strehl) {
-          double ts = (double)Sv[i] * turns_sci_S + (double)s[e][i] * turns_sci_s;
-          ts -= rint(ts);
-          sincospif((float)(2.0 * ts), &sv, &cv);
-          st_re += (double)(cv * apv[i]);
-          st_im += (double)(sv * apv[i]);
-        }
-      }
-    }
-    if (active && env_ok) {
-      // split fp16 operand rows: E[x][k = y] = re, E[x][k = 240 + y] = im
-      uint32_t hr[2], lr[2], hi_[2], li_[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const __half a0 = __float2half_rn(cs[2 * i]), a1 = __float2half_rn(cs[2 * i + 1]);
-        const __half b0 = __float2half_rn(cs[2 * i] - __half2float(a0)), b1 = __float2half_rn(cs[2 * i + 1] - __half2float(a1));
-        const __half c0 = __float2half_rn(sn[2 * i]), c1 = __float2half_rn(sn[2 * i + 1]);
-        const __half d0 = __float2half_rn(sn[2 * i] - __half2float(c0)), d1 = __float2half_rn(sn[2 * i + 1] - __half2float(c1));
-        hr[i] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(a1) << 16);
-        lr[i] = (uint32_t)__half_as_ushort(b0) | ((uint32_t)__half_as_ushort(b1) << 16);
-        hi_[i] = (uint32_t)__half_as_ushort(c0) | ((uint32_t)__half_as_ushort(c1) << 16);
-        li_[i] = (uint32_t)__half_as_ushort(d0) | ((uint32_t)__half_as_ushort(d1) << 16);
-      }
-      const size_t o = ((size_t)(e0 + e) * Np + x) * TC_K + y0;
-      *reinterpret_cast<uint2*>(E_hi + o) = make_uint2(hr[0], hr[1]);
-      *reinterpret_cast<uint2*>(E_lo + o) = make_uint2(lr[0], lr[1]);
-      *reinterpret_cast<uint2*>(E_hi + o + Np) = make_uint2(hi_[0], hi_[1]);
-      *reinterpret_cast<uint2*>(E_lo + o + Np) = make_uint2(li_[0], li_[1]);
-    }
-    // obs arm: r[v] = sum_y m1o[v][y] E[y][x] over this thread's pixels, then over the column
-    for (int v = 0; v < n; ++v) {
-      double re = 0.0, im = 0.0;
-      if (lit && env_ok) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double2 m = m1o[(size_t)v * Np + y0 + i];
-          re += m.x * (double)cs[i] - m.y * (double)sn[i];
-          im += m.x * (double)sn[i] + m.y * (double)cs[i];
-        }
-      }
-      re = warp_sum(re);
-      im = warp_sum(im);
-      if ((threadIdx.x & 31) == 0) { red[e][colw][wcol][2 * v] = re; red[e][colw][wcol][2 * v + 1] = im; }
-    }
-    if (do_strehl) {
-      st_re = warp_sum(st_re);
-      st_im = warp_sum(st_im);
-      if ((threadIdx.x & 31) == 0) { red[e][colw][wcol][2 * n] = st_re; red[e][colw][wcol][2 * n + 1] = st_im; }
-    }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2 * FK_EPI_WARPS; ++s) mbar_init(&pfbar[s], 1);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAct_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAct_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmM_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmM_lo)) : "memory");
+    for (int s = 0; s < FK_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], FK_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
   __syncthreads();
-  // column sums -> R[env][x][v];  block Strehl partial -> strehl_part[env][blockIdx.x]
-  for (int i = threadIdx.x; i < ET * 4 * n; i += blockDim.x) {
-    const int e = i / (4 * n), r = i - e * 4 * n, c = r / n, v = r - c * n;
-    if (e0 + e < nB) {
-      const double re = red[e][c][0][2 * v] + red[e][c][1][2 * v];
-      const double im = red[e][c][0][2 * v + 1] + red[e][c][1][2 * v + 1];
-      R[((size_t)(e0 + e) * Np + blockIdx.x * 4 + c) * n + v] = make_double2(re, im);
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = item_lo; item < item_hi; ++item) {
+        const int eb = item / Np, x = item - eb * Np;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait<200>(&empty[stage], phase ^ 1, p.err_flag, 11);
+          mbar_expect_tx(&full[stage], TX_BYTES);
+          const uint32_t s0 = smem_u32(base + stage * FK_STAGE_BYTES);
+          tma_load_2d(s0, &tmAct_hi, &full[stage], kb * 64, eb * 128);
+          tma_load_2d(s0 + FK_A_TILE, &tmAct_lo, &full[stage], kb * 64, eb * 128);
+          tma_load_2d(s0 + 2 * FK_A_TILE, &tmM_hi, &full[stage], kb * 64, x * Np);
+          tma_load_2d(s0 + 2 * FK_A_TILE + FK_B_TILE, &tmM_lo, &full[stage], kb * 64, x * Np);
+          if (++stage == FK_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
     }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = item_lo; item < item_hi; ++item, ++it) {
+        const int as = it & 1;
+        mbar_wait<200>(&tmem_empty[as], ((it >> 1) & 1) ^ 1, p.err_flag, 12);
+        tc_fence_after();
+        const uint32_t d = tmem_base + as * 256;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait<100>(&full[stage], phase, p.err_flag, 13);
+          tc_fence_after();
+          const uint32_t s0 = smem_u32(base + stage * FK_STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t a_hi = umma_desc_sw128(s0 + ks * 32);
+            const uint64_t a_lo = umma_desc_sw128(s0 + FK_A_TILE + ks * 32);
+            const uint64_t b_hi = umma_desc_sw128(s0 + 2 * FK_A_TILE + ks * 32);
+            const uint64_t b_lo = umma_desc_sw128(s0 + 2 * FK_A_TILE + FK_B_TILE + ks * 32);
+            tc_mma_f16(d, a_hi, b_hi, IDESC, (kb | ks) != 0);
+            tc_mma_f16(d, a_hi, b_lo, IDESC, 1);
+            tc_mma_f16(d, a_lo, b_hi, IDESC, 1);
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == FK_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue: one env per thread =====================
+    const int ew = warp - 2;                  // 0..11
+    const int lg = warp & 3;                  // TMEM lane group this warp may touch
+    const int q = ew >> 2;                    // takes lit chunks first + q, first + q + 3, ... of every column
+    const int row = lg * 32 + lane;           // env within the block
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    double st_re = 0.0, st_im = 0.0;
+    int cur_eb = -1;
+    int it = 0;
+
+    // Phase prefetch: the warp's 32 envs x 16 pixels of atmospheric half-turns (and the science-band copy)
+    // are one contiguous, pre-swizzled 2 KB (4 KB) tile: a single cp.async.bulk one chunk ahead of the arithmetic.
+    const uint32_t pf_warp = smem_u32(pf + ew * (4 * FK_PF_TILE));
+    const uint8_t* pf_warp_ptr = pf + ew * (4 * FK_PF_TILE);
+    uint64_t* pbar = pfbar + 2 * ew;
+    uint32_t pphase0 = 0, pphase1 = 0;
+    int buf = 0;
+    int n_item = item_lo - 1, n_ci = 0, n_end = 0;       // prefetch cursor: chunk n_ci of item n_item
+    auto next_lit = [&]() -> bool {
+      n_ci += FK_PARTS;
+      while (n_ci >= n_end) {
+        if (++n_item >= item_hi) return false;
+        const int xx = n_item - (n_item / Np) * Np;
+        n_ci = run_s[2 * xx] + q;
+        n_end = run_s[2 * xx] + run_s[2 * xx + 1];
+      }
+      return true;
+    };
+    auto issue_prefetch = [&](int b) {
+      if (lane == 0) {
+        const int eb2 = n_item / Np, x2 = n_item - eb2 * Np;
+        int xp2 = x2 + p.col_origin;
+        if (xp2 >= Np) xp2 -= Np;
+        const size_t eb32 = (size_t)(p.env0 + eb2 * 128 + lg * 32) >> 5;
+        const float* src = p.hwt + ((eb32 * Np + xp2) * (Np / 16) + n_ci) * (2 * 32 * 16);
+        constexpr uint32_t bytes = STREHL ? 2 * FK_PF_TILE : FK_PF_TILE;
+        if (!(p.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&pbar[b], bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(pf_warp + b * 2 * FK_PF_TILE), "l"(src), "r"(bytes), "r"(smem_u32(&pbar[b])) : "memory");
+      }
+    };
+    bool n_ok = next_lit();
+    if (n_ok && !(p.dbg & 2)) issue_prefetch(0);
+
+    auto flush_strehl = [&](int eb) {
+      // combine the 4 quarter-warps of every env, one partial per (env, CTA slot)
+      sred[q * 128 + row] = make_double2(st_re, st_im);
+      asm volatile("bar.sync 1, %0;" ::"n"(FK_EPI_WARPS * 32) : "memory");
+      if (q == 0) {
+        const int env = eb * 128 + row;
+        if (env < p.num_envs) {
+          double2 a = sred[row];
+          for (int k = 1; k < FK_PARTS; ++k) { a.x += sred[k * 128 + row].x; a.y += sred[k * 128 + row].y; }
+          const int slot = blockIdx.x - (eb * Np) / p.items_per_cta;
+          p.strehl_part[(size_t)env * FK_SLOTS + slot] = a;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(FK_EPI_WARPS * 32) : "memory");
+      st_re = st_im = 0.0;
+    };
+
+    for (int item = item_lo; item < item_hi; ++item, ++it) {
+      const int eb = item / Np, x = item - eb * Np;
+      if (STREHL && eb != cur_eb) {
+        if (cur_eb >= 0) flush_strehl(cur_eb);
+        cur_eb = eb;
+      }
+      const int as = it & 1;
+      const int env = eb * 128 + row;
+      const bool valid = env < p.num_envs;
+      int xp = x + p.col_origin;
+      if (xp >= Np) xp -= Np;
+      mbar_wait(&tmem_full[as], (it >> 1) & 1, p.err_flag, 14);
+      tc_fence_after();
+      float obs_re[NOBS], obs_im[NOBS];
+#pragma unroll
+      for (int v = 0; v < NOBS; ++v) obs_re[v] = obs_im[v] = 0.f;
+      float sre = 0.f, sim = 0.f;
+      const int run_first = run_s[2 * x], run_end = run_first + run_s[2 * x + 1];
+#pragma unroll 1
+      for (int ci = run_first + q; ci < run_end; ci += FK_PARTS) {       // warp-uniform: only lit chunks
+        const uint32_t mask = apmask_s[x * (Np / 16) + ci];
+        const int y0 = ci * 16;
+        float d[16];
+        if (!(p.dbg & 4)) tc_ld16(lane_addr + as * 256 + y0, d);
+        else { for (int j = 0; j < 16; ++j) d[j] = 0.01f * j; }
+        // this chunk's phases were requested one chunk ago; request the next lit chunk now
+        const int cb = buf;
+        __syncwarp();
+        if (!(p.dbg & 2)) {
+        n_ok = next_lit();
+        if (n_ok) issue_prefetch(cb ^ 1);
+        if (cb == 0) { mbar_wait(&pbar[0], pphase0, p.err_flag, 15); pphase0 ^= 1; }
+        else         { mbar_wait(&pbar[1], pphase1, p.err_flag, 16); pphase1 ^= 1; }
+        }
+        buf ^= 1;
+        const uint8_t* tile = pf_warp_ptr + cb * 2 * FK_PF_TILE + lane * 64;
+        const int sw = (lane >> 1) & 3;                                   // pieces were stored at j ^ ((env >> 1) & 3)
+        float h[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(tile + ((j ^ sw) << 4));
+          h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w;
+        }
+        tc_wait_ld();
+        uint32_t rh[8], rl[8], ih[8], il[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float c0, s0, c1, s1;
+          fast_sincospi(d[2 * j] + h[2 * j], &s0, &c0);
+          fast_sincospi(d[2 * j + 1] + h[2 * j + 1], &s1, &c1);
+          if (!((mask >> (2 * j)) & 1u)) { c0 = 0.f; s0 = 0.f; }
+          if (!((mask >> (2 * j + 1)) & 1u)) { c1 = 0.f; s1 = 0.f; }
+          split_pack2(c0, c1, rh[j], rl[j]);
+          split_pack2(s0, s1, ih[j], il[j]);
+#pragma unroll
+          for (int v = 0; v < NOBS; ++v) {
+            const float2 m0 = m1o_s[v * Np + y0 + 2 * j], m1 = m1o_s[v * Np + y0 + 2 * j + 1];
+            obs_re[v] = fmaf(m0.x, c0, fmaf(-m0.y, s0, obs_re[v]));
+            obs_im[v] = fmaf(m0.x, s0, fmaf(m0.y, c0, obs_im[v]));
+            obs_re[v] = fmaf(m1.x, c1, fmaf(-m1.y, s1, obs_re[v]));
+            obs_im[v] = fmaf(m1.x, s1, fmaf(m1.y, c1, obs_im[v]));
+          }
+        }
+        if (!(p.dbg & 1)) {
+          // Full-sector stores: a lane's 16 pixels of one operand row are 32 contiguous bytes, but a thread
+          // stores at most 16.  Lane pairs swap halves so that each store instruction writes whole 32-byte
+          // sectors (lanes 2i, 2i+1 -> the two halves of env 2i's sector, then of env 2i+1's).
+          const bool odd = lane & 1;
+          const bool valid_even = (env & ~1) < p.num_envs, valid_odd = (env | 1) < p.num_envs;
+          const size_t erow_even = ((size_t)(env & ~1) * Np + x) * TC_K + y0 + (odd ? 8 : 0);
+          const size_t erow_odd = erow_even + (size_t)Np * TC_K;
+          auto store_pair = [&](__half* dst, const uint32_t* a) {
+            uint32_t r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k] = __shfl_xor_sync(0xffffffffu, odd ? a[k] : a[4 + k], 1);
+            // even lane: own[0..3] -> env 2i first half;  received = env 2i+1's first half
+            // odd lane : received = env 2i's second half;  own[4..7] -> env 2i+1 second half
+            if (valid_even)
+              *reinterpret_cast<uint4*>(dst + erow_even) = odd ? make_uint4(r[0], r[1], r[2], r[3]) : make_uint4(a[0], a[1], a[2], a[3]);
+            if (valid_odd)
+              *reinterpret_cast<uint4*>(dst + erow_odd) = odd ? make_uint4(a[4], a[5], a[6], a[7]) : make_uint4(r[0], r[1], r[2], r[3]);
+          };
+          store_pair(p.E_hi, rh);
+          store_pair(p.E_lo, rl);
+          store_pair(p.E_hi + Np, ih);
+          store_pair(p.E_lo + Np, il);
+        }
+        if (STREHL) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(tile + FK_PF_TILE + ((j ^ sw) << 4));
+            h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float c0, s0;
+            fast_sincospi(fmaf(d[j], p.sci_ratio, h[j]), &s0, &c0);
+            if ((mask >> j) & 1u) { sre += c0; sim += s0; }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);       // this warp is done with the accumulator
+      if (valid) {
+        float2* r = p.R4 + (((size_t)env * Np + x) * FK_PARTS + q) * NOBS;
+#pragma unroll
+        for (int v = 0; v < NOBS; ++v) r[v] = make_float2(obs_re[v], obs_im[v]);
+      }
+      if (STREHL) { st_re += (double)sre; st_im += (double)sim; }
+    }
+    if (STREHL && cur_eb >= 0) flush_strehl(cur_eb);
   }
-  if (do_strehl && threadIdx.x < ET && e0 + threadIdx.x < nB) {
-    double re = 0.0, im = 0.0;
-    for (int c = 0; c < 4; ++c)
-      for (int w = 0; w < 2; ++w) { re += red[threadIdx.x][c][w][2 * n]; im += red[threadIdx.x][c][w][2 * n + 1]; }
-    strehl_part[(size_t)(e0 + threadIdx.x) * gridDim.x + blockIdx.x] = make_double2(re, im);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
-// screens FP64 [B][y][xp] -> FP32 transposed [B][xp][y]   (full refresh)
-__global__ void k_screens_to_T(const double* __restrict__ src, float* __restrict__ dst, int Np) {
-  __shared__ float tile[32][33];
-  const size_t b = blockIdx.z;
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int y = y0 + j, x = x0 + threadIdx.x;
-    if (y < Np && x < Np) tile[j][threadIdx.x] = (float)src[(b * Np + y) * Np + x];
-  }
-  __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int x = x0 + j, y = y0 + threadIdx.x;
-    if (y < Np && x < Np) dst[(b * Np + x) * Np + y] = tile[threadIdx.x][j];
-  }
+// actuators (FP64, after normalisation) -> GEMM A operand: half-turn scale, split fp16, zero padded
+__global__ void k_act_pack(const double* __restrict__ act, __half* __restrict__ a_hi, __half* __restrict__ a_lo,
+                           int K, int kpad, int env0, int nB, int rows, double scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * kpad) return;
+  const int r = i / kpad, k = i - r * kpad;
+  const double v = (r < nB && k < K) ? act[(size_t)(env0 + r) * K + k] * scale : 0.0;
+  const __half h = __float2half_rn((float)v);
+  a_hi[i] = h;
+  a_lo[i] = __float2half_rn((float)(v - (double)__half2float(h)));
+}
+
+// screens FP64 [B][y][xp] -> tiled phase / pi at both wavelengths (layout: TensorState::hwt).
+// One thread per output float, output-ordered (coalesced writes, strided reads).
+__device__ __forceinline__ float reduce_halfturns(double S, double inv) {
+  double a = S * inv;
+  a -= 2.0 * rint(0.5 * a);
+  return (float)a;
+}
+__global__ void k_screens_to_tiles(const double* __restrict__ src, float* __restrict__ hwt, int Np, int B,
+                                   size_t total, double inv_w, double inv_s) {
+  const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= total) return;
+  const int e = o & 3, piece = (o >> 2) & 3, l = (o >> 4) & 31, arr = (o >> 9) & 1;
+  const size_t t = o >> 10;                       // ((eb32 * Np) + xp) * (Np / 16) + ci
+  const int ci = (int)(t % (Np / 16));
+  const size_t t2 = t / (Np / 16);
+  const int xp = (int)(t2 % Np);
+  const size_t env = (t2 / Np) * 32 + l;
+  const int y = ci * 16 + ((piece ^ ((l >> 1) & 3)) << 2) + e;
+  float v = 0.f;
+  if (env < (size_t)B) v = reduce_halfturns(src[(env * Np + y) * Np + xp], arr ? inv_s : inv_w);
+  hwt[o] = v;
 }
 // one physical column refresh after an extrusion
-__global__ void k_column_to_T(const double* __restrict__ src, float* __restrict__ dst, int Np, int phys_col) {
-  const size_t b = blockIdx.y;
-  const int y = blockIdx.x * blockDim.x + threadIdx.x;
-  if (y < Np) dst[(b * Np + phys_col) * Np + y] = (float)src[(b * Np + y) * Np + phys_col];
+__global__ void k_column_to_tiles(const double* __restrict__ src, float* __restrict__ hwt, int Np, int B, int phys_col,
+                                  double inv_w, double inv_s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over B * Np
+  if (i >= B * Np) return;
+  const int env = i / Np, y = i - env * Np;
+  const double S = src[((size_t)env * Np + y) * Np + phys_col];
+  const int l = env & 31, ci = y >> 4, piece = ((y >> 2) & 3) ^ ((l >> 1) & 3), e = y & 3;
+  const size_t tile = (((size_t)(env >> 5) * Np + phys_col) * (Np / 16) + ci) * (2 * 32 * 16);
+  hwt[tile + (size_t)l * 16 + piece * 4 + e] = reduce_halfturns(S, inv_w);
+  hwt[tile + 512 + (size_t)l * 16 + piece * 4 + e] = reduce_halfturns(S, inv_s);
 }
 
 // ----------------------------------------------------------------------------- host helpers
@@ -540,17 +812,20 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp16 row-major [rows][480] tensor, box = KB x box_rows, 64-byte swizzle.
-int make_map(aog_env* env, CUtensorMap* map, const __half* ptr, uint64_t rows, uint32_t box_rows) {
+// 2-D fp16 row-major [rows][inner] tensor, box = box_inner x box_rows; box_inner * 2 B is the swizzle span
+// (32 halves -> SWIZZLE_64B for the MFT operands, 64 halves -> SWIZZLE_128B for the DM GEMM operands).
+int make_map(aog_env* env, CUtensorMap* map, const __half* ptr, uint64_t rows, uint32_t box_rows,
+             uint64_t inner = TC_K, uint32_t box_inner = KB) {
   EncodeTiledFn enc = get_encode();
   if (!enc) AOG_FAIL(AOG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-  cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)TC_K * sizeof(__half)};
-  cuuint32_t box[2] = {(cuuint32_t)KB, box_rows};
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * sizeof(__half)};
+  cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) AOG_FAIL(AOG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return AOG_OK;
 }
@@ -604,10 +879,24 @@ int aog_tensor_create(aog_env* env) {
   AOG_CUDA(cudaMemset(ts->T_hi, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
   AOG_CUDA(cudaMemset(ts->T_lo, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
   A(talloc(env, &ts->lpw, (size_t)c.num_lp_modes * env->NF2));
-  A(talloc(env, &ts->screensT, B * P));
-  AOG_CUDA(cudaMemset(ts->screensT, 0, B * P * sizeof(float)));
-  A(talloc(env, &ts->modesT, (size_t)c.num_modes * P));
-  A(talloc(env, &ts->apT, P));
+  if (c.obs_dim > 8) AOG_FAIL(AOG_ERR_UNSUPPORTED, "tensor precision path supports obs_dim <= 8");
+  ts->kpad = ((c.num_modes + 63) / 64) * 64;
+  ts->act_rows = (int)((ch + 127) / 128) * 128;
+  {
+    const size_t tiles = ((B + 127) / 128) * 4 * TC_NP * (TC_NP / 16);   // whole 128-env blocks: the prefetch reads them all
+    A(talloc(env, &ts->hwt, tiles * 1024));
+    AOG_CUDA(cudaMemset(ts->hwt, 0, tiles * 1024 * sizeof(float)));
+  }
+  A(talloc(env, &ts->modesK_hi, P * ts->kpad));
+  A(talloc(env, &ts->modesK_lo, P * ts->kpad));
+  A(talloc(env, &ts->act_hi, (size_t)ts->act_rows * ts->kpad));
+  A(talloc(env, &ts->act_lo, (size_t)ts->act_rows * ts->kpad));
+  A(talloc(env, &ts->apmask, (size_t)TC_NP * (TC_NP / 16)));
+  A(talloc(env, &ts->m1o32, (size_t)c.obs_dim * TC_NP));
+  A(talloc(env, &ts->R4, ch * TC_NP * FK_PARTS * c.obs_dim));
+  // the field kernel only writes in-aperture chunks: everything else of E stays zero forever
+  AOG_CUDA(cudaMemset(ts->E_hi, 0, ch * TC_NP * TC_K * sizeof(__half)));
+  AOG_CUDA(cudaMemset(ts->E_lo, 0, ch * TC_NP * TC_K * sizeof(__half)));
   A(talloc(env, &ts->m2oT, (size_t)c.obs_dim * TC_NP));
   A(talloc(env, &ts->err_flag, 1));
   AOG_CUDA(cudaMemset(ts->err_flag, 0, sizeof(int)));
@@ -619,6 +908,10 @@ int aog_tensor_create(aog_env* env) {
   A(make_map(env, &ts->tmT_lo, ts->T_lo, (ch + 1) * 128, 128));
   A(make_map(env, &ts->tmB2_hi, ts->B2_hi, 256, 256));
   A(make_map(env, &ts->tmB2_lo, ts->B2_lo, 256, 256));
+  A(make_map(env, &ts->tmAct_hi, ts->act_hi, ts->act_rows, 128, ts->kpad, 64));
+  A(make_map(env, &ts->tmAct_lo, ts->act_lo, ts->act_rows, 128, ts->kpad, 64));
+  A(make_map(env, &ts->tmModes_hi, ts->modesK_hi, P, TC_NP, ts->kpad, 64));
+  A(make_map(env, &ts->tmModes_lo, ts->modesK_lo, P, TC_NP, ts->kpad, 64));
 #undef A
   AOG_CUDA(cudaFuncSetAttribute(k_mft_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   AOG_CUDA(cudaFuncSetAttribute(k_mft_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -629,7 +922,8 @@ void aog_tensor_destroy(aog_env* env) {
   TensorState* ts = TS(env);
   if (!ts) return;
   void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->E_hi, ts->E_lo, ts->T_hi, ts->T_lo, ts->lpw,
-                  ts->screensT, ts->modesT, ts->apT, ts->m2oT, ts->err_flag};
+                  ts->hwt, ts->modesK_hi, ts->modesK_lo, ts->act_hi, ts->act_lo, ts->apmask, ts->m1o32, ts->R4,
+                  ts->m2oT, ts->err_flag};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ts;
@@ -685,20 +979,30 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
     AOG_CUDA(cudaMemcpy(ts->lpw, f.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
     ts->have_lp = true;
   } else if (which == AOG_TABLE_DM_MODES) {
+    // modes [K][y][x] FP64 -> GEMM B operand [x][y][KPAD] split fp16 (k contiguous, zero padded)
     const double* m = static_cast<const double*>(host);
-    std::vector<float> f((size_t)c.num_modes * env->P);
+    const int kp = ts->kpad;
+    std::vector<double> f((size_t)env->P * kp, 0.0);
     for (int k = 0; k < c.num_modes; ++k)
       for (int y = 0; y < Np; ++y)
-        for (int x = 0; x < Np; ++x) f[((size_t)k * Np + x) * Np + y] = (float)m[((size_t)k * Np + y) * Np + x];
-    AOG_CUDA(cudaMemcpy(ts->modesT, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+        for (int x = 0; x < Np; ++x) f[((size_t)x * Np + y) * kp + k] = m[((size_t)k * Np + y) * Np + x];
+    int rc = upload_split(env, f, ts->modesK_hi, ts->modesK_lo);
+    if (rc) return rc;
     ts->have_modes = true;
   } else if (which == AOG_TABLE_APERTURE) {
     const double* m = static_cast<const double*>(host);
-    std::vector<float> f(env->P);
+    std::vector<uint16_t> bits((size_t)Np * (Np / 16), 0);
     for (int y = 0; y < Np; ++y)
-      for (int x = 0; x < Np; ++x) f[(size_t)x * Np + y] = (float)m[(size_t)y * Np + x];
-    AOG_CUDA(cudaMemcpy(ts->apT, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+      for (int x = 0; x < Np; ++x)
+        if (m[(size_t)y * Np + x] != 0.0) bits[(size_t)x * (Np / 16) + y / 16] |= (uint16_t)(1u << (y % 16));
+    AOG_CUDA(cudaMemcpy(ts->apmask, bits.data(), bits.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     ts->have_ap = true;
+  } else if (which == AOG_TABLE_MFT_OBS_1) {
+    const double* m = static_cast<const double*>(host);   // [n][Np] complex
+    std::vector<float2> f((size_t)c.obs_dim * Np);
+    for (size_t i = 0; i < f.size(); ++i) f[i] = make_float2((float)m[2 * i], (float)m[2 * i + 1]);
+    AOG_CUDA(cudaMemcpy(ts->m1o32, f.data(), f.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    ts->have_m1o = true;
   } else if (which == AOG_TABLE_MFT_OBS_2) {
     const double* m = static_cast<const double*>(host);   // [Np][n] complex -> [n][Np]
     const int n = c.obs_dim;
@@ -716,9 +1020,12 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
 
 int aog_tensor_screens_updated(aog_env* env) {
   TensorState* ts = TS(env);
-  const int Np = TC_NP;
-  dim3 g(cdiv(Np, 32), cdiv(Np, 32), env->cfg.num_envs), b(32, 8);
-  k_screens_to_T<<<g, b>>>(env->screens, ts->screensT, Np);
+  const int Np = TC_NP, B = env->cfg.num_envs;
+  const double pi = 3.14159265358979323846;
+  const size_t total = (size_t)((B + 127) / 128) * 4 * Np * (Np / 16) * 1024;
+  k_screens_to_tiles<<<(unsigned)((total + 255) / 256), 256>>>(env->screens, ts->hwt, Np, B, total,
+                                                              1.0 / (env->cfg.wavelength_wfs * pi),
+                                                              1.0 / (env->cfg.wavelength_sci * pi));
   AOG_LAUNCH_CHECK();
   AOG_CUDA(cudaDeviceSynchronize());
   return AOG_OK;
@@ -726,8 +1033,11 @@ int aog_tensor_screens_updated(aog_env* env) {
 
 int aog_tensor_column_updated(aog_env* env, int phys_col, cudaStream_t st) {
   TensorState* ts = TS(env);
-  dim3 g(cdiv(TC_NP, 128), env->cfg.num_envs);
-  k_column_to_T<<<g, 128, 0, st>>>(env->screens, ts->screensT, TC_NP, phys_col);
+  const int B = env->cfg.num_envs;
+  const double pi = 3.14159265358979323846;
+  k_column_to_tiles<<<cdiv(B * TC_NP, 256), 256, 0, st>>>(env->screens, ts->hwt, TC_NP, B, phys_col,
+                                                          1.0 / (env->cfg.wavelength_wfs * pi),
+                                                          1.0 / (env->cfg.wavelength_sci * pi));
   AOG_LAUNCH_CHECK();
   return AOG_OK;
 }
@@ -774,28 +1084,76 @@ int aog_tensor_check(aog_env* env) {
   return AOG_OK;
 }
 
+namespace {
+template <bool STREHL, int NOBS>
+int launch_field(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
+  const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES + 1024 + FK_AUX_BAR + FK_PARTS * 128 * (int)sizeof(double2) +
+                   NOBS * TC_NP * (int)sizeof(float2) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
+  static bool configured = false;
+  if (!configured) {
+    AOG_CUDA(cudaFuncSetAttribute(k_dm_field_tc<STREHL, NOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  k_dm_field_tc<STREHL, NOBS><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
+  AOG_LAUNCH_CHECK();
+  return AOG_OK;
+}
+template <bool STREHL>
+int launch_field_n(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
+  switch (p.n) {
+    case 1: return launch_field<STREHL, 1>(env, ts, p, grid, st);
+    case 2: return launch_field<STREHL, 2>(env, ts, p, grid, st);
+    case 3: return launch_field<STREHL, 3>(env, ts, p, grid, st);
+    case 4: return launch_field<STREHL, 4>(env, ts, p, grid, st);
+    case 5: return launch_field<STREHL, 5>(env, ts, p, grid, st);
+    case 6: return launch_field<STREHL, 6>(env, ts, p, grid, st);
+    case 7: return launch_field<STREHL, 7>(env, ts, p, grid, st);
+    case 8: return launch_field<STREHL, 8>(env, ts, p, grid, st);
+  }
+  AOG_FAIL(AOG_ERR_UNSUPPORTED, "obs_dim");
+}
+}  // namespace
+
 int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_outputs& out, cudaStream_t st) {
   TensorState* ts = TS(env);
   const aog_config& c = env->cfg;
-  if (!(ts->have_m1 && ts->have_m2 && ts->have_lp && ts->have_modes && ts->have_ap && ts->have_m2o))
+  if (!(ts->have_m1 && ts->have_m2 && ts->have_lp && ts->have_modes && ts->have_ap && ts->have_m2o && ts->have_m1o))
     AOG_FAIL(AOG_ERR_STATE, "tensor path tables incomplete");
   (void)flat_dm;
   const int Np = TC_NP, n = c.obs_dim, K = c.num_modes, J = c.num_lp_modes, B = c.num_envs;
   const bool strehl = with_reward && c.rew_type == AOG_REW_STREHL_RATIO;
-  constexpr int ET = 8;
-  const double two_pi = 6.283185307179586476925286766559;
-  // phase [turns] = S / (lambda 2 pi) + s * 2 / lambda
-  const double tw_S = 1.0 / (c.wavelength_wfs * two_pi), tw_s = 2.0 / c.wavelength_wfs;
-  const double tsS = 1.0 / (c.wavelength_sci * two_pi), tss = 2.0 / c.wavelength_sci;
   const double2 norm = make_double2(c.mft_norm_re * c.amp_fiber, c.mft_norm_im * c.amp_fiber);
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     const int nB = std::min(env->chunk, B - e0);
     {
-      dim3 g(Np / 4, cdiv(nB, ET));
-      k_field_tc<ET><<<g, 256, ET * K * sizeof(float), st>>>(
-          ts->screensT, env->act, ts->modesT, ts->apT, env->t_m1o, ts->E_hi, ts->E_lo, env->bufR, env->strehl_part, K,
-          n, e0, nB, (int)env->cnt.column_origin, tw_S, tw_s, tsS, tss, strehl ? 1 : 0);
+      // actuators -> half-turns of DM phase per unit mode (2 k s / pi = 4 s / lambda), split fp16
+      const int rows = cdiv(nB, 128) * 128;
+      k_act_pack<<<cdiv(rows * ts->kpad, 256), 256, 0, st>>>(env->act, ts->act_hi, ts->act_lo, K, ts->kpad, e0, nB,
+                                                             rows, 4.0 / c.wavelength_wfs);
       AOG_LAUNCH_CHECK();
+      FieldParams fp{};
+      fp.num_envs = nB;
+      fp.num_items = cdiv(nB, 128) * Np;
+      fp.items_per_cta = std::max(FK_MIN_ITEMS, cdiv(fp.num_items, ts->num_sms));
+      fp.nkb = ts->kpad / 64;
+      fp.n = n;
+      fp.col_origin = (int)env->cnt.column_origin;
+      fp.do_strehl = strehl ? 1 : 0;
+      fp.env0 = e0;
+      { const char* d = getenv("AOG_FK_DEBUG"); fp.dbg = d ? atoi(d) : 0; }
+      fp.sci_ratio = (float)(c.wavelength_wfs / c.wavelength_sci);
+      fp.hwt = ts->hwt; fp.apmask = ts->apmask; fp.m1o32 = ts->m1o32;
+      fp.E_hi = ts->E_hi; fp.E_lo = ts->E_lo; fp.R4 = ts->R4; fp.strehl_part = env->strehl_part;
+      fp.err_flag = ts->err_flag;
+      const int grid = cdiv(fp.num_items, fp.items_per_cta);
+      int rc;
+      if (strehl) {
+        AOG_CUDA(cudaMemsetAsync(env->strehl_part, 0, (size_t)nB * FK_SLOTS * sizeof(double2), st));
+        rc = launch_field_n<true>(env, ts, fp, grid, st);
+      } else {
+        rc = launch_field_n<false>(env, ts, fp, grid, st);
+      }
+      if (rc) return rc;
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev0, st)); }
     TcParams p{};
@@ -817,8 +1175,8 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev1, st)); env->ev_valid = true; }
     FinalizeArgs a{};
-    a.R = env->bufR; a.m1o = ts->m2oT; a.coef = env->coef; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
-    a.strehl_part = env->strehl_part; a.strehl_blocks = Np / 4;
+    a.R = nullptr; a.R4 = ts->R4; a.r4_parts = FK_PARTS; a.m1o = ts->m2oT; a.coef = env->coef; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
+    a.strehl_part = env->strehl_part; a.strehl_blocks = FK_SLOTS;
     a.Np = Np; a.n = n; a.J = J; a.rew_type = c.rew_type; a.has_thr = c.has_rew_threshold;
     a.compute_reward = with_reward ? 1 : 0;
     a.transpose_out = 1;     // R is [x][v] and the table is M2o^T: results come out as (u, v)
@@ -831,7 +1189,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     a.power = out.power ? out.power + e0 : nullptr;
     a.strehl = out.strehl ? out.strehl + e0 : nullptr;
     a.ssim = out.ssim ? out.ssim + e0 : nullptr;
-    k_finalize<<<nB, 64, 0, st>>>(a);
+    k_finalize<<<nB, 128, 0, st>>>(a);
     AOG_LAUNCH_CHECK();
   }
   return AOG_OK;
