@@ -279,6 +279,8 @@ struct FinalizeArgs {
   const double2* strehl_part; int strehl_blocks;
   int Np, n, J, rew_type, has_thr, compute_reward;
   int r4_parts;        // partial sums per contraction index in R4
+  int coef_is_raw;     // coef holds unscaled (re, im) projection sums: multiply by coef_scale
+  double2 coef_scale;
   int transpose_out;   // R / table hold the transposed contraction: result (a, b) is obs pixel (v = b, u = a)
   double thr, obs_weight, strehl_scale, ssim_peak;
   double2 norm;
@@ -350,7 +352,9 @@ static __global__ void k_finalize(FinalizeArgs a) {
   // fibre: out = M (c e^{i beta L});  total power = c'^H G c'
   double2 c[AOG_MAX_LP];
   for (int j = 0; j < a.J; ++j) {
-    const double2 cj = a.coef[(size_t)b * a.J + j], ph = a.lpphase[j];
+    double2 cj = a.coef[(size_t)b * a.J + j];
+    if (a.coef_is_raw) cj = make_double2(cj.x * a.coef_scale.x - cj.y * a.coef_scale.y, cj.x * a.coef_scale.y + cj.y * a.coef_scale.x);
+    const double2 ph = a.lpphase[j];
     c[j] = make_double2(cj.x * ph.x - cj.y * ph.y, cj.x * ph.y + cj.y * ph.x);
   }
   double power = 0.0;

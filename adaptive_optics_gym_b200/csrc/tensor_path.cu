@@ -30,10 +30,10 @@ constexpr int TC_NF = 128;          // focal pixels per side
 constexpr int TC_K = 2 * TC_NP;     // real-embedded contraction length (480)
 constexpr int KB = 32;              // K elements per pipeline stage (64 B rows, SWIZZLE_64B)
 constexpr int NUM_KB = TC_K / KB;   // 15
-constexpr int NUM_STAGES = 3;
+constexpr int NUM_STAGES = 4;
 constexpr int A_TILE = 128 * KB * 2;            // 8 KB: 128 rows x 64 B
 constexpr int B_TILE = 256 * KB * 2;            // 16 KB slot (stage 1 uses 240 rows of it)
-constexpr int STAGE_BYTES = 4 * A_TILE + 2 * B_TILE;   // 64 KB
+constexpr int STAGE_BYTES = 6 * A_TILE;   // 48 KB: stage 1 = 2 A tiles + 2 B slots of 16 KB; stage 2 = 4 A + 2 B tiles
 constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 4096 /*barriers + reduction scratch*/;
 constexpr int TC_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 
@@ -111,11 +111,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same smem offset in both CTAs of the 2-CTA cluster and signals the
+// mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"((uint16_t)3)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// commit that arrives on the barrier at this offset in BOTH CTAs of the cluster
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -155,29 +169,40 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 }
 
 // ----------------------------------------------------------------------------- the GEMM kernel
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo);
+
 struct TcParams {
   int num_items;        // MODE 0: envs;  MODE 1: env pairs
   int num_envs;         // envs in this chunk
   // MODE 0 epilogue: stage-1 product as split fp16, [env][128][480]
   __half* T_hi; __half* T_lo;
-  // MODE 1 epilogue: fibre projection
+  // MODE 1 epilogue: fibre projection, raw sums [env][J][2] (re from cluster rank 0, im from rank 1)
   const float* lpw;     // [J][128][128]
-  double2* coef;        // [env][J]
+  double* coef_raw;
   int J;
-  double2 scale;        // norm * amp * pupil_weight * lpw_scale
   int* err_flag;
 };
 
-// MODE 0: stage 1 (A = constant twiddles, 2 row-halves = real / imaginary rows; B = one env's field)
-// MODE 1: stage 2 (A = stage-1 product of 2 envs, one per row-half; B = constant twiddles)
+// One kernel template for both MFT stages, launched as 2-CTA clusters.  CTA r of a cluster owns one half of
+// the output and receives the operand both halves need by TMA multicast (each CTA fetches half of it):
+//   MODE 0 (stage 1, item = env):      rank r = row half (r = 0: Tr rows, r = 1: Ti rows); A = twiddle rows of
+//                                      that half (own), B = the env's field, 240 x-rows (multicast)
+//   MODE 1 (stage 2, item = env pair): computes F^T: rank r = half of the focal columns (r = 0: Fr, r = 1: Fi);
+//                                      A = twiddle rows of that half (own, M = focal column u), B = the stage-1
+//                                      products of BOTH envs stacked along N (multicast, N = 2 x 128 focal rows v),
+//                                      so every MMA is a full N = 256 instruction
+// TMEM holds SEPARATE accumulators for the main hi.hi chain and for the hi.lo + lo.hi corrections: the
+// tensor core truncates its FP32 accumulation, so every accumulate onto a large sum costs ~ -0.5 ulp; keeping
+// the 2 x 30 tiny correction updates off the main accumulator cuts that bias 3x (tools/tensor_bias_probe.py).
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
-  constexpr int N_TILE = (MODE == 0) ? TC_NP : 2 * TC_NF;            // 240 | 256
-  constexpr uint32_t TX_BYTES = 4 * A_TILE + 2 * N_TILE * KB * 2;    // bytes landing per stage
-  constexpr uint32_t IDESC = umma_idesc_f16(128, N_TILE);
-
+  constexpr int N_MMA = (MODE == 0) ? TC_NP : 2 * TC_NF;             // 240 | 256
+  constexpr uint32_t TX_BYTES = (MODE == 0) ? (2 * A_TILE + 2 * TC_NP * KB * 2) : (2 * A_TILE + 4 * A_TILE);
+  constexpr uint32_t IDESC = umma_idesc_f16(128, N_MMA);
+  // stage layout (48 KB).  MODE 0: [A_hi 8K][A_lo 8K][B_hi 16K slot][B_lo 16K slot]
+  //                        MODE 1: [A_hi 8K][A_lo 8K][T0_hi][T1_hi][T0_lo][T1_lo] (8K each; T pairs contiguous = N 256)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint64_t* full = reinterpret_cast<uint64_t*>(base + NUM_STAGES * STAGE_BYTES);
@@ -185,27 +210,33 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
   uint64_t* tmem_full = empty + NUM_STAGES;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  double* red = reinterpret_cast<double*>(base + NUM_STAGES * STAGE_BYTES + 128);   // [2][4][2*AOG_MAX_LP*2] max 2*4*32
+  double* red = reinterpret_cast<double*>(base + NUM_STAGES * STAGE_BYTES + 128);   // [2 bufs][4 lane groups][2 envs][AOG_MAX_LP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_lo)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_lo)) : "memory");
-    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }   // empty: both CTAs' MMAs
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: all 512 columns (two 128-lane x 256-column FP32 accumulators)
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  // the peer's barriers must exist before a multicast copy or a remote commit can signal them
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -214,20 +245,29 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int a_row0 = (MODE == 0) ? 0 : item * 256;
-        const int b_row0 = (MODE == 0) ? item * TC_NP : 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
         for (int kb = 0; kb < NUM_KB; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 1);
+          mbar_wait<32>(&empty[stage], phase ^ 1, p.err_flag, 1);       // freed by BOTH CTAs (we write into both)
           mbar_expect_tx(&full[stage], TX_BYTES);
           const uint32_t s0 = smem_u32(base + stage * STAGE_BYTES);
           const int k0 = kb * KB;
-          tma_load_2d(s0 + 0 * A_TILE, &tmA_hi, &full[stage], k0, a_row0);
-          tma_load_2d(s0 + 1 * A_TILE, &tmA_hi, &full[stage], k0, a_row0 + 128);
-          tma_load_2d(s0 + 2 * A_TILE, &tmA_lo, &full[stage], k0, a_row0);
-          tma_load_2d(s0 + 3 * A_TILE, &tmA_lo, &full[stage], k0, a_row0 + 128);
-          tma_load_2d(s0 + 4 * A_TILE, &tmB_hi, &full[stage], k0, b_row0);
-          tma_load_2d(s0 + 4 * A_TILE + B_TILE, &tmB_lo, &full[stage], k0, b_row0);
+          if (MODE == 0) {
+            tma_load_2d(s0, &tmA_hi, &full[stage], k0, (int)rank * 128);
+            tma_load_2d(s0 + A_TILE, &tmA_lo, &full[stage], k0, (int)rank * 128);
+            const uint32_t off = rank * (TC_NP / 2) * KB * 2;           // my 120 rows of the shared field tile
+            tma_load_2d_mc(s0 + 2 * A_TILE + off, &tmB_hi, &full[stage], k0, item * TC_NP + (int)rank * (TC_NP / 2));
+            tma_load_2d_mc(s0 + 2 * A_TILE + B_TILE + off, &tmB_lo, &full[stage], k0, item * TC_NP + (int)rank * (TC_NP / 2));
+          } else {
+            tma_load_2d(s0, &tmA_hi, &full[stage], k0, (int)rank * 128);
+            tma_load_2d(s0 + A_TILE, &tmA_lo, &full[stage], k0, (int)rank * 128);
+            const uint32_t off = rank * 64 * KB * 2;                    // my 64 rows of each shared stage-1 tile
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int row = (2 * item + e) * 128 + (int)rank * 64;
+              tma_load_2d_mc(s0 + (2 + e) * A_TILE + off, &tmB_hi, &full[stage], k0, row);
+              tma_load_2d_mc(s0 + (4 + e) * A_TILE + off, &tmB_lo, &full[stage], k0, row);
+            }
+          }
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -237,8 +277,8 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        mbar_wait(tmem_empty, tphase ^ 1, p.err_flag, 2);   // epilogue has drained the accumulators
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        mbar_wait<32>(tmem_empty, tphase ^ 1, p.err_flag, 2);
         tc_fence_after();
         for (int kb = 0; kb < NUM_KB; ++kb) {
           mbar_wait(&full[stage], phase, p.err_flag, 3);
@@ -246,132 +286,120 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
           const uint32_t s0 = smem_u32(base + stage * STAGE_BYTES);
 #pragma unroll
           for (int ks = 0; ks < KB / 16; ++ks) {
-            const uint64_t b_hi = umma_desc_sw64(s0 + 4 * A_TILE + ks * 32);
-            const uint64_t b_lo = umma_desc_sw64(s0 + 4 * A_TILE + B_TILE + ks * 32);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint64_t a_hi = umma_desc_sw64(s0 + h * A_TILE + ks * 32);
-              const uint64_t a_lo = umma_desc_sw64(s0 + (2 + h) * A_TILE + ks * 32);
-              const uint32_t d = tmem_base + h * 256;
-              tc_mma_f16(d, a_hi, b_hi, IDESC, (kb | ks) != 0);
-              tc_mma_f16(d, a_hi, b_lo, IDESC, 1);
-              tc_mma_f16(d, a_lo, b_hi, IDESC, 1);
-            }
+            const uint32_t acc = (kb | ks) != 0;
+            // same tile arithmetic for both modes: the B slot is 16 KB (240 rows used | two 128-row tiles)
+            const uint64_t a_hi = umma_desc_sw64(s0 + ks * 32), a_lo = umma_desc_sw64(s0 + A_TILE + ks * 32);
+            const uint64_t b_hi = umma_desc_sw64(s0 + 2 * A_TILE + ks * 32);
+            const uint64_t b_lo = umma_desc_sw64(s0 + 2 * A_TILE + B_TILE + ks * 32);
+            tc_mma_f16(tmem_base, a_hi, b_hi, IDESC, acc);              // main
+            tc_mma_f16(tmem_base + 256, a_hi, b_lo, IDESC, acc);        // corrections
+            tc_mma_f16(tmem_base + 256, a_lo, b_hi, IDESC, 1);
           }
-          tc_commit(&empty[stage]);                 // frees the smem slot when these MMAs retire
+          tc_commit_mc(&empty[stage]);              // frees the slot in BOTH CTAs when these MMAs retire
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tmem_full);                       // accumulators complete
+        tc_commit(tmem_full);
         tphase ^= 1;
       }
     }
   } else {
     // ===================== epilogue: 4 warps, TMEM lane group = warp % 4 =====================
     const int lg = warp & 3;
-    const int row = lg * 32 + lane;                 // accumulator row (focal row v)
+    const int row = lg * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     uint32_t tphase = 0;
     int it = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+    for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
       mbar_wait(tmem_full, tphase, p.err_flag, 4);
       tc_fence_after();
       if constexpr (MODE == 0) {
-        // stage-1 product -> split fp16, row-major [v][k] with k = (x | 240 + x)
+        // (main + corrections) -> split fp16, row-major [v][k], my half of k = rank * 240 + x
+        const bool odd = lane & 1;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll 1
-          for (int c = 0; c < TC_NP / 16; ++c) {
-            float v[16];
-            tc_ld16(lane_addr + h * 256 + c * 16, v);
-            tc_wait_ld();
-            uint32_t hi[8], lo[8];
+        for (int c = 0; c < TC_NP / 16; ++c) {
+          float v[16], w[16];
+          tc_ld16(lane_addr + c * 16, v);
+          tc_ld16(lane_addr + 256 + c * 16, w);
+          tc_wait_ld();
+          uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-              const __half l0 = __float2half_rn(v[2 * i] - __half2float(h0));
-              const __half l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-              hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-            }
-            // full-sector stores: lane pairs (rows v, v+1) swap halves so each instruction writes whole
-            // 32-byte sectors instead of two half-sector partial writes per row
-            const bool odd = lane & 1;
-            const size_t r_even = ((size_t)item * 128 + (row & ~1)) * TC_K + h * TC_NP + c * 16 + (odd ? 8 : 0);
-            const size_t r_odd = r_even + TC_K;
-            uint32_t xh[4], xl[4];
+          for (int i = 0; i < 8; ++i) split_pack2(v[2 * i] + w[2 * i], v[2 * i + 1] + w[2 * i + 1], hi[i], lo[i]);
+          // full-sector stores: lane pairs (rows v, v+1) swap halves so each instruction writes whole sectors
+          const size_t r_even = ((size_t)item * 128 + (row & ~1)) * TC_K + rank * TC_NP + c * 16 + (odd ? 8 : 0);
+          const size_t r_odd = r_even + TC_K;
+          uint32_t xh[4], xl[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              xh[k] = __shfl_xor_sync(0xffffffffu, odd ? hi[k] : hi[4 + k], 1);
-              xl[k] = __shfl_xor_sync(0xffffffffu, odd ? lo[k] : lo[4 + k], 1);
-            }
-            *reinterpret_cast<uint4*>(p.T_hi + r_even) = odd ? make_uint4(xh[0], xh[1], xh[2], xh[3]) : make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(p.T_lo + r_even) = odd ? make_uint4(xl[0], xl[1], xl[2], xl[3]) : make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<uint4*>(p.T_hi + r_odd) = odd ? make_uint4(hi[4], hi[5], hi[6], hi[7]) : make_uint4(xh[0], xh[1], xh[2], xh[3]);
-            *reinterpret_cast<uint4*>(p.T_lo + r_odd) = odd ? make_uint4(lo[4], lo[5], lo[6], lo[7]) : make_uint4(xl[0], xl[1], xl[2], xl[3]);
+          for (int k = 0; k < 4; ++k) {
+            xh[k] = __shfl_xor_sync(0xffffffffu, odd ? hi[k] : hi[4 + k], 1);
+            xl[k] = __shfl_xor_sync(0xffffffffu, odd ? lo[k] : lo[4 + k], 1);
           }
+          *reinterpret_cast<uint4*>(p.T_hi + r_even) = odd ? make_uint4(xh[0], xh[1], xh[2], xh[3]) : make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(p.T_lo + r_even) = odd ? make_uint4(xl[0], xl[1], xl[2], xl[3]) : make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(p.T_hi + r_odd) = odd ? make_uint4(hi[4], hi[5], hi[6], hi[7]) : make_uint4(xh[0], xh[1], xh[2], xh[3]);
+          *reinterpret_cast<uint4*>(p.T_lo + r_odd) = odd ? make_uint4(lo[4], lo[5], lo[6], lo[7]) : make_uint4(xl[0], xl[1], xl[2], xl[3]);
         }
         tc_fence_before();
         mbar_arrive(tmem_empty);
       } else {
-        // fibre projection: c_j = sum_{v,u} F[v][u] (mode_j w)[v][u], F = Fr + i Fi out of TMEM
-        double acc[2][AOG_MAX_LP][2];
+        // fibre projection of my half (rank 0: sum Fr w, rank 1: sum Fi w), both envs of the pair.
+        // Accumulator = F^T: lane = focal column u, TMEM column = env * 128 + focal row v.
+        double acc[2][AOG_MAX_LP];
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int e = 0; e < 2; ++e)
 #pragma unroll
-          for (int j = 0; j < AOG_MAX_LP; ++j) acc[h][j][0] = acc[h][j][1] = 0.0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (2 * item + h >= p.num_envs) continue;
+          for (int j = 0; j < AOG_MAX_LP; ++j) acc[e][j] = 0.0;
+        const bool env1_ok = 2 * item + 1 < p.num_envs;
 #pragma unroll 1
-          for (int c = 0; c < TC_NF / 16; ++c) {
-            float fr[16], fi[16];
-            tc_ld16(lane_addr + h * 256 + c * 16, fr);
-            tc_ld16(lane_addr + h * 256 + TC_NF + c * 16, fi);
-            tc_wait_ld();
+        for (int c = 0; c < TC_NF / 16; ++c) {
+          float f0[16], f1[16], g[16];
+          tc_ld16(lane_addr + c * 16, f0);
+          tc_ld16(lane_addr + 256 + c * 16, g);
+          tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < AOG_MAX_LP; ++j) {
-              if (j < p.J) {
-                const float4* w4 = reinterpret_cast<const float4*>(p.lpw + ((size_t)j * TC_NF + row) * TC_NF + c * 16);
-                float sr = 0.f, si = 0.f;
+          for (int i = 0; i < 16; ++i) f0[i] += g[i];
+          tc_ld16(lane_addr + 128 + c * 16, f1);
+          tc_ld16(lane_addr + 256 + 128 + c * 16, g);
+          tc_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 w = __ldg(w4 + q);
-                  sr = fmaf(fr[4 * q + 0], w.x, sr); si = fmaf(fi[4 * q + 0], w.x, si);
-                  sr = fmaf(fr[4 * q + 1], w.y, sr); si = fmaf(fi[4 * q + 1], w.y, si);
-                  sr = fmaf(fr[4 * q + 2], w.z, sr); si = fmaf(fi[4 * q + 2], w.z, si);
-                  sr = fmaf(fr[4 * q + 3], w.w, sr); si = fmaf(fi[4 * q + 3], w.w, si);
-                }
-                acc[h][j][0] += (double)sr;
-                acc[h][j][1] += (double)si;
+          for (int i = 0; i < 16; ++i) f1[i] += g[i];
+#pragma unroll
+          for (int j = 0; j < AOG_MAX_LP; ++j) {
+            if (j < p.J) {
+              // transposed weight table: lpw[j][u = row][v], one load serves both envs
+              const float4* w4 = reinterpret_cast<const float4*>(p.lpw + ((size_t)j * TC_NF + row) * TC_NF + c * 16);
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w = __ldg(w4 + q);
+                s0 = fmaf(f0[4 * q + 0], w.x, s0); s1 = fmaf(f1[4 * q + 0], w.x, s1);
+                s0 = fmaf(f0[4 * q + 1], w.y, s0); s1 = fmaf(f1[4 * q + 1], w.y, s1);
+                s0 = fmaf(f0[4 * q + 2], w.z, s0); s1 = fmaf(f1[4 * q + 2], w.z, s1);
+                s0 = fmaf(f0[4 * q + 3], w.w, s0); s1 = fmaf(f1[4 * q + 3], w.w, s1);
               }
+              acc[0][j] += (double)s0;
+              if (env1_ok) acc[1][j] += (double)s1;
             }
           }
         }
         tc_fence_before();
         mbar_arrive(tmem_empty);                    // TMEM is free: the next tile's MMAs may start
-        double* rbuf = red + (it & 1) * (4 * 2 * AOG_MAX_LP * 2);
+        double* rbuf = red + (it & 1) * (4 * 2 * AOG_MAX_LP);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int e = 0; e < 2; ++e)
 #pragma unroll
           for (int j = 0; j < AOG_MAX_LP; ++j)
             if (j < p.J) {
-              const double a = warp_sum(acc[h][j][0]), b = warp_sum(acc[h][j][1]);
-              if (lane == 0) {
-                rbuf[((lg * 2 + h) * AOG_MAX_LP + j) * 2 + 0] = a;
-                rbuf[((lg * 2 + h) * AOG_MAX_LP + j) * 2 + 1] = b;
-              }
+              const double a = warp_sum(acc[e][j]);
+              if (lane == 0) rbuf[(lg * 2 + e) * AOG_MAX_LP + j] = a;
             }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane < 2 * p.J) {
-          const int h = lane / p.J, j = lane - h * p.J;
-          const int e = 2 * item + h;
-          if (e < p.num_envs) {
-            double sr = 0.0, si = 0.0;
-            for (int g = 0; g < 4; ++g) {
-              sr += rbuf[((g * 2 + h) * AOG_MAX_LP + j) * 2 + 0];
-              si += rbuf[((g * 2 + h) * AOG_MAX_LP + j) * 2 + 1];
-            }
-            p.coef[(size_t)e * p.J + j] = make_double2(sr * p.scale.x - si * p.scale.y, sr * p.scale.y + si * p.scale.x);
+          const int e = lane / p.J, j = lane - e * p.J;
+          const int env = 2 * item + e;
+          if (env < p.num_envs) {
+            double s = 0.0;
+            for (int g4 = 0; g4 < 4; ++g4) s += rbuf[(g4 * 2 + e) * AOG_MAX_LP + j];
+            p.coef_raw[((size_t)env * p.J + j) * 2 + rank] = s;
           }
         }
       }
@@ -380,6 +408,9 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  // neither CTA may exit while the peer can still multicast into its smem or signal its barriers
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -902,12 +933,12 @@ int aog_tensor_create(aog_env* env) {
   AOG_CUDA(cudaMemset(ts->err_flag, 0, sizeof(int)));
   A(make_map(env, &ts->tmA1_hi, ts->A1_hi, 256, 128));
   A(make_map(env, &ts->tmA1_lo, ts->A1_lo, 256, 128));
-  A(make_map(env, &ts->tmE_hi, ts->E_hi, ch * TC_NP, TC_NP));
-  A(make_map(env, &ts->tmE_lo, ts->E_lo, ch * TC_NP, TC_NP));
-  A(make_map(env, &ts->tmT_hi, ts->T_hi, (ch + 1) * 128, 128));
-  A(make_map(env, &ts->tmT_lo, ts->T_lo, (ch + 1) * 128, 128));
-  A(make_map(env, &ts->tmB2_hi, ts->B2_hi, 256, 256));
-  A(make_map(env, &ts->tmB2_lo, ts->B2_lo, 256, 256));
+  A(make_map(env, &ts->tmE_hi, ts->E_hi, ch * TC_NP, TC_NP / 2));   // each CTA of the cluster fetches half
+  A(make_map(env, &ts->tmE_lo, ts->E_lo, ch * TC_NP, TC_NP / 2));
+  A(make_map(env, &ts->tmT_hi, ts->T_hi, (ch + 1) * 128, 64));
+  A(make_map(env, &ts->tmT_lo, ts->T_lo, (ch + 1) * 128, 64));
+  A(make_map(env, &ts->tmB2_hi, ts->B2_hi, 256, 128));
+  A(make_map(env, &ts->tmB2_lo, ts->B2_lo, 256, 128));
   A(make_map(env, &ts->tmAct_hi, ts->act_hi, ts->act_rows, 128, ts->kpad, 64));
   A(make_map(env, &ts->tmAct_lo, ts->act_lo, ts->act_rows, 128, ts->kpad, 64));
   A(make_map(env, &ts->tmModes_hi, ts->modesK_hi, P, TC_NP, ts->kpad, 64));
@@ -974,8 +1005,12 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
     for (size_t i = 0; i < cnt; ++i) mx = std::max(mx, std::fabs(m[i]));
     if (mx == 0.0) mx = 1.0;
     ts->lpw_scale = mx;
+    // stored transposed ([j][u][v]): the stage-2 accumulator is F^T (lane = focal column u)
     std::vector<float> f(cnt);
-    for (size_t i = 0; i < cnt; ++i) f[i] = (float)(m[i] / mx);
+    for (int j = 0; j < c.num_lp_modes; ++j)
+      for (int v = 0; v < Nf; ++v)
+        for (int u = 0; u < Nf; ++u)
+          f[((size_t)j * Nf + u) * Nf + v] = (float)(m[((size_t)j * Nf + v) * Nf + u] / mx);
     AOG_CUDA(cudaMemcpy(ts->lpw, f.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
     ts->have_lp = true;
   } else if (which == AOG_TABLE_DM_MODES) {
@@ -1160,22 +1195,27 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     p.num_envs = nB;
     p.err_flag = ts->err_flag;
     p.T_hi = ts->T_hi; p.T_lo = ts->T_lo;
-    p.lpw = ts->lpw; p.coef = env->coef; p.J = J;
-    const double sc = c.amp_fiber * ts->pupil_weight * ts->lpw_scale;
-    p.scale = make_double2(c.mft_norm_re * sc, c.mft_norm_im * sc);
+    p.lpw = ts->lpw; p.coef_raw = reinterpret_cast<double*>(env->coef); p.J = J;
     p.num_items = nB;
-    k_mft_tc<0><<<std::min(ts->num_sms, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmE_hi,
+    const int max_clusters = ts->num_sms / 2;
+    k_mft_tc<0><<<2 * std::min(max_clusters, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmE_hi,
                                                                                     ts->tmE_lo, p);
     AOG_LAUNCH_CHECK();
     if (with_reward) {
       p.num_items = (nB + 1) / 2;
-      k_mft_tc<1><<<std::min(ts->num_sms, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmT_hi, ts->tmT_lo, ts->tmB2_hi,
-                                                                                      ts->tmB2_lo, p);
+      k_mft_tc<1><<<2 * std::min(max_clusters, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmB2_hi, ts->tmB2_lo, ts->tmT_hi,
+                                                                                      ts->tmT_lo, p);
       AOG_LAUNCH_CHECK();
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev1, st)); env->ev_valid = true; }
     FinalizeArgs a{};
-    a.R = nullptr; a.R4 = ts->R4; a.r4_parts = FK_PARTS; a.m1o = ts->m2oT; a.coef = env->coef; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
+    a.R = nullptr; a.R4 = ts->R4; a.r4_parts = FK_PARTS; a.m1o = ts->m2oT;
+    {
+      // coef holds the raw projection sums (re, im): scale = norm * amp * pupil weight * table scale
+      const double sc = c.amp_fiber * ts->pupil_weight * ts->lpw_scale;
+      a.coef_scale = make_double2(c.mft_norm_re * sc, c.mft_norm_im * sc);
+      a.coef_is_raw = 1;
+    } a.coef = env->coef; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
     a.strehl_part = env->strehl_part; a.strehl_blocks = FK_SLOTS;
     a.Np = Np; a.n = n; a.J = J; a.rew_type = c.rew_type; a.has_thr = c.has_rew_threshold;
     a.compute_reward = with_reward ? 1 : 0;
