@@ -24,9 +24,14 @@ TABLE_IDS = {
     'aperture': 0, 'dm_modes': 1, 'dm_gram': 2, 'mft_fib_1': 3, 'mft_fib_2': 4, 'mft_obs_1': 5,
     'mft_obs_2': 6, 'lp_modes_w': 7, 'lp_phase': 8, 'lp_gram': 9, 'ar_stencil': 10, 'ar_A': 11,
     'ar_B': 12, 'scr_C1': 13, 'scr_W1': 14, 'scr_C2': 15, 'scr_W2': 16,
+    # Shack-Hartmann integrator (after Handle.sh_configure)
+    'sh_mla_phase': 17, 'sh_fresnel': 18, 'sh_pix_offsets': 19, 'sh_pix_index': 20, 'sh_pix_x': 21,
+    'sh_pix_y': 22, 'sh_offset': 23, 'sh_recon': 24, 'sh_act0': 25,
 }
+INT32_TABLES = ('ar_stencil', 'sh_pix_offsets', 'sh_pix_index')
+SH_NOISE = {'none': 0, 'poisson': 1, 'injected': 2}
 FIELD_IDS = {'screen': 0, 'pupil': 1, 'focal': 2, 'focal_power': 3, 'obs_power': 4, 'actuators': 5,
-             'tc_pupil': 6, 'tc_stage1': 7}
+             'tc_pupil': 6, 'tc_stage1': 7, 'sh_image': 8, 'sh_actuators': 9}
 
 
 class AogConfig(C.Structure):
@@ -82,6 +87,9 @@ def load():
         'aog_reset_host': (C.c_int, [P, C.POINTER(AogOutputs)]),
         'aog_step': (C.c_int, [P, P, C.c_int, P, C.POINTER(AogOutputs), C.POINTER(C.c_int32), P]),
         'aog_step_host': (C.c_int, [P, P, C.c_int, P, C.POINTER(AogOutputs), C.POINTER(C.c_int32)]),
+        'aog_sh_configure': (C.c_int, [P, C.c_int, C.c_int, C.c_double, C.c_double]),
+        'aog_sh_step': (C.c_int, [P, C.c_int, P, P, P]),
+        'aog_sh_step_host': (C.c_int, [P, C.c_int, P, P]),
         'aog_get_counters': (C.c_int, [P, C.POINTER(AogCounters)]),
         'aog_set_counters': (C.c_int, [P, C.POINTER(AogCounters)]),
         'aog_get_actuators': (C.c_int, [P, P]),
@@ -137,7 +145,7 @@ class Handle:
     # ---- tables / state
     def set_table(self, name, arr):
         tid = TABLE_IDS[name]
-        if name == 'ar_stencil':
+        if name in INT32_TABLES:
             a = np.ascontiguousarray(arr, dtype=np.int32)
             count = a.size
         elif np.iscomplexobj(arr):
@@ -198,7 +206,7 @@ class Handle:
         c = self.cfg
         P, nf2, n2 = c.num_pupil_pixels ** 2, c.num_focal_pixels ** 2, c.obs_dim ** 2
         size = {'screen': P, 'pupil': 2 * P, 'focal': 2 * nf2, 'focal_power': nf2, 'obs_power': n2,
-                'actuators': c.num_modes, 'tc_pupil': 2 * P,
+                'actuators': c.num_modes, 'tc_pupil': 2 * P, 'sh_image': P, 'sh_actuators': c.num_modes,
                 'tc_stage1': 2 * c.num_focal_pixels * c.num_pupil_pixels}[which]
         out = np.empty(size)
         self.check(self.lib.aog_get_field(self._h, FIELD_IDS[which], env_index, _ptr(out), size), 'aog_get_field')
@@ -254,6 +262,27 @@ class Handle:
                                      C.c_void_p(noise_ptr) if noise_ptr else None, C.byref(out), C.byref(done),
                                      C.c_void_p(stream)), 'aog_step')
         return bool(done.value)
+
+    # ---- Shack-Hartmann integrator (AOEnv.SH_step)
+    def sh_configure(self, num_sub, num_pix, amplitude, weight_dt):
+        self.check(self.lib.aog_sh_configure(self._h, int(num_sub), int(num_pix), float(amplitude), float(weight_dt)),
+                   'aog_sh_configure')
+
+    def sh_step_host(self, noise='poisson', noisy_image=None):
+        B, K, P = self.cfg.num_envs, self.cfg.num_modes, self.cfg.num_pupil_pixels ** 2
+        img = None
+        if noise == 'injected':
+            img = np.ascontiguousarray(noisy_image, dtype=np.float64)
+            if img.size != B * P:
+                raise ValueError(f'noisy_image must have {B} x {P} elements')
+        out = np.empty((B, K))
+        self.check(self.lib.aog_sh_step_host(self._h, SH_NOISE[noise], _ptr(img), _ptr(out)), 'aog_sh_step_host')
+        return out
+
+    def sh_step_device(self, action_out_ptr, noise='poisson', noisy_image_ptr=None, stream=0):
+        self.check(self.lib.aog_sh_step(self._h, SH_NOISE[noise],
+                                        C.c_void_p(noisy_image_ptr) if noisy_image_ptr else None,
+                                        C.c_void_p(action_out_ptr), C.c_void_p(stream)), 'aog_sh_step')
 
     def launch_count(self):
         return int(self.lib.aog_launch_count(self._h))

@@ -204,6 +204,18 @@ int copy_outputs_to_host(aog_env* env, const aog_outputs* out, cudaStream_t st) 
   return AOG_OK;
 }
 
+// FP64 scratch (pupil field, stage-1 product, focal field) for handles that did not allocate it at create
+int ensure_f64_scratch(aog_env* env) {
+  if (env->bufA) return AOG_OK;
+  const aog_config& c = env->cfg;
+  const size_t ch = env->chunk, P = env->P;
+  int rc;
+  if ((rc = dev_alloc(env, &env->bufA, ch * P))) return rc;
+  if ((rc = dev_alloc(env, &env->bufB, ch * (size_t)c.num_pupil_pixels * std::max(c.num_focal_pixels, c.num_pupil_pixels)))) return rc;
+  if ((rc = dev_alloc(env, &env->bufC, ch * std::max<size_t>(env->NF2, P)))) return rc;
+  return AOG_OK;
+}
+
 aog_outputs device_outputs(aog_env* env) {
   aog_outputs o{};
   o.obs_f16 = env->o_obs16; o.obs_f64 = env->o_obs64; o.reward = env->o_reward; o.power = env->o_power;
@@ -313,7 +325,9 @@ void aog_destroy(aog_env* env) {
                   env->t_scrC1, env->t_scrW1, env->t_scrW1T, env->t_scrC2, env->t_scrW2, env->t_scrW2T,
                   env->screens, env->act, env->bufA, env->bufB, env->bufC, env->bufR, env->coef,
                   env->strehl_part, env->arZ, env->arNew, env->act_in, env->noise_in, env->o_obs16, env->o_obs64,
-                  env->o_reward, env->o_power, env->o_strehl, env->o_ssim};
+                  env->o_reward, env->o_power, env->o_strehl, env->o_ssim, env->t_sh_mla, env->t_sh_C, env->t_sh_CT,
+                  env->t_sh_off, env->t_sh_pix, env->t_sh_px, env->t_sh_py, env->t_sh_offset, env->t_sh_recon,
+                  env->t_sh_act0, env->act_sh, env->o_action, env->sh_noisy_in};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (env->h_pinned) cudaFreeHost(env->h_pinned);
@@ -349,6 +363,15 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
     case AOG_TABLE_SCR_W1: dst = env->t_scrW1; want = P; esz = sizeof(double2); break;
     case AOG_TABLE_SCR_C2: dst = env->t_scrC2; want = N2 * N2; break;
     case AOG_TABLE_SCR_W2: dst = env->t_scrW2; want = Np * N2; esz = sizeof(double2); break;
+    case AOG_TABLE_SH_MLA_PHASE: dst = env->t_sh_mla; want = P; break;
+    case AOG_TABLE_SH_FRESNEL: dst = env->t_sh_C; want = P; esz = sizeof(double2); break;
+    case AOG_TABLE_SH_PIX_OFFSETS: dst = env->t_sh_off; want = (size_t)env->sh_num_sub + 1; esz = sizeof(int32_t); break;
+    case AOG_TABLE_SH_PIX_INDEX: dst = env->t_sh_pix; want = (size_t)env->sh_num_pix; esz = sizeof(int32_t); break;
+    case AOG_TABLE_SH_PIX_X: dst = env->t_sh_px; want = (size_t)env->sh_num_pix; break;
+    case AOG_TABLE_SH_PIX_Y: dst = env->t_sh_py; want = (size_t)env->sh_num_pix; break;
+    case AOG_TABLE_SH_OFFSET: dst = env->t_sh_offset; want = 2 * (size_t)env->sh_num_sub; break;
+    case AOG_TABLE_SH_RECON: dst = env->t_sh_recon; want = K * 2 * (size_t)env->sh_num_sub; break;
+    case AOG_TABLE_SH_ACT0: dst = env->t_sh_act0; want = K; break;
     default: AOG_FAIL(AOG_ERR_INVALID, "unknown table id");
   }
   if (!dst || want == 0) AOG_FAIL(AOG_ERR_INVALID, "table not configured for this handle");
@@ -364,6 +387,14 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
   }
   if (which == AOG_TABLE_SCR_W1) {
     k_transpose_z<<<cdiv((int)P, 256), 256>>>(env->t_scrW1, env->t_scrW1T, (int)Np, (int)Np);
+    AOG_LAUNCH_CHECK();
+  }
+  if (which == AOG_TABLE_SH_FRESNEL) {
+    k_transpose_z<<<cdiv((int)P, 256), 256>>>(env->t_sh_C, env->t_sh_CT, (int)Np, (int)Np);
+    AOG_LAUNCH_CHECK();
+  }
+  if (which == AOG_TABLE_SH_ACT0) {   // every env's SH mirror starts from the same actuators (AO_env.py:431-447)
+    k_broadcast_rows<<<cdiv((int)K * c.num_envs, 256), 256>>>(env->t_sh_act0, env->act_sh, (int)K, c.num_envs);
     AOG_LAUNCH_CHECK();
   }
   if (which == AOG_TABLE_SCR_W2) {
@@ -575,6 +606,101 @@ int aog_step_host(aog_env* env, const void* actions_host, int act_dtype, const d
   return copy_outputs_to_host(env, out_host, st);
 }
 
+int aog_sh_configure(aog_env* env, int num_sub, int num_pix, double amplitude, double weight_dt) {
+  if (!env) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  if (num_sub < 1 || num_pix < num_sub || num_pix > env->P) AOG_FAIL(AOG_ERR_INVALID, "Shack-Hartmann sizes");
+  AOG_CUDA(cudaSetDevice(c.device));
+  const size_t P = env->P, K = c.num_modes, B = c.num_envs;
+  env->sh_num_sub = num_sub;
+  env->sh_num_pix = num_pix;
+  env->sh_amplitude = amplitude;
+  env->sh_weight_dt = weight_dt;
+  int rc;
+#define A(expr) if ((rc = (expr))) return rc
+  A(dev_alloc(env, &env->t_sh_mla, P));
+  A(dev_alloc(env, &env->t_sh_C, P));
+  A(dev_alloc(env, &env->t_sh_CT, P));
+  A(dev_alloc(env, &env->t_sh_off, (size_t)num_sub + 1));
+  A(dev_alloc(env, &env->t_sh_pix, (size_t)num_pix));
+  A(dev_alloc(env, &env->t_sh_px, (size_t)num_pix));
+  A(dev_alloc(env, &env->t_sh_py, (size_t)num_pix));
+  A(dev_alloc(env, &env->t_sh_offset, 2 * (size_t)num_sub));
+  A(dev_alloc(env, &env->t_sh_recon, K * 2 * (size_t)num_sub));
+  A(dev_alloc(env, &env->t_sh_act0, K));
+  A(dev_alloc(env, &env->act_sh, B * K));
+  A(dev_alloc(env, &env->o_action, B * K));
+#undef A
+  AOG_CUDA(cudaMemset(env->act_sh, 0, B * K * sizeof(double)));
+  for (int t = AOG_TABLE_SH_MLA_PHASE; t <= AOG_TABLE_SH_ACT0; ++t) env->have[t] = false;
+  return AOG_OK;
+}
+
+// AO_env.py:254-290 for every env of the handle: atmosphere + the SH mirror + micro-lens array (k_sh_field_f64),
+// Fresnel propagation to the lenslet focal plane as E_out = C E C^T (two batched complex GEMMs), then camera
+// image, photon noise, centroids, slopes and the leaky-integrator update (k_sh_centroid_update).
+int aog_sh_step(aog_env* env, int noise_mode, const double* noisy_image_dev, double* action_out_dev, void* stream) {
+  if (!env) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  if (env->sh_num_sub == 0) AOG_FAIL(AOG_ERR_STATE, "aog_sh_configure not called");
+  for (int t = AOG_TABLE_SH_MLA_PHASE; t <= AOG_TABLE_SH_ACT0; ++t)
+    if (!env->have[t]) AOG_FAIL(AOG_ERR_STATE, "Shack-Hartmann table " + std::to_string(t) + " not set");
+  if (!env->have[AOG_TABLE_APERTURE] || !env->have[AOG_TABLE_DM_MODES]) AOG_FAIL(AOG_ERR_STATE, "tables not set");
+  if (noise_mode < AOG_SH_NOISE_NONE || noise_mode > AOG_SH_NOISE_INJECTED) AOG_FAIL(AOG_ERR_INVALID, "noise_mode");
+  if (noise_mode == AOG_SH_NOISE_INJECTED && !noisy_image_dev) AOG_FAIL(AOG_ERR_INVALID, "noisy image missing");
+  AOG_CUDA(cudaSetDevice(c.device));
+  int rc = ensure_f64_scratch(env);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Np = c.num_pupil_pixels, K = c.num_modes, P = env->P, B = c.num_envs, Nsub = env->sh_num_sub;
+  const long long sB = (long long)Np * std::max(c.num_focal_pixels, Np);
+  const long long sC = (long long)std::max<size_t>(env->NF2, P);
+  constexpr int ET = 4;
+  for (int e0 = 0; e0 < B; e0 += env->chunk) {
+    const int nB = std::min(env->chunk, B - e0);
+    if (noise_mode != AOG_SH_NOISE_INJECTED) {
+      k_sh_field_f64<ET><<<dim3(cdiv(P, 128), cdiv(nB, ET)), 128, ET * K * sizeof(double), st>>>(
+          env->screens, env->act_sh, env->t_modes, env->t_aperture, env->t_sh_mla, env->bufA, P, Np, K, e0, nB,
+          (int)env->cnt.column_origin, c.wavelength_wfs, env->sh_amplitude);
+      AOG_LAUNCH_CHECK();
+      k_zgemm<<<dim3(cdiv(Np, 64), cdiv(Np, 64), nB), 256, 0, st>>>(env->t_sh_C, env->bufA, env->bufB, Np, Np, Np, Np,
+                                                                     Np, Np, 0, (long long)P, sB);
+      AOG_LAUNCH_CHECK();
+      k_zgemm<<<dim3(cdiv(Np, 64), cdiv(Np, 64), nB), 256, 0, st>>>(env->bufB, env->t_sh_CT, env->bufC, Np, Np, Np, Np,
+                                                                     Np, Np, sB, 0, sC);
+      AOG_LAUNCH_CHECK();
+    }
+    k_sh_centroid_update<<<nB, 256, 2 * Nsub * sizeof(double), st>>>(
+        env->bufC, sC, env->t_sh_off, env->t_sh_pix, env->t_sh_px, env->t_sh_py, env->t_sh_offset, env->t_sh_recon,
+        env->act_sh, action_out_dev, noisy_image_dev, P, K, Nsub, e0, env->sh_weight_dt, noise_mode,
+        c.seed ^ 0xD1B54A32D192ED03ull, (unsigned long long)c.env_id_base, (unsigned long long)env->sh_draws);
+    AOG_LAUNCH_CHECK();
+  }
+  env->sh_draws++;
+  return AOG_OK;
+}
+
+int aog_sh_step_host(aog_env* env, int noise_mode, const double* noisy_image_host, double* action_out_host) {
+  if (!env || !action_out_host) return AOG_ERR_INVALID;
+  const aog_config& c = env->cfg;
+  AOG_CUDA(cudaSetDevice(c.device));
+  cudaStream_t st = env->own_stream;
+  const size_t B = c.num_envs, K = c.num_modes, P = env->P;
+  if (!env->o_action) AOG_FAIL(AOG_ERR_STATE, "aog_sh_configure not called");
+  const double* noisy = nullptr;
+  if (noise_mode == AOG_SH_NOISE_INJECTED) {
+    if (!noisy_image_host) AOG_FAIL(AOG_ERR_INVALID, "noisy image missing");
+    if (!env->sh_noisy_in) { int rc = dev_alloc(env, &env->sh_noisy_in, B * P); if (rc) return rc; }
+    AOG_CUDA(cudaMemcpyAsync(env->sh_noisy_in, noisy_image_host, B * P * sizeof(double), cudaMemcpyHostToDevice, st));
+    noisy = env->sh_noisy_in;
+  }
+  int rc = aog_sh_step(env, noise_mode, noisy, env->o_action, st);
+  if (rc) return rc;
+  AOG_CUDA(cudaMemcpyAsync(action_out_host, env->o_action, B * K * sizeof(double), cudaMemcpyDeviceToHost, st));
+  AOG_CUDA(cudaStreamSynchronize(st));
+  return AOG_OK;
+}
+
 int aog_get_counters(const aog_env* env, aog_counters* out) {
   if (!env || !out) return AOG_ERR_INVALID;
   *out = env->cnt;
@@ -623,18 +749,43 @@ int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size
                         cudaMemcpyDeviceToHost));
     return AOG_OK;
   }
+  if (which == AOG_FIELD_SH_ACTUATORS) {
+    if (!env->act_sh) AOG_FAIL(AOG_ERR_STATE, "aog_sh_configure not called");
+    if (count != (size_t)c.num_modes) AOG_FAIL(AOG_ERR_INVALID, "count");
+    AOG_CUDA(cudaMemcpy(host_out, env->act_sh + (size_t)env_index * c.num_modes, count * sizeof(double),
+                        cudaMemcpyDeviceToHost));
+    return AOG_OK;
+  }
+  if (which == AOG_FIELD_SH_IMAGE) {   // noise-free camera image (power x dt) for the current state
+    if (!env->act_sh || !env->have[AOG_TABLE_SH_FRESNEL] || !env->have[AOG_TABLE_SH_MLA_PHASE])
+      AOG_FAIL(AOG_ERR_STATE, "Shack-Hartmann tables not set");
+    if (count != P) AOG_FAIL(AOG_ERR_INVALID, "count");
+    int rc = ensure_f64_scratch(env);
+    if (rc) return rc;
+    const int Np = c.num_pupil_pixels, K = c.num_modes;
+    cudaStream_t st = env->own_stream;
+    k_sh_field_f64<1><<<dim3(cdiv((int)P, 128), 1), 128, K * sizeof(double), st>>>(
+        env->screens, env->act_sh, env->t_modes, env->t_aperture, env->t_sh_mla, env->bufA, (int)P, Np, K, env_index,
+        1, (int)env->cnt.column_origin, c.wavelength_wfs, env->sh_amplitude);
+    AOG_LAUNCH_CHECK();
+    k_zgemm<<<dim3(cdiv(Np, 64), cdiv(Np, 64), 1), 256, 0, st>>>(env->t_sh_C, env->bufA, env->bufB, Np, Np, Np, Np, Np,
+                                                                  Np, 0, 0, 0);
+    AOG_LAUNCH_CHECK();
+    k_zgemm<<<dim3(cdiv(Np, 64), cdiv(Np, 64), 1), 256, 0, st>>>(env->bufB, env->t_sh_CT, env->bufC, Np, Np, Np, Np, Np,
+                                                                  Np, 0, 0, 0);
+    AOG_LAUNCH_CHECK();
+    std::vector<double> f(2 * P);
+    AOG_CUDA(cudaMemcpyAsync(f.data(), env->bufC, 2 * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    AOG_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < P; ++i) host_out[i] = (f[2 * i] * f[2 * i] + f[2 * i + 1] * f[2 * i + 1]) * env->sh_weight_dt;
+    return AOG_OK;
+  }
   if (which == AOG_FIELD_TC_PUPIL || which == AOG_FIELD_TC_STAGE1) {
     if (c.precision != AOG_PRECISION_TENSOR) AOG_FAIL(AOG_ERR_INVALID, "tensor-path field on an FP64 handle");
     return aog_tensor_get_field(env, which, env_index % env->chunk, host_out, count);
   }
   // optical fields: recompute the FP64 chain for that one env from the current state
-  if (!env->bufA) {
-    int rc;
-    const size_t ch = env->chunk;
-    if ((rc = dev_alloc(env, &env->bufA, ch * P))) return rc;
-    if ((rc = dev_alloc(env, &env->bufB, ch * (size_t)c.num_pupil_pixels * std::max(c.num_focal_pixels, c.num_pupil_pixels)))) return rc;
-    if ((rc = dev_alloc(env, &env->bufC, ch * std::max<size_t>(env->NF2, P)))) return rc;
-  }
+  { int rc = ensure_f64_scratch(env); if (rc) return rc; }
   aog_outputs d = device_outputs(env);
   aog_outputs none{};
   none.obs_f64 = d.obs_f64;   // optics_chunk_f64 applies the env offset itself

@@ -37,6 +37,24 @@ struct aog_env {
   double2* t_scrW2 = nullptr;      // [Np][N2]
   double2* t_scrW2T = nullptr;     // [N2][Np]
 
+  // ---- Shack-Hartmann tables / state ----
+  int sh_num_sub = 0, sh_num_pix = 0;
+  double sh_amplitude = 0.0, sh_weight_dt = 0.0;
+  double* t_sh_mla = nullptr;      // [P]
+  double2* t_sh_C = nullptr;       // [Np][Np]
+  double2* t_sh_CT = nullptr;      // transpose
+  int* t_sh_off = nullptr;         // [Nsub+1]
+  int* t_sh_pix = nullptr;         // [npix]
+  double* t_sh_px = nullptr;       // [npix]
+  double* t_sh_py = nullptr;       // [npix]
+  double* t_sh_offset = nullptr;   // [2][Nsub]
+  double* t_sh_recon = nullptr;    // [K][2 Nsub]
+  double* t_sh_act0 = nullptr;     // [K]
+  double* act_sh = nullptr;        // [B][K] actuators of the SH integrator's mirror
+  double* o_action = nullptr;      // [B][K] device staging for aog_sh_step_host
+  double* sh_noisy_in = nullptr;   // [B][P] staging for an injected camera image
+  int64_t sh_draws = 0;
+
   // ---- per-env state (device) ----
   double* screens = nullptr;       // [B][P], ring-buffered along x (column_origin)
   double* act = nullptr;           // [B][K] DM actuators (after normalisation)

@@ -450,6 +450,104 @@ static __global__ void k_scr_combine(double* __restrict__ screens, const double2
   *s = accumulate ? (*s + v) : v;
 }
 
+// --------------------------------------------------------------------------------------
+// Shack-Hartmann integrator (AO_env.py:254-290).
+// field: E = amp A exp(i (S / l_wfs + 2 k s_sh + mla_phase)),  s_sh = M a_sh  (atmosphere, the SH mirror,
+// magnifier 1/m folded in amp, micro-lens array); the Fresnel step is E_out = C E C^T (k_zgemm x 2).
+// --------------------------------------------------------------------------------------
+template <int ET>
+static __global__ void k_sh_field_f64(const double* __restrict__ screens, const double* __restrict__ act,
+                                      const double* __restrict__ modes, const double* __restrict__ aperture,
+                                      const double* __restrict__ mla_phase, double2* __restrict__ E, int P, int Np,
+                                      int K, int env0, int nB, int col_origin, double l_wfs, double amp) {
+  extern __shared__ double sh_act[];   // [ET][K]
+  const int e0 = blockIdx.y * ET;
+  for (int i = threadIdx.x; i < ET * K; i += blockDim.x) {
+    int e = i / K, k = i - e * K;
+    sh_act[i] = (e0 + e < nB) ? act[(size_t)(env0 + e0 + e) * K + k] : 0.0;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double s[ET];
+#pragma unroll
+  for (int e = 0; e < ET; ++e) s[e] = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double m = modes[(size_t)k * P + p];
+#pragma unroll
+    for (int e = 0; e < ET; ++e) s[e] = fma(m, sh_act[e * K + k], s[e]);
+  }
+  const double ap = aperture[p], ml = mla_phase[p];
+  const int y = p / Np;
+  int xp = p - y * Np + col_origin;
+  if (xp >= Np) xp -= Np;
+  const double kw = 6.283185307179586476925286766559 / l_wfs;
+#pragma unroll
+  for (int e = 0; e < ET; ++e)
+    if (e0 + e < nB) {
+      const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)y * Np + xp];
+      double sn, cs;
+      sincos(S / l_wfs + 2.0 * s[e] * kw + ml, &sn, &cs);
+      E[(size_t)(e0 + e) * P + p] = make_double2(amp * ap * cs, amp * ap * sn);
+    }
+}
+
+// camera image (power x dt), photon noise, flux-weighted centroids per selected lenslet (one warp each,
+// deterministic), slopes, leaky integrator a <- 0.99 a - 0.3 R slopes.  Block per env.
+static __global__ void k_sh_centroid_update(const double2* __restrict__ F, long long strideF,
+                                            const int* __restrict__ off, const int* __restrict__ pix,
+                                            const double* __restrict__ px, const double* __restrict__ py,
+                                            const double* __restrict__ offset, const double* __restrict__ recon,
+                                            double* __restrict__ act_sh, double* __restrict__ action_out,
+                                            const double* __restrict__ noisy, int P, int K, int Nsub, int env0,
+                                            double weight_dt, int noise_mode, unsigned long long seed,
+                                            unsigned long long env_id_base, unsigned long long draw) {
+  extern __shared__ double slopes[];   // [2 Nsub]
+  const int b = blockIdx.x;
+  const double2* f = F + (size_t)b * strideF;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int m = warp; m < Nsub; m += nw) {
+    double fl = 0.0, sx = 0.0, sy = 0.0;
+    for (int i = off[m] + lane; i < off[m + 1]; i += 32) {
+      const int p = pix[i];
+      double v;
+      if (noise_mode == AOG_SH_NOISE_INJECTED) {
+        v = noisy[(size_t)(env0 + b) * P + p];
+      } else {
+        const double2 e = f[p];
+        v = (e.x * e.x + e.y * e.y) * weight_dt;
+        if (noise_mode == AOG_SH_NOISE_POISSON) {     // hcipy large_poisson: Poisson below 1e6, rounded normal above
+          curandStatePhilox4_32_10_t st;
+          // one Philox subsequence per (global env, pixel); successive SH_step draws are 256 outputs apart
+          curand_init(seed, (env_id_base + env0 + b) * (unsigned long long)P + p, draw * 256ull, &st);
+          v = (v > 1e6) ? rint(v + sqrt(v) * curand_normal_double(&st)) : (double)curand_poisson(&st, v);
+        }
+      }
+      v += 1e-10;                                     // AO_env.py:277
+      fl += v; sx += v * px[i]; sy += v * py[i];
+    }
+    fl = warp_sum(fl); sx = warp_sum(sx); sy = warp_sum(sy);
+    if (lane == 0) {
+      slopes[m] = sx / fl - offset[m];
+      slopes[Nsub + m] = sy / fl - offset[Nsub + m];
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double r = 0.0;
+    for (int m = 0; m < 2 * Nsub; ++m) r += recon[(size_t)k * 2 * Nsub + m] * slopes[m];
+    const size_t i = (size_t)(env0 + b) * K + k;
+    const double a = (1.0 - 0.01) * act_sh[i] - 0.3 * r;
+    act_sh[i] = a;
+    if (action_out) action_out[i] = a;
+  }
+}
+
+static __global__ void k_broadcast_rows(const double* __restrict__ row, double* __restrict__ out, int K, int B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * B) out[i] = row[i % K];
+}
+
 // misc ---------------------------------------------------------------------------------
 static __global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from ._gym_compat import Env, spaces
-from .tables import AOConfig, build_tables, synthesize_screens
+from .tables import AOConfig, build_sh_tables, build_tables, synthesize_screens
 
 
 def _coerce_velocity(atm_type, velocity_value):
@@ -109,8 +109,19 @@ class _AOCore:
         c.seed = self._seed
         self._h = _lib.Handle(c)
         for name in _lib.TABLE_IDS:
-            if name in t.arrays:
+            if name in t.arrays and not name.startswith('sh_'):
                 self._h.set_table(name, t.arrays[name])
+        # Shack-Hartmann integrator (AO_env.py:396-465): calibrated on the host once, tables on the device
+        self.sh_tables = None
+        if SH_operation:
+            sh = build_sh_tables(cfg, t)
+            if tables:
+                sh.update({k: v for k, v in tables.items() if k.startswith('sh_')})
+            self.sh_tables = sh
+            self._h.sh_configure(sh['sh_num_sub'], sh['sh_pix_index'].size, sh['sh_amplitude'], sh['sh_weight_dt'])
+            for name in _lib.TABLE_IDS:
+                if name.startswith('sh_'):
+                    self._h.set_table(name, sh[name])
         # initial screen(s) (hcipy draws one at construction; AO_env.py:370)
         if initial_screens is not None:
             s = np.asarray(initial_screens)
@@ -205,8 +216,16 @@ class AOEnv(_AOCore, Env):
         reward = np.float64(h['reward'][0])
         return h['obs_f16'][0].copy(), reward, done, False, {"power": float(h['power'][0])}
 
-    def SH_step(self):
-        raise NotImplementedError('SH_step (AO_env.py:254-290) is not built yet; see DESIGN.md')
+    def SH_step(self, noise='poisson', noisy_image=None):
+        """AO_env.py:254-290 -> (action float64 [act_dim], torch.tensor([1])).  The action is the state of the
+        integrator's own mirror after ``a <- 0.99 a - 0.3 R slopes``.  Parity-only arguments: ``noise`` =
+        'poisson' (device Philox photon noise, the reference's unseeded ``large_poisson``) | 'none' | 'injected'
+        (``noisy_image`` [P] = the camera image after photon noise)."""
+        if not self.SH_operation:
+            raise AttributeError("'AOEnv' object has no attribute 'shwfs'")   # reference: built only with SH_operation
+        import torch
+        action = self._h.sh_step_host(noise, noisy_image)[0]
+        return action, torch.tensor([1])
 
     def render(self, close=False):
         """AO_env.py:156-194.  Reads the three panels' fields back from the device; draws them when
@@ -318,6 +337,23 @@ class AOVecEnv(_AOCore):
         done = self._h.step_device(actions.data_ptr(), dt, self._out, nz_ptr, self._stream())
         self._sync_counters()
         return self.obs, self.reward, (self._true if done else self._false), self._false, {"power": self.power}
+
+    def SH_step(self, noise='poisson', noisy_image=None):
+        """Batched ``SH_step`` (AO_env.py:254-290): -> (actions [B, K] float64 cuda, ones [B] int64)."""
+        torch = self._torch
+        if not self.SH_operation:
+            raise AttributeError("'AOVecEnv' object has no attribute 'shwfs'")
+        if not hasattr(self, 'sh_action'):
+            self.sh_action = torch.empty((self.num_envs, self.num_modes), dtype=torch.float64, device=self.device)
+            self._ones = torch.ones(self.num_envs, dtype=torch.int64, device=self.device)
+        img_ptr = None
+        if noise == 'injected':
+            img = torch.as_tensor(noisy_image).to(self.device, torch.float64).contiguous()
+            if img.numel() != self.num_envs * self.num_pupil_pixels ** 2:
+                raise ValueError('noisy_image must be [B, Np^2]')
+            img_ptr = img.data_ptr()
+        self._h.sh_step_device(self.sh_action.data_ptr(), noise, img_ptr, self._stream())
+        return self.sh_action, self._ones
 
     def set_screens(self, screens):
         """[B, Np^2] torch (cuda, float32/float64) or NumPy array."""

@@ -342,3 +342,98 @@ def build_tables(cfg: AOConfig, rng=None, overrides=None) -> AOTables:
         for k, v in overrides.items():
             (A if isinstance(v, np.ndarray) else S)[k] = v
     return t
+
+
+# ---------------------------------------------------------------- Shack-Hartmann (SH_operation=True)
+def build_sh_tables(cfg: AOConfig, T: AOTables) -> dict:
+    """Tables of the Shack-Hartmann integrator (reference ``shack_hartmann_init``, AO_env.py:396-465, and
+    ``SH_step``, :254-290).
+
+    hcipy chain restated: ``Magnifier(m)`` (grid x m, field / m), ``SquareShackHartmannWavefrontSensorOptics``
+    (lenslet centres ``arange(-D_sh, D_sh, D_sh/12)``, nearest-lenslet phase ``-k d^2 / (2 f)``, ``f = 50 pitch``),
+    ``FresnelPropagator`` over ``f`` -- an angular-spectrum filter with a 2x zero-padded FFT whose transfer
+    function factorises in x and y, so pad -> FFT -> filter -> IFFT -> crop is the separable linear map
+    ``E_out = C E C^T`` with one precomputed ``C [Np, Np]`` -- ``NoiselessDetector`` (image = power x dt,
+    carried on the science focal grid, :412) and the flux-weighted centroid estimator.  Calibration (sub-aperture
+    selection at half the peak flux, reference slopes, push-pull interaction matrix at 0.01 lambda, Tikhonov
+    inverse rcond 1e-3) runs here on the host once, through the same ``C``.
+    """
+    Np, D = cfg.num_pupil_pixels, cfg.telescope_diameter
+    lam = cfg.wavelength_wfs
+    k = 2 * np.pi / lam
+    mag = cfg.sh_diameter / D
+    xp, dp = pupil_coords(Np, D)
+    xs, ds = xp * mag, dp * mag
+    pitch = cfg.sh_diameter / cfg.num_lenslets
+    cen = np.arange(-cfg.sh_diameter, cfg.sh_diameter, pitch)
+    nl = cen.size
+    near = np.argmin(np.abs(xs[:, None] - cen[None, :]), axis=1)              # lenslet of each pixel, per axis
+    lens_of_pixel = (near[:, None] * nl + near[None, :]).ravel()             # [y][x] flat
+    f = cfg.f_number * pitch
+    d2 = ((xs - cen[near]) ** 2)
+    mla_phase = (-(d2[:, None] + d2[None, :]) / (2 * f) * k).ravel()
+
+    q = 2 * np.pi * np.fft.fftfreq(2 * Np, d=ds)
+    h1 = np.exp(-0.5j * (f / k) * q * q)
+    pad = np.zeros((2 * Np, Np), dtype=np.complex128)
+    pad[Np // 2:Np // 2 + Np, :] = np.eye(Np)
+    C = np.fft.ifft(h1[:, None] * np.fft.fft(pad, axis=0), axis=0)[Np // 2:Np // 2 + Np, :]
+
+    xs_det = T['sci_focal_coords']                                            # the detector grid the reference passes
+    if xs_det.size != Np:
+        raise ValueError('SH_operation needs num_pupil_pixels == 240 (the reference reads the camera on the '
+                         '240 x 240 science focal grid, AO_env.py:412)')
+    gx, gy = np.tile(xs_det, Np), np.repeat(xs_det, Np)
+    ap = T['aperture']
+
+    def image(E_pupil, dt):
+        e = (E_pupil / mag * np.exp(1j * mla_phase)).reshape(Np, Np)
+        out = C @ e @ C.T
+        return (np.abs(out) ** 2).ravel() * (ds * ds) * dt
+
+    def sums(img, lenslets):
+        fl = np.bincount(lens_of_pixel, weights=img, minlength=nl * nl)[lenslets]
+        sx = np.bincount(lens_of_pixel, weights=img * gx, minlength=nl * nl)[lenslets]
+        sy = np.bincount(lens_of_pixel, weights=img * gy, minlength=nl * nl)[lenslets]
+        return fl, sx, sy
+
+    # reference image of the bare aperture (unit amplitude, dt = 1; AO_env.py:413-415)
+    img_ref = image(ap.astype(np.complex128), 1.0)
+    present = np.unique(lens_of_pixel)
+    flux, _, _ = sums(img_ref, present)
+    selected = present[flux > 0.5 * flux.max()]
+    centres = np.array((np.tile(cen, nl)[selected], np.repeat(cen, nl)[selected]))
+
+    def slopes(img):
+        fl, sx, sy = sums(img, selected)
+        return np.array((sx / fl, sy / fl)) - centres
+
+    slopes_ref = slopes(img_ref)
+    modes = T['dm_modes']                                                     # [K, P]
+    probe = 0.01 * lam
+    E_cal = T['amp_fiber'] * ap
+    resp = []
+    for i in range(cfg.num_modes):
+        acc = 0
+        for amp in (-probe, probe):
+            acc = acc + amp * slopes(image(E_cal * np.exp(2j * k * amp * modes[i]), 1.0)) / probe ** 2
+        resp.append(acc.ravel())
+    resp = np.stack(resp, axis=1)                                             # [2 Nsub, K]
+    U, S, Vt = np.linalg.svd(resp, full_matrices=False)
+    recon = (Vt.T * (S / (S * S + (1e-3 * S.max()) ** 2))) @ U.T              # [K, 2 Nsub]
+
+    # per selected lenslet: CSR list of its pixels (deterministic warp reductions on the device)
+    order = np.argsort(lens_of_pixel, kind='stable')
+    slot_of_lens = np.full(nl * nl, -1)
+    slot_of_lens[selected] = np.arange(selected.size)
+    keep = order[slot_of_lens[lens_of_pixel[order]] >= 0]
+    slots = slot_of_lens[lens_of_pixel[keep]]
+    offsets = np.concatenate(([0], np.cumsum(np.bincount(slots, minlength=selected.size)))).astype(np.int32)
+    act0 = np.zeros(cfg.num_modes)
+    act0[-1] = probe          # the calibration loop leaves its last probe on the SH mirror (AO_env.py:446-447)
+    return dict(
+        sh_mla_phase=mla_phase, sh_fresnel=C, sh_pix_offsets=offsets, sh_pix_index=keep.astype(np.int32),
+        sh_pix_x=gx[keep], sh_pix_y=gy[keep], sh_offset=(centres + slopes_ref), sh_recon=recon, sh_act0=act0,
+        sh_amplitude=float(T['amp_flux'] / mag), sh_weight_dt=float(ds * ds * cfg.delta_t),
+        sh_num_sub=int(selected.size), sh_selected=selected, sh_slopes_ref=slopes_ref, sh_response=resp,
+    )

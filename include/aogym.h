@@ -13,7 +13,7 @@
  *                                                              (AO_env.py:77,370)
  *   aog_reset[_host]                <- AOEnv.reset             (AO_env.py:74-103)
  *   aog_step[_host]                 <- AOEnv.step + reward_function (AO_env.py:106-153,468-503)
- *   aog_sh_calibrate / aog_sh_step[_host]
+ *   aog_sh_configure + SH tables / aog_sh_step[_host]
  *                                   <- shack_hartmann_init / SH_step (AO_env.py:396-465,254-290)
  *   aog_get_field                   <- the fields AOEnv.render reads (AO_env.py:156-194)
  *
@@ -79,8 +79,20 @@ typedef enum aog_table {
   AOG_TABLE_SCR_W1 = 14,    /* [Np][Np]  complex */
   AOG_TABLE_SCR_C2 = 15,    /* [N2][N2]  spectral amplitudes, fine scale */
   AOG_TABLE_SCR_W2 = 16,    /* [Np][N2]  complex */
-  AOG_TABLE_COUNT = 17
+  /* Shack-Hartmann integrator (SH_operation; AO_env.py:396-465), sizes from aog_sh_configure */
+  AOG_TABLE_SH_MLA_PHASE = 17,   /* [P]        micro-lens array phase [rad] at lambda_wfs */
+  AOG_TABLE_SH_FRESNEL = 18,     /* [Np][Np]   complex separable Fresnel operator C: E_out = C E C^T */
+  AOG_TABLE_SH_PIX_OFFSETS = 19, /* [Nsub+1]   int32 CSR offsets of the pixels of each selected lenslet */
+  AOG_TABLE_SH_PIX_INDEX = 20,   /* [npix]     int32 flat pixel index */
+  AOG_TABLE_SH_PIX_X = 21,       /* [npix]     detector x coordinate of that pixel */
+  AOG_TABLE_SH_PIX_Y = 22,       /* [npix] */
+  AOG_TABLE_SH_OFFSET = 23,      /* [2][Nsub]  lenslet centre + reference slope (subtracted from the centroid) */
+  AOG_TABLE_SH_RECON = 24,       /* [K][2 Nsub] reconstruction matrix */
+  AOG_TABLE_SH_ACT0 = 25,        /* [K]        initial actuators of the SH mirror (broadcast to all envs) */
+  AOG_TABLE_COUNT = 26
 } aog_table;
+
+enum { AOG_SH_NOISE_NONE = 0, AOG_SH_NOISE_POISSON = 1, AOG_SH_NOISE_INJECTED = 2 };
 
 typedef enum aog_field {
   AOG_FIELD_SCREEN = 0,      /* [P]     achromatic screen S (phase = S / lambda), logical order */
@@ -91,7 +103,9 @@ typedef enum aog_field {
   AOG_FIELD_ACTUATORS = 5,   /* [K]     DM actuators after normalisation */
   /* tensor-path intermediates of the last step (tests / debugging), hi + lo recombined: */
   AOG_FIELD_TC_PUPIL = 6,    /* [P]       complex, unit modulus x aperture */
-  AOG_FIELD_TC_STAGE1 = 7    /* [Nf*Np]   complex stage-1 product M1~ . E~ (unit-modulus twiddles) */
+  AOG_FIELD_TC_STAGE1 = 7,   /* [Nf*Np]   complex stage-1 product M1~ . E~ (unit-modulus twiddles) */
+  AOG_FIELD_SH_IMAGE = 8,    /* [P]       noise-free Shack-Hartmann camera image for the current state */
+  AOG_FIELD_SH_ACTUATORS = 9 /* [K]       actuators of the SH integrator's own mirror */
 } aog_field;
 
 typedef struct aog_config {
@@ -173,6 +187,14 @@ AOG_API int aog_step(aog_env* env, const void* actions_dev, int act_dtype, const
              const aog_outputs* out_dev, int32_t* done_out, void* stream);
 AOG_API int aog_step_host(aog_env* env, const void* actions_host, int act_dtype, const double* noise_host,
                   const aog_outputs* out_host, int32_t* done_out);
+
+/* Shack-Hartmann integrator (AOEnv.SH_step, AO_env.py:254-290).  aog_sh_configure sizes the SH tables
+ * (set them afterwards with aog_set_table).  noise_mode: AOG_SH_NOISE_*; `noisy_image` ([N][P] FP64, the
+ * camera image AFTER photon noise) is read only in INJECTED mode.  action_out: [N][K] FP64. */
+AOG_API int aog_sh_configure(aog_env* env, int num_sub, int num_pix, double amplitude, double weight_dt);
+AOG_API int aog_sh_step(aog_env* env, int noise_mode, const double* noisy_image_dev, double* action_out_dev,
+                        void* stream);
+AOG_API int aog_sh_step_host(aog_env* env, int noise_mode, const double* noisy_image_host, double* action_out_host);
 
 AOG_API int aog_get_counters(const aog_env* env, aog_counters* out);
 AOG_API int aog_set_counters(aog_env* env, const aog_counters* in);

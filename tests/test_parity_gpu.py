@@ -263,3 +263,86 @@ def test_get_state_set_state_roundtrip_and_render_fields():
     assert 0 < fp.sum() <= 1.0 + 1e-9
     np.testing.assert_allclose(env.last_render['obs_power'], env.last_obs_f64, rtol=1e-12)
     env.close()
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_config4_shack_hartmann_closed_loop(precision):
+    """BASELINE config 4 shape: dynamic v = 20 m/s, r0 = 0.10, 64 modes, strehl_ratio, SH_operation=True.
+    SH_step (AO_env.py:254-290) then step with the unscaled action (:115-116), closed loop, against the oracle:
+    noise-free camera, then an injected photon-noise image; finally the device's own Philox photon noise."""
+    from oracle.ao_oracle import OracleAOEnv, hcipy_large_poisson
+    kw = dict(atm_type='dynamic', atm_vel=20, atm_fried=0.10, act_dim=64, obs_dim=2, rew_type='strehl_ratio',
+              timesteps_per_episode=4, SH_operation=True)
+    scr = _screen(12, 0.10)
+    ref = OracleAOEnv(**kw, initial_screen=scr, seed=5)
+    lay, sh = ref.layer, ref.shwfs
+    idx = sh.estimation_subapertures
+    tabs = dict(ar_stencil=np.flatnonzero(lay.stencil_left).astype(np.int32), ar_A=lay.A_horizontal,
+                ar_B=lay.B_horizontal, sh_recon=ref.reconstruction_matrix,
+                sh_offset=np.array((sh.mla_x[idx], sh.mla_y[idx])) + ref.slopes_ref)
+    env = _mk(precision, **kw, initial_screen=scr, tables=tabs)
+    assert env.sh_tables['sh_num_sub'] == idx.size
+    rng = np.random.default_rng(13)
+    rtol = RTOL[precision]
+    env.reset(), ref.reset()
+    for t in range(4):
+        if t < 2:
+            a, one = env.SH_step(noise='none')
+            ra, _ = ref.SH_step(poisson=False)
+        else:
+            ref.SH_step(poisson=False)                       # fills last_sh_image for the current state ...
+            ref.deformable_mirror_shack.actuators = ra.copy()  # ... and undo its integrator update
+            noisy = hcipy_large_poisson(ref.last_sh_image, rng).astype('float')
+            np.testing.assert_allclose(env._h.get_field('sh_image'), ref.last_sh_image,
+                                       atol=1e-9 * ref.last_sh_image.max())
+            a, one = env.SH_step(noise='injected', noisy_image=noisy)
+            ra, _ = ref.SH_step(poisson_image=noisy)
+        ra = np.array(ra)
+        assert a.dtype == np.float64 and a.shape == (64,) and int(one[0]) == 1
+        np.testing.assert_allclose(a, ra, rtol=0, atol=1e-8 * np.abs(ra).max())
+        noise = rng.standard_normal((ref.num_extrusions_for_next_step(), 240))
+        o, r, d, _, info = env.step(a, extrusion_noise=noise)
+        ro, rr, rd, _, rinfo = ref.step(ra, extrusion_noise=noise)
+        assert d == rd
+        _close(env.last_obs_f64, ref.last_obs_f64, max(rtol, 1e-6), 'obs')
+        _close(r, rr, max(rtol, 1e-6), 'reward')
+        _close(info['power'], rinfo['power'], max(rtol, 1e-6), 'power')
+    # device photon noise: perturbs the action at the shot-noise level, differently per draw
+    a0 = env._h.get_field('sh_actuators')
+    st = env.get_state()
+    acts = []
+    for k in range(3):
+        env._h.set_table('sh_act0', a0)      # same integrator state before every draw
+        acts.append(env.SH_step(noise='poisson' if k else 'none')[0])
+    d1, d2 = acts[1] - acts[0], acts[2] - acts[0]
+    scale = np.abs(acts[0]).max()
+    assert 0 < np.abs(d1).max() < 1e-2 * scale and 0 < np.abs(d2).max() < 1e-2 * scale
+    assert not np.array_equal(d1, d2)
+    env.close()
+
+
+def test_vec_env_shack_hartmann_matches_single():
+    import torch
+    from adaptive_optics_gym_b200 import AOVecEnv
+    kw = dict(atm_type='dynamic', atm_vel=20, atm_fried=0.10, act_type='zernike', act_dim=6, obs_dim=2,
+              timesteps_per_episode=3, SH_operation=True, seed=2)
+    B = 5
+    scr = np.stack([_screen(40 + i, 0.10) for i in range(B)])
+    vec = AOVecEnv(B, **kw, initial_screens=scr)
+    singles = [_mk('f64', **kw, initial_screen=scr[i]) for i in range(B)]
+    vec.reset()
+    for s in singles:
+        s.reset()
+    for t in range(2):
+        acts, ones = vec.SH_step(noise='none')
+        assert acts.shape == (B, 6) and acts.is_cuda and int(ones.sum()) == B
+        obs, rew, done, _, info = vec.step(acts)
+        torch.cuda.synchronize()
+        for i, s in enumerate(singles):
+            a1, _ = s.SH_step(noise='none')
+            np.testing.assert_array_equal(acts[i].cpu().numpy(), a1)
+            _, r1, _, _, _ = s.step(a1)
+            assert rew[i].item() == r1        # same Philox extrusion noise: stream = global env id ... of env 0
+            break                             # only env 0 shares env_id_base with its single twin
+    for e in [vec] + singles:
+        e.close()

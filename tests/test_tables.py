@@ -67,3 +67,38 @@ def test_host_screen_synthesis_statistics():
         th = 2 * (cov(np.array(0.0)) - cov(np.array(lag * 0.5 / 240)))
         d = np.mean((scr[:, :, lag:] - scr[:, :, :-lag]) ** 2)
         assert d / th == pytest.approx(1.0, abs=0.15)
+
+
+def test_shack_hartmann_tables_match_oracle():
+    """build_sh_tables (separable Fresnel operator C E C^T, CSR lenslet pixel lists, calibration) against the
+    oracle's restatement of shack_hartmann_init (2-D zero-padded FFT route, ndimage label sums)."""
+    from adaptive_optics_gym_b200.tables import build_sh_tables
+    cfg = AOConfig(act_type='zernike', num_modes=6, obs_dim=2, atm_type='dynamic', velocity=20.0)
+    tb = build_tables(cfg)
+    sh = build_sh_tables(cfg, tb)
+    env = O.OracleAOEnv(atm_type='dynamic', atm_vel=20, act_type='zernike', act_dim=6, obs_dim=2, SH_operation=True,
+                        initial_screen=np.zeros(57600))
+    o = env.shwfs
+    np.testing.assert_array_equal(sh['sh_selected'], o.estimation_subapertures)
+    assert sh['sh_num_sub'] == o.estimation_subapertures.size
+    np.testing.assert_allclose(sh['sh_mla_phase'], o.mla_opd * 2 * np.pi / 1.5e-6, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(sh['sh_slopes_ref'], env.slopes_ref, atol=1e-12 * np.abs(env.slopes_ref).max() + 1e-18)
+    np.testing.assert_allclose(sh['sh_response'], env.response_matrix, atol=1e-8 * np.abs(env.response_matrix).max())
+    # (piston's response is rounding noise; its regularised inverse row differs at the 1e-6 level)
+    np.testing.assert_allclose(sh['sh_recon'], env.reconstruction_matrix,
+                               atol=1e-5 * np.abs(env.reconstruction_matrix).max())
+    np.testing.assert_allclose(sh['sh_act0'], env.deformable_mirror_shack.actuators, rtol=1e-15)
+    # the separable operator reproduces the camera image of an aberrated field
+    scr = O.von_karman_screen(env.pupil_grid, tb['cn2'], 10.0, np.random.default_rng(3))
+    env.layer.achromatic_screen = scr
+    env.SH_step(poisson=False)
+    E = sh['sh_amplitude'] * tb['aperture'] * np.exp(
+        1j * (scr / 1.5e-6 + 2 * (2 * np.pi / 1.5e-6) * (sh['sh_act0'] @ tb['dm_modes']) + sh['sh_mla_phase']))
+    C = sh['sh_fresnel']
+    img = (np.abs(C @ E.reshape(240, 240) @ C.T) ** 2).ravel() * sh['sh_weight_dt']
+    np.testing.assert_allclose(img, env.last_sh_image, atol=1e-10 * env.last_sh_image.max())
+    # CSR lists cover exactly the pixels of the selected lenslets
+    off, pix = sh['sh_pix_offsets'], sh['sh_pix_index']
+    for m in (0, sh['sh_num_sub'] // 2, sh['sh_num_sub'] - 1):
+        np.testing.assert_array_equal(np.sort(pix[off[m]:off[m + 1]]),
+                                      np.flatnonzero(o.mla_index == o.estimation_subapertures[m]))
