@@ -99,6 +99,7 @@ def load():
         'aog_chunk_size': (C.c_int, [P]),
         'aog_set_timing': (C.c_int, [P, C.c_int]),
         'aog_last_mft_ms': (C.c_double, [P]),
+        'aog_last_kernel_ms': (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -292,6 +293,11 @@ class Handle:
 
     def set_timing(self, on):
         self.check(self.lib.aog_set_timing(self._h, int(bool(on))), 'aog_set_timing')
+
+    def last_kernel_ms(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.check(self.lib.aog_last_kernel_ms(self._h, C.byref(a), C.byref(b), C.byref(c)), 'aog_last_kernel_ms')
+        return dict(field=a.value, stage1=b.value, stage2=c.value)
 
     def last_mft_ms(self):
         return float(self.lib.aog_last_mft_ms(self._h))

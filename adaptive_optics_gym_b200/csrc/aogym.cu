@@ -312,6 +312,8 @@ int aog_create(const aog_config* cfg, aog_env** out) {
   AOG_CUDA(cudaStreamCreate(&env->own_stream));   // blocking: ordered with the default stream
   AOG_CUDA(cudaEventCreate(&env->ev0));
   AOG_CUDA(cudaEventCreate(&env->ev1));
+  AOG_CUDA(cudaEventCreate(&env->evf));
+  AOG_CUDA(cudaEventCreate(&env->evm));
   return AOG_OK;
 }
 
@@ -334,6 +336,8 @@ void aog_destroy(aog_env* env) {
   if (env->own_stream) cudaStreamDestroy(env->own_stream);
   if (env->ev0) cudaEventDestroy(env->ev0);
   if (env->ev1) cudaEventDestroy(env->ev1);
+  if (env->evf) cudaEventDestroy(env->evf);
+  if (env->evm) cudaEventDestroy(env->evm);
   delete env;
 }
 
@@ -834,6 +838,20 @@ int aog_set_timing(aog_env* env, int enabled) {
   if (!env) return AOG_ERR_INVALID;
   env->timing = enabled != 0;
   env->ev_valid = false;
+  return AOG_OK;
+}
+
+int aog_last_kernel_ms(aog_env* env, double* field_ms, double* stage1_ms, double* stage2_ms) {
+  if (!env) return AOG_ERR_INVALID;
+  if (!env->ev_valid || env->cfg.precision != AOG_PRECISION_TENSOR) AOG_FAIL(AOG_ERR_STATE, "no timed tensor-path step yet");
+  AOG_CUDA(cudaEventSynchronize(env->ev1));
+  float a = 0.f, b = 0.f, c = 0.f;
+  AOG_CUDA(cudaEventElapsedTime(&a, env->evf, env->ev0));
+  AOG_CUDA(cudaEventElapsedTime(&b, env->ev0, env->evm));
+  AOG_CUDA(cudaEventElapsedTime(&c, env->evm, env->ev1));
+  if (field_ms) *field_ms = a;
+  if (stage1_ms) *stage1_ms = b;
+  if (stage2_ms) *stage2_ms = c;
   return AOG_OK;
 }
 

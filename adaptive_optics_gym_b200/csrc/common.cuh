@@ -86,7 +86,7 @@ struct aog_env {
   void* tensor_state = nullptr;     // TensorState (tensor_path.cu) when precision == TENSOR
   cudaStream_t own_stream = nullptr;
   bool timing = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evf = nullptr, evm = nullptr;   // evf: before the field kernel, evm: between the MFT stages
   bool ev_valid = false;
 };
 

@@ -44,6 +44,7 @@ struct TensorState {
   __half* E_hi = nullptr; __half* E_lo = nullptr;     // [chunk][240][480]  pupil field, x-major
   __half* T_hi = nullptr; __half* T_lo = nullptr;     // [chunk][128][480]  stage-1 product
   float* lpw = nullptr;                               // [J][128][128] fibre modes * weight / max
+  float* lpwq = nullptr;                              // the same, [J][v / 4][u][4 v] (coalesced epilogue reads)
   // atmospheric phase / pi reduced to [-1, 1], FP32, tiled for the field kernel's bulk prefetch:
   // [env / 32][Np xp][Np / 16 chunks][2 = {lambda_wfs, lambda_sci}][32 envs][16 pixels], ring-buffered in xp,
   // the four 16-byte pieces of each env row pre-swizzled (piece j at j ^ ((env >> 1) & 3)) so the
@@ -59,6 +60,8 @@ struct TensorState {
   double2* m2oT = nullptr;                            // [n][Np] transposed obs table
   int* err_flag = nullptr;                            // device flag set by a timed-out barrier wait
   CUtensorMap tmA1_hi, tmA1_lo, tmE_hi, tmE_lo, tmT_hi, tmT_lo, tmB2_hi, tmB2_lo;
+  CUtensorMap tmT128_hi, tmT128_lo;
+  CUtensorMap tmTout_hi, tmTout_lo;                   // stage-1 epilogue stores: 128 rows x 16 columns, SWIZZLE_32B                   // stage-1 product, one env (128 rows) per box
   CUtensorMap tmAct_hi, tmAct_lo, tmModes_hi, tmModes_lo;
   double pupil_weight = 0.0;                          // |M1| (grid weight folded in the table)
   double lpw_scale = 0.0;
@@ -178,8 +181,10 @@ struct TcParams {
   __half* T_hi; __half* T_lo;
   // MODE 1 epilogue: fibre projection, raw sums [env][J][2] (re from cluster rank 0, im from rank 1)
   const float* lpw;     // [J][128][128]
+  const float* lpwq;    // same weights as [J][128 / 4 (v)][128 (u)][4 (v)]
   double* coef_raw;
   int J;
+  int dbg;              // AOG_TC_DEBUG bits (tuning experiments only): 1 no MMA, 2 no TMA, 4 no epilogue work
   int* err_flag;
 };
 
@@ -413,6 +418,356 @@ k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUt
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- pair-MMA MFT kernel
+// k_mft2: both MFT stages as cta_group::2 MMAs (M = 256 over the CTA pair, each CTA holds 128 rows of A and
+// HALF of the B tile in its own shared memory, so no operand is multicast or duplicated and the per-SM
+// shared-memory traffic per MMA drops by a third against the cta_group::1 kernel above):
+//   MODE 0 (stage 1, item = env):      A = twiddle rows (CTA 0: Tr rows, CTA 1: Ti rows), B = the env's field,
+//                                      N = 240 pupil columns x (CTA r stages x in [120 r, 120 r + 120))
+//   MODE 1 (stage 2, item = env pair): F^T: A = twiddle rows (CTA 0: Fr, CTA 1: Fi; M = focal column u),
+//                                      B = the stage-1 products of the two envs stacked along N = 2 x 128
+//                                      focal rows v (CTA r stages env 2 item + r)
+// Only the leader CTA (rank 0) issues MMAs; both CTAs' TMA loads complete on the leader's `full` barrier,
+// tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs, and both CTAs' epilogue warps arrive on the
+// leader's `tmem_empty`.  8 epilogue warps per CTA (two per TMEM lane group, half of the columns each).
+constexpr int M2_STAGES = 5;
+constexpr int M2_STAGE_BYTES = 4 * A_TILE;          // 32 KB: [A_hi][A_lo][B_hi slot][B_lo slot], 8 KB each
+constexpr int M2_EPI_WARPS = 8;
+constexpr int M2_THREADS = (2 + M2_EPI_WARPS) * 32; // 320
+constexpr int M2_OUT_TILE = 128 * 16 * 2;           // 4 KB: 128 rows x 16 fp16 of the stage-1 product (SWIZZLE_32B)
+constexpr int M2_OUT_BUFS = 3;                      // per column half: ring of (hi, lo) tile pairs for the TMA stores
+constexpr int M2_EPI_BYTES = 2 * M2_OUT_BUFS * 2 * M2_OUT_TILE;   // 48 KB
+constexpr int M2_SMEM_BYTES = M2_STAGES * M2_STAGE_BYTES + M2_EPI_BYTES + 1024 /*align*/ + 4096 /*barriers + reduction scratch*/;
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// JT: compile-time bound on the fibre modes held in registers (3 = the reference's LP01 + 2 x LP11; 8 = generic)
+template <int MODE, int JT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(M2_THREADS, 1)
+k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+       const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo, const TcParams p) {
+  constexpr int N_MMA = (MODE == 0) ? TC_NP : 2 * TC_NF;             // 240 | 256
+  constexpr int B_ROWS = N_MMA / 2;                                  // rows of B each CTA stages: 120 | 128
+  // bytes landing per stage over BOTH CTAs (all of them complete on the leader's barrier)
+  constexpr uint32_t TX_BYTES = 2 * (2 * A_TILE + 2 * B_ROWS * KB * 2);
+  constexpr uint32_t IDESC = umma_idesc_f16(256, N_MMA);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* epi = base + M2_STAGES * M2_STAGE_BYTES;      // MODE 0: output tile ring
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi + M2_EPI_BYTES);
+  uint64_t* empty = full + M2_STAGES;
+  uint64_t* tmem_full = empty + M2_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  double* red = reinterpret_cast<double*>(epi + M2_EPI_BYTES + 256);   // [2 bufs][8 warps][2 envs][AOG_MAX_LP]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_lo)) : "memory");
+    for (int s = 0; s < M2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 2 * M2_EPI_WARPS);          // every epilogue warp of both CTAs (used in the leader only)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; completion on the leader's barrier) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        const int b_row0 = (MODE == 0) ? item * TC_NP + (int)rank * B_ROWS : (2 * item + (int)rank) * TC_NF;
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          mbar_wait<32>(&empty[stage], phase ^ 1, p.err_flag, 1);
+          if (p.dbg & 2) { if (rank == 0) mbar_arrive(&full[stage]); if (++stage == M2_STAGES) { stage = 0; phase ^= 1; } continue; }
+          if (rank == 0) mbar_expect_tx(&full[stage], TX_BYTES);
+          const uint32_t s0 = smem_u32(base + stage * M2_STAGE_BYTES);
+          const uint32_t fb = mapa_rank(smem_u32(&full[stage]), 0);
+          const int k0 = kb * KB;
+          tma_load_2d_pair(s0, &tmA_hi, fb, k0, (int)rank * 128);
+          tma_load_2d_pair(s0 + A_TILE, &tmA_lo, fb, k0, (int)rank * 128);
+          tma_load_2d_pair(s0 + 2 * A_TILE, &tmB_hi, fb, k0, b_row0);
+          tma_load_2d_pair(s0 + 3 * A_TILE, &tmB_lo, fb, k0, b_row0);
+          if (++stage == M2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (rank == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        mbar_wait<32>(tmem_empty, tphase ^ 1, p.err_flag, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          mbar_wait(&full[stage], phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t s0 = smem_u32(base + stage * M2_STAGE_BYTES);
+          if (!(p.dbg & 1))
+#pragma unroll
+          for (int ks = 0; ks < KB / 16; ++ks) {
+            const uint32_t acc = (kb | ks) != 0;
+            const uint64_t a_hi = umma_desc_sw64(s0 + ks * 32), a_lo = umma_desc_sw64(s0 + A_TILE + ks * 32);
+            const uint64_t b_hi = umma_desc_sw64(s0 + 2 * A_TILE + ks * 32);
+            const uint64_t b_lo = umma_desc_sw64(s0 + 3 * A_TILE + ks * 32);
+            tc_mma_f16_pair(tmem_base, a_hi, b_hi, IDESC, acc);              // main
+            tc_mma_f16_pair(tmem_base + 256, a_hi, b_lo, IDESC, acc);        // corrections
+            tc_mma_f16_pair(tmem_base + 256, a_lo, b_hi, IDESC, 1);
+          }
+          tc_commit_pair(&empty[stage]);            // frees the slot in both CTAs when these MMAs retire
+          if (++stage == M2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(tmem_full);
+        tphase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps, TMEM lane group = warp % 4, column half = (warp - 2) / 4 =========
+    const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = lg * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    const uint32_t tmem_empty_leader = mapa_rank(smem_u32(tmem_empty), 0);
+    uint32_t tphase = 0;
+    int it = 0;
+    uint32_t out_seq = 0;
+    for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
+      mbar_wait(tmem_full, tphase, p.err_flag, 4);
+      tc_fence_after();
+      if (p.dbg & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+        tphase ^= 1;
+        continue;
+      }
+      if constexpr (MODE == 0) {
+        // Phase 1: drain this warp's accumulator columns (main + corrections) into registers and hand the
+        // TMEM back, so the next env's MMAs run under phase 2.  The 4 warps of a column half own the
+        // 16-column chunks c = 8 half ... (8 | 7 of the 15).
+        const int c0 = half * 8, c_end = half ? TC_NP / 16 : 8;
+        float acc[128];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float v[32], w[32];
+          if (c0 + i + 1 < c_end) {
+            tc_ld32(lane_addr + (c0 + i) * 16, v);
+            tc_ld32(lane_addr + 256 + (c0 + i) * 16, w);
+          } else {
+            tc_ld16(lane_addr + (c0 + i) * 16, v);
+            tc_ld16(lane_addr + 256 + (c0 + i) * 16, w);
+#pragma unroll
+            for (int q = 16; q < 32; ++q) v[q] = w[q] = 0.f;
+          }
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) acc[i * 16 + q] = v[q] + w[q];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+        if (p.dbg & 8) { if (acc[0] == 1.2345f && acc[127] == 6.789f) p.T_hi[0] = __float2half(1.f); tphase ^= 1; continue; }
+        // Phase 2: split fp16 -> swizzled 128 x 16 tiles in shared memory -> TMA stores into
+        // T[env][v][k = rank * 240 + x].
+        uint8_t* ring = epi + half * (M2_OUT_BUFS * 2 * M2_OUT_TILE);
+        const uint32_t sw = (uint32_t)((row >> 2) & 1);                 // SWIZZLE_32B: 16-byte piece ^= address bit 7
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = c0 + i;
+          if (c < c_end) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split_pack2(acc[i * 16 + 2 * q], acc[i * 16 + 2 * q + 1], hi[q], lo[q]);
+            uint8_t* t_hi = ring + (out_seq % M2_OUT_BUFS) * (2 * M2_OUT_TILE);
+            uint8_t* t_lo = t_hi + M2_OUT_TILE;
+            *reinterpret_cast<uint4*>(t_hi + row * 32 + ((0u ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(t_hi + row * 32 + ((1u ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(t_lo + row * 32 + ((0u ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(t_lo + row * 32 + ((1u ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else           asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (lg == 0 && lane == 0) {
+              tma_store_2d(&tmO_hi, smem_u32(t_hi), (int)rank * TC_NP + c * 16, item * 128);
+              tma_store_2d(&tmO_lo, smem_u32(t_lo), (int)rank * TC_NP + c * 16, item * 128);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              // the store issued one chunk ago has left shared memory: with 3 buffers the slot written two
+              // chunks from now is free by the time its writers pass the next barrier
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
+            ++out_seq;
+          }
+        }
+      } else {
+        // Accumulator = F^T: lane = focal column u, TMEM column = env * 128 + focal row v; this warp takes
+        // v in [64 half, 64 half + 64) of both envs of the pair.
+        // Phase 1: drain those columns (main + corrections) into registers and hand the TMEM back.
+        float f0[64], f1[64];
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          const int col = half * 64 + c * 16;
+          float a[32], b[32];
+          tc_ld32(lane_addr + col, a);
+          tc_ld32(lane_addr + 256 + col, b);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) f0[c * 16 + q] = a[q] + b[q];
+          tc_ld32(lane_addr + 128 + col, a);
+          tc_ld32(lane_addr + 256 + 128 + col, b);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) f1[c * 16 + q] = a[q] + b[q];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);   // TMEM is free: the next tile's MMAs may start
+        // Phase 2: fibre projection of my half (rank 0: sum Fr w, rank 1: sum Fi w); one weight load serves
+        // both envs.
+        double acc[2][JT];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int j = 0; j < JT; ++j) acc[e][j] = 0.0;
+        const bool env1_ok = 2 * item + 1 < p.num_envs;
+        // weights lpwq[j][v / 4][u][4 v]: a warp's 32 focal columns u read 512 contiguous bytes per load
+        const float4* wbase = reinterpret_cast<const float4*>(p.lpwq) + (size_t)(half * 16) * TC_NF + row;
+        float4 wq[JT][4];
+        auto load_w = [&](int c) {
+#pragma unroll
+          for (int j = 0; j < JT; ++j)
+            if (j < p.J) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                wq[j][q] = (p.dbg & 16) ? make_float4(1.f, 2.f, 3.f, (float)c)
+                                        : __ldg(wbase + ((size_t)j * (TC_NF / 4) + c * 4 + q) * TC_NF);
+            }
+        };
+        load_w(0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float s0[JT], s1[JT];
+#pragma unroll
+          for (int j = 0; j < JT; ++j) {
+            s0[j] = 0.f; s1[j] = 0.f;
+            if (j < p.J) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w = wq[j][q];
+                s0[j] = fmaf(f0[c * 16 + 4 * q + 0], w.x, s0[j]); s1[j] = fmaf(f1[c * 16 + 4 * q + 0], w.x, s1[j]);
+                s0[j] = fmaf(f0[c * 16 + 4 * q + 1], w.y, s0[j]); s1[j] = fmaf(f1[c * 16 + 4 * q + 1], w.y, s1[j]);
+                s0[j] = fmaf(f0[c * 16 + 4 * q + 2], w.z, s0[j]); s1[j] = fmaf(f1[c * 16 + 4 * q + 2], w.z, s1[j]);
+                s0[j] = fmaf(f0[c * 16 + 4 * q + 3], w.w, s0[j]); s1[j] = fmaf(f1[c * 16 + 4 * q + 3], w.w, s1[j]);
+              }
+            }
+          }
+          if (c + 1 < 4) load_w(c + 1);            // next chunk's weights fly while the sums are folded
+#pragma unroll
+          for (int j = 0; j < JT; ++j)
+            if (j < p.J) {
+              acc[0][j] += (double)s0[j];
+              if (env1_ok) acc[1][j] += (double)s1[j];
+            }
+        }
+        double* rbuf = red + (it & 1) * (M2_EPI_WARPS * 2 * AOG_MAX_LP);
+        const int ew = warp - 2;
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int j = 0; j < JT; ++j)
+            if (j < p.J) {
+              const double a = warp_sum(acc[e][j]);
+              if (lane == 0) rbuf[(ew * 2 + e) * AOG_MAX_LP + j] = a;
+            }
+        asm volatile("bar.sync 1, %0;" ::"n"(M2_EPI_WARPS * 32) : "memory");
+        if (warp == 2 && lane < 2 * p.J) {
+          const int e = lane / p.J, j = lane - e * p.J;
+          const int env = 2 * item + e;
+          if (env < p.num_envs) {
+            double s = 0.0;
+            for (int g4 = 0; g4 < M2_EPI_WARPS; ++g4) s += rbuf[(g4 * 2 + e) * AOG_MAX_LP + j];
+            p.coef_raw[((size_t)env * p.J + j) * 2 + rank] = s;
+          }
+        }
+      }
+      tphase ^= 1;
+    }
+    if (MODE == 0 && lg == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
+  }
+  tc_fence_before();
+  __syncthreads();
+  // neither CTA may exit (or free its TMEM) while the pair's MMAs, loads or barrier signals can still touch it
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -855,7 +1210,8 @@ int make_map(aog_env* env, CUtensorMap* map, const __half* ptr, uint64_t rows, u
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) AOG_FAIL(AOG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return AOG_OK;
@@ -910,6 +1266,7 @@ int aog_tensor_create(aog_env* env) {
   AOG_CUDA(cudaMemset(ts->T_hi, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
   AOG_CUDA(cudaMemset(ts->T_lo, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
   A(talloc(env, &ts->lpw, (size_t)c.num_lp_modes * env->NF2));
+  A(talloc(env, &ts->lpwq, (size_t)c.num_lp_modes * env->NF2));
   if (c.obs_dim > 8) AOG_FAIL(AOG_ERR_UNSUPPORTED, "tensor precision path supports obs_dim <= 8");
   ts->kpad = ((c.num_modes + 63) / 64) * 64;
   ts->act_rows = (int)((ch + 127) / 128) * 128;
@@ -937,6 +1294,10 @@ int aog_tensor_create(aog_env* env) {
   A(make_map(env, &ts->tmE_lo, ts->E_lo, ch * TC_NP, TC_NP / 2));
   A(make_map(env, &ts->tmT_hi, ts->T_hi, (ch + 1) * 128, 64));
   A(make_map(env, &ts->tmT_lo, ts->T_lo, (ch + 1) * 128, 64));
+  A(make_map(env, &ts->tmT128_hi, ts->T_hi, (ch + 1) * 128, 128));
+  A(make_map(env, &ts->tmT128_lo, ts->T_lo, (ch + 1) * 128, 128));
+  A(make_map(env, &ts->tmTout_hi, ts->T_hi, (ch + 1) * 128, 128, TC_K, 16));
+  A(make_map(env, &ts->tmTout_lo, ts->T_lo, (ch + 1) * 128, 128, TC_K, 16));
   A(make_map(env, &ts->tmB2_hi, ts->B2_hi, 256, 128));
   A(make_map(env, &ts->tmB2_lo, ts->B2_lo, 256, 128));
   A(make_map(env, &ts->tmAct_hi, ts->act_hi, ts->act_rows, 128, ts->kpad, 64));
@@ -946,13 +1307,16 @@ int aog_tensor_create(aog_env* env) {
 #undef A
   AOG_CUDA(cudaFuncSetAttribute(k_mft_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   AOG_CUDA(cudaFuncSetAttribute(k_mft_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  AOG_CUDA(cudaFuncSetAttribute(k_mft2<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
+  AOG_CUDA(cudaFuncSetAttribute(k_mft2<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
+  AOG_CUDA(cudaFuncSetAttribute(k_mft2<1, AOG_MAX_LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
   return AOG_OK;
 }
 
 void aog_tensor_destroy(aog_env* env) {
   TensorState* ts = TS(env);
   if (!ts) return;
-  void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->E_hi, ts->E_lo, ts->T_hi, ts->T_lo, ts->lpw,
+  void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->E_hi, ts->E_lo, ts->T_hi, ts->T_lo, ts->lpw, ts->lpwq,
                   ts->hwt, ts->modesK_hi, ts->modesK_lo, ts->act_hi, ts->act_lo, ts->apmask, ts->m1o32, ts->R4,
                   ts->m2oT, ts->err_flag};
   for (void* p : ptrs)
@@ -1012,6 +1376,12 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
         for (int u = 0; u < Nf; ++u)
           f[((size_t)j * Nf + u) * Nf + v] = (float)(m[((size_t)j * Nf + v) * Nf + u] / mx);
     AOG_CUDA(cudaMemcpy(ts->lpw, f.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> g(cnt);
+    for (int j = 0; j < c.num_lp_modes; ++j)
+      for (int v = 0; v < Nf; ++v)
+        for (int u = 0; u < Nf; ++u)
+          g[(((size_t)j * (Nf / 4) + v / 4) * Nf + u) * 4 + (v & 3)] = (float)(m[((size_t)j * Nf + v) * Nf + u] / mx);
+    AOG_CUDA(cudaMemcpy(ts->lpwq, g.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
     ts->have_lp = true;
   } else if (which == AOG_TABLE_DM_MODES) {
     // modes [K][y][x] FP64 -> GEMM B operand [x][y][KPAD] split fp16 (k contiguous, zero padded)
@@ -1160,6 +1530,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
   const double2 norm = make_double2(c.mft_norm_re * c.amp_fiber, c.mft_norm_im * c.amp_fiber);
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     const int nB = std::min(env->chunk, B - e0);
+    if (env->timing) { AOG_CUDA(cudaEventRecord(env->evf, st)); }
     {
       // actuators -> half-turns of DM phase per unit mode (2 k s / pi = 4 s / lambda), split fp16
       const int rows = cdiv(nB, 128) * 128;
@@ -1194,17 +1565,31 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     TcParams p{};
     p.num_envs = nB;
     p.err_flag = ts->err_flag;
+    { const char* d = getenv("AOG_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
     p.T_hi = ts->T_hi; p.T_lo = ts->T_lo;
-    p.lpw = ts->lpw; p.coef_raw = reinterpret_cast<double*>(env->coef); p.J = J;
+    p.lpw = ts->lpw; p.lpwq = ts->lpwq; p.coef_raw = reinterpret_cast<double*>(env->coef); p.J = J;
     p.num_items = nB;
     const int max_clusters = ts->num_sms / 2;
-    k_mft_tc<0><<<2 * std::min(max_clusters, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmE_hi,
-                                                                                    ts->tmE_lo, p);
+    static const int mft_old = getenv("AOG_MFT_OLD") ? atoi(getenv("AOG_MFT_OLD")) : 0;   // bring-up A/B switch: bit 0 stage 1, bit 1 stage 2
+    if (mft_old & 1)
+      k_mft_tc<0><<<2 * std::min(max_clusters, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmE_hi,
+                                                                                      ts->tmE_lo, p);
+    else
+      k_mft2<0, 1><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmE_hi,
+                                                                                       ts->tmE_lo, ts->tmTout_hi, ts->tmTout_lo, p);
     AOG_LAUNCH_CHECK();
+    if (env->timing) { AOG_CUDA(cudaEventRecord(env->evm, st)); }
     if (with_reward) {
       p.num_items = (nB + 1) / 2;
-      k_mft_tc<1><<<2 * std::min(max_clusters, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmB2_hi, ts->tmB2_lo, ts->tmT_hi,
-                                                                                      ts->tmT_lo, p);
+      if (mft_old & 2)
+        k_mft_tc<1><<<2 * std::min(max_clusters, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmB2_hi, ts->tmB2_lo, ts->tmT_hi,
+                                                                                        ts->tmT_lo, p);
+      else if (J <= 3)
+        k_mft2<1, 3><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi,
+                                                                                            ts->tmT128_lo, ts->tmTout_hi, ts->tmTout_lo, p);
+      else
+        k_mft2<1, AOG_MAX_LP><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(
+            ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi, ts->tmT128_lo, ts->tmTout_hi, ts->tmTout_lo, p);
       AOG_LAUNCH_CHECK();
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev1, st)); env->ev_valid = true; }

@@ -269,11 +269,14 @@ def main():
     # roofline of the dominant kernel sequence: MFT GEMMs, CUDA events inside the library
     env._h.set_timing(True)
     mft_ms = []
+    kms = []
     state['t'] = 1          # no reset inside this loop
     for i in range(6):
         step_device(i)
         torch.cuda.synchronize()
         mft_ms.append(env._h.last_mft_ms())
+        if precision == 'tensor':
+            kms.append(env._h.last_kernel_ms())
     env._h.set_timing(False)
     mft_ms = sorted(mft_ms[1:])
     mft = mft_ms[len(mft_ms) // 2]
@@ -299,6 +302,8 @@ def main():
                 'traffic': None, 'kernel': 'MFT stage-1 + stage-2 complex GEMMs', 'ms_per_launch': mft,
                 'envs_per_launch': last_chunk, 'algorithmic_flop_per_env': MFT_FLOP_PER_ENV(Np, Nf),
                 'issued_over_algorithmic': issued, 'peak_source': peak_note}
+    if kms:
+        roofline['kernel_ms'] = {k: sorted(d[k] for d in kms[1:])[len(kms[1:]) // 2] for k in kms[0]}
 
     if rank != 0:
         if world > 1:
