@@ -30,36 +30,38 @@ constexpr int TC_NF = 128;          // focal pixels per side
 constexpr int TC_K = 2 * TC_NP;     // real-embedded contraction length (480)
 constexpr int KB = 32;              // K elements per pipeline stage (64 B rows, SWIZZLE_64B)
 constexpr int NUM_KB = TC_K / KB;   // 15
-constexpr int NUM_STAGES = 4;
 constexpr int A_TILE = 128 * KB * 2;            // 8 KB: 128 rows x 64 B
 constexpr int B_TILE = 256 * KB * 2;            // 16 KB slot (stage 1 uses 240 rows of it)
-constexpr int STAGE_BYTES = 6 * A_TILE;   // 48 KB: stage 1 = 2 A tiles + 2 B slots of 16 KB; stage 2 = 4 A + 2 B tiles
-constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align*/ + 4096 /*barriers + reduction scratch*/;
-constexpr int TC_THREADS = 192;     // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr float PHI_ONE = 4194304.f;   // 2^22 fixed-point units per half-turn of phase
 
 struct TensorState {
   // operands (device)
   __half* A1_hi = nullptr; __half* A1_lo = nullptr;   // [256][480]  stage-1 constant
   __half* B2_hi = nullptr; __half* B2_lo = nullptr;   // [256][480]  stage-2 constant (N-major rows, K contiguous)
-  __half* E_hi = nullptr; __half* E_lo = nullptr;     // [chunk][240][480]  pupil field, x-major
   __half* T_hi = nullptr; __half* T_lo = nullptr;     // [chunk][128][480]  stage-1 product
   float* lpw = nullptr;                               // [J][128][128] fibre modes * weight / max
   float* lpwq = nullptr;                              // the same, [J][v / 4][u][4 v] (coalesced epilogue reads)
-  // atmospheric phase / pi reduced to [-1, 1], FP32, tiled for the field kernel's bulk prefetch:
-  // [env / 32][Np xp][Np / 16 chunks][2 = {lambda_wfs, lambda_sci}][32 envs][16 pixels], ring-buffered in xp,
-  // the four 16-byte pieces of each env row pre-swizzled (piece j at j ^ ((env >> 1) & 3)) so the
-  // shared-memory image is bank-conflict free.
-  float* hwt = nullptr;
+  // atmospheric phase at lambda_wfs, UNREDUCED, int32 fixed point in units of 2^-22 half-turns (PHI_ONE per
+  // half-turn; +-512 half-turns of range), tiled for the phase kernel's bulk prefetch:
+  // [env / 32][Np xp][Np / 16 chunks][32 envs][16 pixels], ring-buffered in xp, the four 16-byte pieces of
+  // each env row pre-swizzled (piece j at j ^ ((env >> 1) & 3)) so the shared-memory image is conflict free.
+  int32_t* hwt = nullptr;
+  // total wavefront phase (atmosphere + DM) at lambda_wfs reduced to [-pi, pi) radians, FP32,
+  // [chunk][Np / 16 (y chunk)][Np x][16 y] (the 120 columns x 16 pixels one CTA needs per K block are one
+  // contiguous 7.5 KB run): written by the phase kernel, read by the stage-1 kernel's field warps, which form
+  // the pupil field on chip -- the field itself never goes to HBM.
+  float* phi = nullptr;
+  CUtensorMap tmPhi;
   __half* modesK_hi = nullptr; __half* modesK_lo = nullptr;   // [Np x][Np y][KPAD] DM modes, k contiguous (GEMM B operand)
   __half* act_hi = nullptr; __half* act_lo = nullptr;         // [chunk rows padded to 128][KPAD] actuators * 4 / lambda_wfs
   uint16_t* apmask = nullptr;                         // [Np x][Np / 16] aperture bits of each 16-pixel column chunk
-  float2* m1o32 = nullptr;                            // [n][Np] first obs-arm table in FP32
   float2* R4 = nullptr;                               // [chunk][Np x][FK_PARTS][n] obs-arm column partial sums
+  float2* m1o32 = nullptr;                            // [n][Np] first obs-arm table in FP32
   int kpad = 64;
   int act_rows = 128;
   double2* m2oT = nullptr;                            // [n][Np] transposed obs table
   int* err_flag = nullptr;                            // device flag set by a timed-out barrier wait
-  CUtensorMap tmA1_hi, tmA1_lo, tmE_hi, tmE_lo, tmT_hi, tmT_lo, tmB2_hi, tmB2_lo;
+  CUtensorMap tmA1_hi, tmA1_lo, tmB2_hi, tmB2_lo;
   CUtensorMap tmT128_hi, tmT128_lo;
   CUtensorMap tmTout_hi, tmTout_lo;                   // stage-1 epilogue stores: 128 rows x 16 columns, SWIZZLE_32B                   // stage-1 product, one env (128 rows) per box
   CUtensorMap tmAct_hi, tmAct_lo, tmModes_hi, tmModes_lo;
@@ -188,239 +190,6 @@ struct TcParams {
   int* err_flag;
 };
 
-// One kernel template for both MFT stages, launched as 2-CTA clusters.  CTA r of a cluster owns one half of
-// the output and receives the operand both halves need by TMA multicast (each CTA fetches half of it):
-//   MODE 0 (stage 1, item = env):      rank r = row half (r = 0: Tr rows, r = 1: Ti rows); A = twiddle rows of
-//                                      that half (own), B = the env's field, 240 x-rows (multicast)
-//   MODE 1 (stage 2, item = env pair): computes F^T: rank r = half of the focal columns (r = 0: Fr, r = 1: Fi);
-//                                      A = twiddle rows of that half (own, M = focal column u), B = the stage-1
-//                                      products of BOTH envs stacked along N (multicast, N = 2 x 128 focal rows v),
-//                                      so every MMA is a full N = 256 instruction
-// TMEM holds SEPARATE accumulators for the main hi.hi chain and for the hi.lo + lo.hi corrections: the
-// tensor core truncates its FP32 accumulation, so every accumulate onto a large sum costs ~ -0.5 ulp; keeping
-// the 2 x 30 tiny correction updates off the main accumulator cuts that bias 3x (tools/tensor_bias_probe.py).
-template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-k_mft_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
-  constexpr int N_MMA = (MODE == 0) ? TC_NP : 2 * TC_NF;             // 240 | 256
-  constexpr uint32_t TX_BYTES = (MODE == 0) ? (2 * A_TILE + 2 * TC_NP * KB * 2) : (2 * A_TILE + 4 * A_TILE);
-  constexpr uint32_t IDESC = umma_idesc_f16(128, N_MMA);
-  // stage layout (48 KB).  MODE 0: [A_hi 8K][A_lo 8K][B_hi 16K slot][B_lo 16K slot]
-  //                        MODE 1: [A_hi 8K][A_lo 8K][T0_hi][T1_hi][T0_lo][T1_lo] (8K each; T pairs contiguous = N 256)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + NUM_STAGES * STAGE_BYTES);
-  uint64_t* empty = full + NUM_STAGES;
-  uint64_t* tmem_full = empty + NUM_STAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  double* red = reinterpret_cast<double*>(base + NUM_STAGES * STAGE_BYTES + 128);   // [2 bufs][4 lane groups][2 envs][AOG_MAX_LP]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t rank;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_hi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_lo)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_hi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_lo)) : "memory");
-    for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }   // empty: both CTAs' MMAs
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 128);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  // the peer's barriers must exist before a multicast copy or a remote commit can signal them
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
-        for (int kb = 0; kb < NUM_KB; ++kb) {
-          mbar_wait<32>(&empty[stage], phase ^ 1, p.err_flag, 1);       // freed by BOTH CTAs (we write into both)
-          mbar_expect_tx(&full[stage], TX_BYTES);
-          const uint32_t s0 = smem_u32(base + stage * STAGE_BYTES);
-          const int k0 = kb * KB;
-          if (MODE == 0) {
-            tma_load_2d(s0, &tmA_hi, &full[stage], k0, (int)rank * 128);
-            tma_load_2d(s0 + A_TILE, &tmA_lo, &full[stage], k0, (int)rank * 128);
-            const uint32_t off = rank * (TC_NP / 2) * KB * 2;           // my 120 rows of the shared field tile
-            tma_load_2d_mc(s0 + 2 * A_TILE + off, &tmB_hi, &full[stage], k0, item * TC_NP + (int)rank * (TC_NP / 2));
-            tma_load_2d_mc(s0 + 2 * A_TILE + B_TILE + off, &tmB_lo, &full[stage], k0, item * TC_NP + (int)rank * (TC_NP / 2));
-          } else {
-            tma_load_2d(s0, &tmA_hi, &full[stage], k0, (int)rank * 128);
-            tma_load_2d(s0 + A_TILE, &tmA_lo, &full[stage], k0, (int)rank * 128);
-            const uint32_t off = rank * 64 * KB * 2;                    // my 64 rows of each shared stage-1 tile
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int row = (2 * item + e) * 128 + (int)rank * 64;
-              tma_load_2d_mc(s0 + (2 + e) * A_TILE + off, &tmB_hi, &full[stage], k0, row);
-              tma_load_2d_mc(s0 + (4 + e) * A_TILE + off, &tmB_lo, &full[stage], k0, row);
-            }
-          }
-          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, tphase = 0;
-      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
-        mbar_wait<32>(tmem_empty, tphase ^ 1, p.err_flag, 2);
-        tc_fence_after();
-        for (int kb = 0; kb < NUM_KB; ++kb) {
-          mbar_wait(&full[stage], phase, p.err_flag, 3);
-          tc_fence_after();
-          const uint32_t s0 = smem_u32(base + stage * STAGE_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < KB / 16; ++ks) {
-            const uint32_t acc = (kb | ks) != 0;
-            // same tile arithmetic for both modes: the B slot is 16 KB (240 rows used | two 128-row tiles)
-            const uint64_t a_hi = umma_desc_sw64(s0 + ks * 32), a_lo = umma_desc_sw64(s0 + A_TILE + ks * 32);
-            const uint64_t b_hi = umma_desc_sw64(s0 + 2 * A_TILE + ks * 32);
-            const uint64_t b_lo = umma_desc_sw64(s0 + 2 * A_TILE + B_TILE + ks * 32);
-            tc_mma_f16(tmem_base, a_hi, b_hi, IDESC, acc);              // main
-            tc_mma_f16(tmem_base + 256, a_hi, b_lo, IDESC, acc);        // corrections
-            tc_mma_f16(tmem_base + 256, a_lo, b_hi, IDESC, 1);
-          }
-          tc_commit_mc(&empty[stage]);              // frees the slot in BOTH CTAs when these MMAs retire
-          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-        }
-        tc_commit(tmem_full);
-        tphase ^= 1;
-      }
-    }
-  } else {
-    // ===================== epilogue: 4 warps, TMEM lane group = warp % 4 =====================
-    const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-    uint32_t tphase = 0;
-    int it = 0;
-    for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
-      mbar_wait(tmem_full, tphase, p.err_flag, 4);
-      tc_fence_after();
-      if constexpr (MODE == 0) {
-        // (main + corrections) -> split fp16, row-major [v][k], my half of k = rank * 240 + x
-        const bool odd = lane & 1;
-#pragma unroll 1
-        for (int c = 0; c < TC_NP / 16; ++c) {
-          float v[16], w[16];
-          tc_ld16(lane_addr + c * 16, v);
-          tc_ld16(lane_addr + 256 + c * 16, w);
-          tc_wait_ld();
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) split_pack2(v[2 * i] + w[2 * i], v[2 * i + 1] + w[2 * i + 1], hi[i], lo[i]);
-          // full-sector stores: lane pairs (rows v, v+1) swap halves so each instruction writes whole sectors
-          const size_t r_even = ((size_t)item * 128 + (row & ~1)) * TC_K + rank * TC_NP + c * 16 + (odd ? 8 : 0);
-          const size_t r_odd = r_even + TC_K;
-          uint32_t xh[4], xl[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            xh[k] = __shfl_xor_sync(0xffffffffu, odd ? hi[k] : hi[4 + k], 1);
-            xl[k] = __shfl_xor_sync(0xffffffffu, odd ? lo[k] : lo[4 + k], 1);
-          }
-          *reinterpret_cast<uint4*>(p.T_hi + r_even) = odd ? make_uint4(xh[0], xh[1], xh[2], xh[3]) : make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(p.T_lo + r_even) = odd ? make_uint4(xl[0], xl[1], xl[2], xl[3]) : make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(p.T_hi + r_odd) = odd ? make_uint4(hi[4], hi[5], hi[6], hi[7]) : make_uint4(xh[0], xh[1], xh[2], xh[3]);
-          *reinterpret_cast<uint4*>(p.T_lo + r_odd) = odd ? make_uint4(lo[4], lo[5], lo[6], lo[7]) : make_uint4(xl[0], xl[1], xl[2], xl[3]);
-        }
-        tc_fence_before();
-        mbar_arrive(tmem_empty);
-      } else {
-        // fibre projection of my half (rank 0: sum Fr w, rank 1: sum Fi w), both envs of the pair.
-        // Accumulator = F^T: lane = focal column u, TMEM column = env * 128 + focal row v.
-        double acc[2][AOG_MAX_LP];
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-          for (int j = 0; j < AOG_MAX_LP; ++j) acc[e][j] = 0.0;
-        const bool env1_ok = 2 * item + 1 < p.num_envs;
-#pragma unroll 1
-        for (int c = 0; c < TC_NF / 16; ++c) {
-          float f0[16], f1[16], g[16];
-          tc_ld16(lane_addr + c * 16, f0);
-          tc_ld16(lane_addr + 256 + c * 16, g);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f0[i] += g[i];
-          tc_ld16(lane_addr + 128 + c * 16, f1);
-          tc_ld16(lane_addr + 256 + 128 + c * 16, g);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f1[i] += g[i];
-#pragma unroll
-          for (int j = 0; j < AOG_MAX_LP; ++j) {
-            if (j < p.J) {
-              // transposed weight table: lpw[j][u = row][v], one load serves both envs
-              const float4* w4 = reinterpret_cast<const float4*>(p.lpw + ((size_t)j * TC_NF + row) * TC_NF + c * 16);
-              float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 w = __ldg(w4 + q);
-                s0 = fmaf(f0[4 * q + 0], w.x, s0); s1 = fmaf(f1[4 * q + 0], w.x, s1);
-                s0 = fmaf(f0[4 * q + 1], w.y, s0); s1 = fmaf(f1[4 * q + 1], w.y, s1);
-                s0 = fmaf(f0[4 * q + 2], w.z, s0); s1 = fmaf(f1[4 * q + 2], w.z, s1);
-                s0 = fmaf(f0[4 * q + 3], w.w, s0); s1 = fmaf(f1[4 * q + 3], w.w, s1);
-              }
-              acc[0][j] += (double)s0;
-              if (env1_ok) acc[1][j] += (double)s1;
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(tmem_empty);                    // TMEM is free: the next tile's MMAs may start
-        double* rbuf = red + (it & 1) * (4 * 2 * AOG_MAX_LP);
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-          for (int j = 0; j < AOG_MAX_LP; ++j)
-            if (j < p.J) {
-              const double a = warp_sum(acc[e][j]);
-              if (lane == 0) rbuf[(lg * 2 + e) * AOG_MAX_LP + j] = a;
-            }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 2 && lane < 2 * p.J) {
-          const int e = lane / p.J, j = lane - e * p.J;
-          const int env = 2 * item + e;
-          if (env < p.num_envs) {
-            double s = 0.0;
-            for (int g4 = 0; g4 < 4; ++g4) s += rbuf[(g4 * 2 + e) * AOG_MAX_LP + j];
-            p.coef_raw[((size_t)env * p.J + j) * 2 + rank] = s;
-          }
-        }
-      }
-      tphase ^= 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  // neither CTA may exit while the peer can still multicast into its smem or signal its barriers
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
-
 // ----------------------------------------------------------------------------- pair-MMA MFT kernel
 // k_mft2: both MFT stages as cta_group::2 MMAs (M = 256 over the CTA pair, each CTA holds 128 rows of A and
 // HALF of the B tile in its own shared memory, so no operand is multicast or duplicated and the per-SM
@@ -468,8 +237,12 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
+// Arrive on a barrier that may live in the peer CTA.  CTA-scope release (the PTX default, as CUTLASS's
+// ClusterBarrier::arrive): what is handed over lives in shared memory and is published to the async proxy by the
+// caller's fence.proxy.async; a cluster-scope release here would also wait for the caller's outstanding global
+// loads (the phase prefetch) and flush L1 on every K block.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -771,19 +544,19 @@ k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
   }
 }
 
-// ----------------------------------------------------------------------------- field kernel
-// k_dm_field_tc: DM surface as a tensor-core GEMM with the whole field formation in its epilogue
-// (reference AO_env.py:119-120 surface, :132-135 atmosphere + DM phase, :139 obs arm, :479-483
-// Strehl sum).
+// ----------------------------------------------------------------------------- phase kernel
+// k_dm_phase_tc: DM surface as a tensor-core GEMM with the wavefront-phase formation in its epilogue
+// (reference AO_env.py:119-120 surface, :132-135 atmosphere + DM phase, :479-483 Strehl sum).
 //
 //   D[env][y] (half-turns of DM phase at lambda_wfs) = act'[env][k] . modes[x][y][k]      per pupil column x
 //
 // A = 128 envs x KPAD (actuators scaled by 4 / lambda_wfs, split fp16), B = the 240 pixels of column x
 // (split fp16 modes, k contiguous), accumulator = 128 TMEM lanes (envs) x 240 columns (pixels), double
 // buffered (2 x 256 columns).  12 epilogue warps (3 per TMEM lane group, each a third of the column)
-// own ONE ENV PER THREAD: add the atmospheric half-turns, sincospif, apply the aperture, split to
-// fp16 hi/lo and store the stage-1 B operand E[env][x][y | 240 + y], accumulate the obs-arm column
-// products and the Strehl sum in registers -- no shuffles, no FP64 in the loop.
+// own ONE ENV PER THREAD: add the atmospheric phase (int32 fixed point, bulk-prefetched tiles), store the
+// total phase (reduced, FP32 radians) for the stage-1 kernel's field warps, and accumulate in registers the
+// obs-arm column sums R[x][v] = sum_y m1o[v][y] E[y][x] (AO_env.py:139; FP32 per 16 pixels, FP64 across)
+// and the Strehl sum sum_ap exp(i phi lambda_wfs / lambda_sci).
 // Work item = (block of 128 envs, column x); each CTA takes a contiguous range of items.
 constexpr int FK_STAGES = 1;                            // the double-buffered TMEM accumulator hides the operand load
 constexpr int FK_A_TILE = 128 * 64 * 2;                 // 16 KB: 128 env rows x 128 B
@@ -794,8 +567,8 @@ constexpr int FK_PARTS = FK_EPI_WARPS / 4;
 constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
 constexpr int FK_SLOTS = 16;                            // Strehl partial slots per env (>= CTAs touching an env block)
 constexpr int FK_MIN_ITEMS = 16;                        // items per CTA at least (bounds the slots)
-constexpr int FK_PF_TILE = 32 * 16 * 4;                 // 2 KB: 32 envs x 16 pixels of phase (one TMA box)
-constexpr int FK_PF_BYTES = FK_EPI_WARPS * 2 * 2 * FK_PF_TILE;   // per warp: 2 buffers x {wfs, sci}
+constexpr int FK_PF_TILE = 32 * 16 * 4;                 // 2 KB: 32 envs x 16 pixels of phase (one bulk copy)
+constexpr int FK_PF_BYTES = FK_EPI_WARPS * 2 * FK_PF_TILE;   // per warp: 2 buffers
 constexpr int FK_AUX_BAR = 256;
 
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -808,11 +581,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// sin / cos of pi * a for |a| up to a few half-turns: reduce to [-1/2, 1/2] turns exactly in FP32, then the
-// SFU (MUFU.SIN / MUFU.COS, abs error 2^-21.4 on [-pi, pi] -- below the FP32 phase rounding already present).
-__device__ __forceinline__ void fast_sincospi(float a, float* s, float* c) {
-  const float t = 0.5f * a;
-  const float x = (t - rintf(t)) * 6.283185307179586f;
+// sin / cos of a fixed-point phase (PHI_ONE units per half-turn): the low 23 bits are the phase mod one turn,
+// exactly; the SFU (MUFU.SIN / MUFU.COS) has abs error 2^-21.4 on [-pi, pi].
+__device__ __forceinline__ void sincos_fixed(int32_t t, float* s, float* c) {
+  const float x = (float)((t << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(x));
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(x));
 }
@@ -830,24 +602,22 @@ struct FieldParams {
   int num_items;         // env blocks x 240 columns
   int items_per_cta;
   int nkb;               // KPAD / 64
-  int n;                 // obs_dim
   int col_origin;
-  int do_strehl;
-  int env0;              // first env of the chunk (index into hw / hs)
-  int dbg;               // AOG_FK_DEBUG bits (tuning experiments only): 1 no E stores, 2 no prefetch, 4 no TMEM load, 8 no fence
-  float sci_ratio;       // lambda_wfs / lambda_sci
-  const float* hwt;     // tiled phase array (see TensorState::hwt)
+  int env0;              // first env of the chunk (index into the tiles)
+  int dbg;               // AOG_FK_DEBUG bits (tuning experiments only): 1 no phi stores, 2 no prefetch, 4 no TMEM load
+  uint32_t sci_ratio_q32; // lambda_wfs / lambda_sci in 0.32 fixed point
+  const int32_t* hwt;    // tiled atmospheric phase (see TensorState::hwt)
   const uint16_t* apmask;
-  const float2* m1o32;
-  __half* E_hi; __half* E_lo;
-  float2* R4;
+  const float2* m1o32;   // [n][Np] first obs-arm table, FP32
+  float* phi;            // [env][Np / 16][Np x][16 y] total phase out, radians in [-pi, pi)
+  float2* R4;            // [env][Np x][FK_PARTS][n] obs-arm column partial sums out
   double2* strehl_part;  // [env][FK_SLOTS]
   int* err_flag;
 };
 
 template <bool STREHL, int NOBS>
 __global__ void __launch_bounds__(FK_THREADS, 1)
-k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constant__ CUtensorMap tmAct_lo,
+k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constant__ CUtensorMap tmAct_lo,
               const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
               const FieldParams p) {
   constexpr int Np = TC_NP;
@@ -864,7 +634,7 @@ k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
   uint64_t* pfbar = tmem_empty + 2;              // [FK_EPI_WARPS][2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pfbar + 2 * FK_EPI_WARPS);
   double2* sred = reinterpret_cast<double2*>(aux + FK_AUX_BAR);          // [FK_PARTS][128 envs]
-  float2* m1o_s = reinterpret_cast<float2*>(aux + FK_AUX_BAR + FK_PARTS * 128 * sizeof(double2));   // [n][Np]
+  float2* m1o_s = reinterpret_cast<float2*>(sred + FK_PARTS * 128);      // [n][Np]
   uint16_t* apmask_s = reinterpret_cast<uint16_t*>(m1o_s + NOBS * Np);  // [Np][Np / 16]
   uint8_t* run_s = reinterpret_cast<uint8_t*>(apmask_s + Np * (Np / 16));   // [Np][2]: first lit chunk, lit count
 
@@ -962,10 +732,10 @@ k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
     int cur_eb = -1;
     int it = 0;
 
-    // Phase prefetch: the warp's 32 envs x 16 pixels of atmospheric half-turns (and the science-band copy)
-    // are one contiguous, pre-swizzled 2 KB (4 KB) tile: a single cp.async.bulk one chunk ahead of the arithmetic.
-    const uint32_t pf_warp = smem_u32(pf + ew * (4 * FK_PF_TILE));
-    const uint8_t* pf_warp_ptr = pf + ew * (4 * FK_PF_TILE);
+    // Phase prefetch: the warp's 32 envs x 16 pixels of atmospheric phase are one contiguous, pre-swizzled
+    // 2 KB tile: a single cp.async.bulk one chunk ahead of the arithmetic.
+    const uint32_t pf_warp = smem_u32(pf + ew * (2 * FK_PF_TILE));
+    const uint8_t* pf_warp_ptr = pf + ew * (2 * FK_PF_TILE);
     uint64_t* pbar = pfbar + 2 * ew;
     uint32_t pphase0 = 0, pphase1 = 0;
     int buf = 0;
@@ -986,19 +756,18 @@ k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
         int xp2 = x2 + p.col_origin;
         if (xp2 >= Np) xp2 -= Np;
         const size_t eb32 = (size_t)(p.env0 + eb2 * 128 + lg * 32) >> 5;
-        const float* src = p.hwt + ((eb32 * Np + xp2) * (Np / 16) + n_ci) * (2 * 32 * 16);
-        constexpr uint32_t bytes = STREHL ? 2 * FK_PF_TILE : FK_PF_TILE;
-        if (!(p.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&pbar[b], bytes);
+        const int32_t* src = p.hwt + ((eb32 * Np + xp2) * (Np / 16) + n_ci) * (32 * 16);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&pbar[b], FK_PF_TILE);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(pf_warp + b * 2 * FK_PF_TILE), "l"(src), "r"(bytes), "r"(smem_u32(&pbar[b])) : "memory");
+                     ::"r"(pf_warp + b * FK_PF_TILE), "l"(src), "r"((uint32_t)FK_PF_TILE), "r"(smem_u32(&pbar[b])) : "memory");
       }
     };
     bool n_ok = next_lit();
     if (n_ok && !(p.dbg & 2)) issue_prefetch(0);
 
     auto flush_strehl = [&](int eb) {
-      // combine the 4 quarter-warps of every env, one partial per (env, CTA slot)
+      // combine the thirds of every env, one partial per (env, CTA slot)
       sred[q * 128 + row] = make_double2(st_re, st_im);
       asm volatile("bar.sync 1, %0;" ::"n"(FK_EPI_WARPS * 32) : "memory");
       if (q == 0) {
@@ -1022,14 +791,12 @@ k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       }
       const int as = it & 1;
       const int env = eb * 128 + row;
-      const bool valid = env < p.num_envs;
-      int xp = x + p.col_origin;
-      if (xp >= Np) xp -= Np;
       mbar_wait(&tmem_full[as], (it >> 1) & 1, p.err_flag, 14);
       tc_fence_after();
-      float obs_re[NOBS], obs_im[NOBS];
+      const bool valid = env < p.num_envs;
+      double obs_re[NOBS], obs_im[NOBS];
 #pragma unroll
-      for (int v = 0; v < NOBS; ++v) obs_re[v] = obs_im[v] = 0.f;
+      for (int v = 0; v < NOBS; ++v) obs_re[v] = obs_im[v] = 0.0;
       float sre = 0.f, sim = 0.f;
       const int run_first = run_s[2 * x], run_end = run_first + run_s[2 * x + 1];
 #pragma unroll 1
@@ -1043,74 +810,77 @@ k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
         const int cb = buf;
         __syncwarp();
         if (!(p.dbg & 2)) {
-        n_ok = next_lit();
-        if (n_ok) issue_prefetch(cb ^ 1);
-        if (cb == 0) { mbar_wait(&pbar[0], pphase0, p.err_flag, 15); pphase0 ^= 1; }
-        else         { mbar_wait(&pbar[1], pphase1, p.err_flag, 16); pphase1 ^= 1; }
+          n_ok = next_lit();
+          if (n_ok) issue_prefetch(cb ^ 1);
+          if (cb == 0) { mbar_wait(&pbar[0], pphase0, p.err_flag, 15); pphase0 ^= 1; }
+          else         { mbar_wait(&pbar[1], pphase1, p.err_flag, 16); pphase1 ^= 1; }
         }
         buf ^= 1;
-        const uint8_t* tile = pf_warp_ptr + cb * 2 * FK_PF_TILE + lane * 64;
+        const uint8_t* tile = pf_warp_ptr + cb * FK_PF_TILE + lane * 64;
         const int sw = (lane >> 1) & 3;                                   // pieces were stored at j ^ ((env >> 1) & 3)
-        float h[16];
+        int32_t t[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 t = *reinterpret_cast<const float4*>(tile + ((j ^ sw) << 4));
-          h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w;
+          const int4 h = *reinterpret_cast<const int4*>(tile + ((j ^ sw) << 4));
+          t[4 * j] = h.x; t[4 * j + 1] = h.y; t[4 * j + 2] = h.z; t[4 * j + 3] = h.w;
         }
         tc_wait_ld();
-        uint32_t rh[8], rl[8], ih[8], il[8];
+        float ph[16];                                                     // total phase at lambda_wfs, [-pi, pi)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float c0, s0, c1, s1;
-          fast_sincospi(d[2 * j] + h[2 * j], &s0, &c0);
-          fast_sincospi(d[2 * j + 1] + h[2 * j + 1], &s1, &c1);
-          if (!((mask >> (2 * j)) & 1u)) { c0 = 0.f; s0 = 0.f; }
-          if (!((mask >> (2 * j + 1)) & 1u)) { c1 = 0.f; s1 = 0.f; }
-          split_pack2(c0, c1, rh[j], rl[j]);
-          split_pack2(s0, s1, ih[j], il[j]);
-#pragma unroll
-          for (int v = 0; v < NOBS; ++v) {
-            const float2 m0 = m1o_s[v * Np + y0 + 2 * j], m1 = m1o_s[v * Np + y0 + 2 * j + 1];
-            obs_re[v] = fmaf(m0.x, c0, fmaf(-m0.y, s0, obs_re[v]));
-            obs_im[v] = fmaf(m0.x, s0, fmaf(m0.y, c0, obs_im[v]));
-            obs_re[v] = fmaf(m1.x, c1, fmaf(-m1.y, s1, obs_re[v]));
-            obs_im[v] = fmaf(m1.x, s1, fmaf(m1.y, c1, obs_im[v]));
-          }
+        for (int j = 0; j < 16; ++j) {
+          t[j] += __float2int_rn(d[j] * PHI_ONE);                         // atmosphere + DM, fixed point, unreduced
+          ph[j] = (float)((t[j] << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
         }
         if (!(p.dbg & 1)) {
-          // Full-sector stores: a lane's 16 pixels of one operand row are 32 contiguous bytes, but a thread
-          // stores at most 16.  Lane pairs swap halves so that each store instruction writes whole 32-byte
-          // sectors (lanes 2i, 2i+1 -> the two halves of env 2i's sector, then of env 2i+1's).
+          // Full-sector stores: a lane's 16 pixels are 64 contiguous bytes, but a thread stores at most 16 per
+          // instruction.  Lane pairs swap halves so that each store instruction writes whole 32-byte sectors
+          // (lanes 2i, 2i+1 -> the two halves of a sector of env 2i, then of env 2i+1).
           const bool odd = lane & 1;
           const bool valid_even = (env & ~1) < p.num_envs, valid_odd = (env | 1) < p.num_envs;
-          const size_t erow_even = ((size_t)(env & ~1) * Np + x) * TC_K + y0 + (odd ? 8 : 0);
-          const size_t erow_odd = erow_even + (size_t)Np * TC_K;
-          auto store_pair = [&](__half* dst, const uint32_t* a) {
-            uint32_t r[4];
+          float* row_even = p.phi + (((size_t)(env & ~1) * (Np / 16) + ci) * Np + x) * 16 + (odd ? 4 : 0);
+          float* row_odd = row_even + (size_t)Np * Np;
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {              // pixels [8 h8, 8 h8 + 8) = one sector per env
+            const float* a = ph + 8 * h8;
+            float r[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) r[k] = __shfl_xor_sync(0xffffffffu, odd ? a[k] : a[4 + k], 1);
             // even lane: own[0..3] -> env 2i first half;  received = env 2i+1's first half
             // odd lane : received = env 2i's second half;  own[4..7] -> env 2i+1 second half
             if (valid_even)
-              *reinterpret_cast<uint4*>(dst + erow_even) = odd ? make_uint4(r[0], r[1], r[2], r[3]) : make_uint4(a[0], a[1], a[2], a[3]);
+              *reinterpret_cast<float4*>(row_even + 8 * h8) = odd ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(a[0], a[1], a[2], a[3]);
             if (valid_odd)
-              *reinterpret_cast<uint4*>(dst + erow_odd) = odd ? make_uint4(a[4], a[5], a[6], a[7]) : make_uint4(r[0], r[1], r[2], r[3]);
-          };
-          store_pair(p.E_hi, rh);
-          store_pair(p.E_lo, rl);
-          store_pair(p.E_hi + Np, ih);
-          store_pair(p.E_lo + Np, il);
-        }
-        if (STREHL) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t = *reinterpret_cast<const float4*>(tile + FK_PF_TILE + ((j ^ sw) << 4));
-            h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w;
+              *reinterpret_cast<float4*>(row_odd + 8 * h8) = odd ? make_float4(a[4], a[5], a[6], a[7]) : make_float4(r[0], r[1], r[2], r[3]);
           }
+        }
+        {
+          // obs arm: 16-pixel partial sums in FP32, folded into FP64 per chunk
+          float ore[NOBS], oim[NOBS];
+#pragma unroll
+          for (int v = 0; v < NOBS; ++v) ore[v] = oim[v] = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float c0, s0;
-            fast_sincospi(fmaf(d[j], p.sci_ratio, h[j]), &s0, &c0);
+            asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(ph[j]));
+            asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(ph[j]));
+            if (!((mask >> j) & 1u)) { c0 = 0.f; s0 = 0.f; }
+#pragma unroll
+            for (int v = 0; v < NOBS; ++v) {
+              const float2 m = m1o_s[v * Np + y0 + j];
+              ore[v] = fmaf(m.x, c0, fmaf(-m.y, s0, ore[v]));
+              oim[v] = fmaf(m.x, s0, fmaf(m.y, c0, oim[v]));
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < NOBS; ++v) { obs_re[v] += (double)ore[v]; obs_im[v] += (double)oim[v]; }
+        }
+        if (STREHL) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // phase at lambda_sci = phase at lambda_wfs x (lambda_wfs / lambda_sci), exact to one fixed-point unit
+            const int32_t ts = (int32_t)(((long long)t[j] * (long long)p.sci_ratio_q32) >> 32);
+            float c0, s0;
+            sincos_fixed(ts, &s0, &c0);
             if ((mask >> j) & 1u) { sre += c0; sim += s0; }
           }
         }
@@ -1121,7 +891,7 @@ k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       if (valid) {
         float2* r = p.R4 + (((size_t)env * Np + x) * FK_PARTS + q) * NOBS;
 #pragma unroll
-        for (int v = 0; v < NOBS; ++v) r[v] = make_float2(obs_re[v], obs_im[v]);
+        for (int v = 0; v < NOBS; ++v) r[v] = make_float2((float)obs_re[v], (float)obs_im[v]);
       }
       if (STREHL) { st_re += (double)sre; st_im += (double)sim; }
     }
@@ -1131,6 +901,321 @@ k_dm_field_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- field + MFT stage 1
+// k_field_mft1: the pupil field is formed ON CHIP and fed straight into the stage-1 pair MMA
+// (reference AO_env.py:132-135 field, :138 first MFT product):
+//
+//   [Tr ; Ti] (256 x 240) = [[M1r, -M1i], [M1i, M1r]] (256 x 480) . [Er ; Ei] (480 x 240)      per env
+//
+// cta_group::2, M = 256 over the CTA pair (CTA 0: Tr rows, CTA 1: Ti rows), N = 240 pupil columns x, CTA r
+// stages x in [120 r, 120 r + 120).  The K order is 15 blocks of [16 y real | 16 y imaginary].  16 warps:
+//   warp 0      TMA producer of the twiddle tiles (A): a deep ring (8 x 16 KB) because every tile is an
+//               L2 round trip; completion on the leader's `a_full` barrier
+//   warp 1      MMA issuer (leader CTA only)
+//   warps 4-11  epilogue: TMEM -> registers -> accumulators released -> split fp16 -> smem ring -> TMA store
+//   warp 2      TMA producer of the phase tiles (120 columns x 16 y, FP32 radians, SWIZZLE_64B ring of 6): the
+//               field warps must not have global loads of their own in flight, because the release fence of
+//               their barrier arrival waits for them
+//   warps 12-15 field warps, one pupil column x per thread: phase -> sincos (SFU) -> aperture -> fp16 hi/lo
+//               split -> the B operand rows of a short ring (3 x 16 KB), written in the UMMA SWIZZLE_64B
+//               image; `b_full` collects one arrival per field warp of BOTH CTAs
+// Registers are re-partitioned with setmaxnreg: the epilogue warps hold 128 accumulator columns each.
+constexpr int F1_A_SLOTS = 5;
+constexpr int F1_B_SLOTS = 3;
+constexpr int F1_SLOT_BYTES = 2 * A_TILE;             // 16 KB: [hi 8 KB][lo 8 KB]
+constexpr int F1_PHI_SLOTS = 6;
+constexpr int F1_PHI_TILE = 8192;                     // 120 rows x 64 B in an 8 KB slot
+constexpr int F1_THREADS = 512;
+constexpr int F1_SMEM_BYTES = (F1_A_SLOTS + F1_B_SLOTS) * F1_SLOT_BYTES + F1_PHI_SLOTS * F1_PHI_TILE + M2_EPI_BYTES +
+                              1024 /*align*/ + 1024 /*barriers*/;
+
+struct F1Params {
+  int num_items;            // envs in this chunk
+  const uint16_t* apmask;   // [Np x][Np / 16] aperture bits
+  int dbg;                  // AOG_TC_DEBUG bits: 1 no MMA, 4 no epilogue work, 32 no field arithmetic, 64 no phase tiles, 128 no twiddle tiles
+  int* err_flag;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F1_THREADS, 1)
+k_field_mft1(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+             const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ CUtensorMap tmO_hi,
+             const __grid_constant__ CUtensorMap tmO_lo, const F1Params p) {
+  constexpr int B_ROWS = TC_NP / 2;                                    // 120 rows of B per CTA
+  constexpr uint32_t TX_BYTES = 2 * 2 * A_TILE;                        // A tiles of both CTAs
+  constexpr uint32_t IDESC = umma_idesc_f16(256, TC_NP);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_ring = base;
+  uint8_t* b_ring = base + F1_A_SLOTS * F1_SLOT_BYTES;
+  uint8_t* phis = b_ring + F1_B_SLOTS * F1_SLOT_BYTES;                 // phase tile ring
+  uint8_t* epi = phis + F1_PHI_SLOTS * F1_PHI_TILE;                    // output tile ring
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(epi + M2_EPI_BYTES);
+  uint64_t* a_empty = a_full + F1_A_SLOTS;
+  uint64_t* b_full = a_empty + F1_A_SLOTS;
+  uint64_t* b_empty = b_full + F1_B_SLOTS;
+  uint64_t* phi_full = b_empty + F1_B_SLOTS;
+  uint64_t* phi_empty = phi_full + F1_PHI_SLOTS;
+  uint64_t* tmem_full = phi_empty + F1_PHI_SLOTS;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmPhi)) : "memory");
+    for (int s = 0; s < F1_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < F1_B_SLOTS; ++s) { mbar_init(&b_full[s], 8); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < F1_PHI_SLOTS; ++s) { mbar_init(&phi_full[s], 1); mbar_init(&phi_empty[s], 4); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 2 * M2_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer: twiddle tiles =====================
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          mbar_wait<32>(&a_empty[slot], phase ^ 1, p.err_flag, 1);
+          if (p.dbg & 128) {
+            if (rank == 0) mbar_arrive(&a_full[slot]);
+          } else {
+            if (rank == 0) mbar_expect_tx(&a_full[slot], TX_BYTES);
+            const uint32_t s0 = smem_u32(a_ring + slot * F1_SLOT_BYTES);
+            const uint32_t fb = mapa_rank(smem_u32(&a_full[slot]), 0);
+            tma_load_2d_pair(s0, &tmA_hi, fb, kb * KB, (int)rank * 128);
+            tma_load_2d_pair(s0 + A_TILE, &tmA_lo, fb, kb * KB, (int)rank * 128);
+          }
+          if (++slot == F1_A_SLOTS) { slot = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && rank == 0 && lane == 0) {
+      // ===================== MMA issuer (one thread of the leader CTA) =====================
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0, tphase = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        mbar_wait<32>(tmem_empty, tphase ^ 1, p.err_flag, 2);
+        tc_fence_after();
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          mbar_wait(&a_full[sa], pa, p.err_flag, 3);
+          mbar_wait(&b_full[sb], pb, p.err_flag, 8);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(a_ring + sa * F1_SLOT_BYTES);
+          const uint32_t b0 = smem_u32(b_ring + sb * F1_SLOT_BYTES);
+          if (!(p.dbg & 1))
+#pragma unroll
+          for (int ks = 0; ks < KB / 16; ++ks) {
+            const uint32_t acc = (kb | ks) != 0;
+            const uint64_t a_hi = umma_desc_sw64(a0 + ks * 32), a_lo = umma_desc_sw64(a0 + A_TILE + ks * 32);
+            const uint64_t b_hi = umma_desc_sw64(b0 + ks * 32), b_lo = umma_desc_sw64(b0 + A_TILE + ks * 32);
+            tc_mma_f16_pair(tmem_base, a_hi, b_hi, IDESC, acc);              // main
+            tc_mma_f16_pair(tmem_base + 256, a_hi, b_lo, IDESC, acc);        // corrections
+            tc_mma_f16_pair(tmem_base + 256, a_lo, b_hi, IDESC, 1);
+          }
+          tc_commit_pair(&a_empty[sa]);             // both slots are free in both CTAs when these MMAs retire
+          tc_commit_pair(&b_empty[sb]);
+          if (++sa == F1_A_SLOTS) { sa = 0; pa ^= 1; }
+          if (++sb == F1_B_SLOTS) { sb = 0; pb ^= 1; }
+        }
+        tc_commit_pair(tmem_full);
+        tphase ^= 1;
+      }
+    } else if (warp == 2 && lane == 0 && !(p.dbg & 64)) {
+      // ===================== TMA producer: phase tiles of my 120 pupil columns =====================
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          mbar_wait<32>(&phi_empty[slot], phase ^ 1, p.err_flag, 5);
+          mbar_expect_tx(&phi_full[slot], B_ROWS * 64);
+          tma_load_2d(smem_u32(phis + slot * F1_PHI_TILE), &tmPhi, &phi_full[slot], 0,
+                      (item * NUM_KB + kb) * TC_NP + (int)rank * B_ROWS);
+          if (++slot == F1_PHI_SLOTS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // ===================== epilogue: 8 warps, TMEM lane group = warp % 4, column half = (warp - 4) / 4 =========
+    const int lg = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = lg * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    const uint32_t tmem_empty_leader = mapa_rank(smem_u32(tmem_empty), 0);
+    uint32_t tphase = 0;
+    uint32_t out_seq = 0;
+    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+      mbar_wait(tmem_full, tphase, p.err_flag, 4);
+      tc_fence_after();
+      tphase ^= 1;
+      if (p.dbg & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+        continue;
+      }
+      // Phase 1: drain this warp's accumulator columns (main + corrections) into registers and hand the
+      // TMEM back, so the next env's MMAs run under phase 2.  The 4 warps of a column half own the
+      // 16-column chunks c = 8 half ... (8 | 7 of the 15).
+      const int c0 = half * 8, c_end = half ? TC_NP / 16 : 8;
+      float acc[128];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        float v[32], w[32];
+        if (c0 + i + 1 < c_end) {
+          tc_ld32(lane_addr + (c0 + i) * 16, v);
+          tc_ld32(lane_addr + 256 + (c0 + i) * 16, w);
+        } else {
+          tc_ld16(lane_addr + (c0 + i) * 16, v);
+          tc_ld16(lane_addr + 256 + (c0 + i) * 16, w);
+#pragma unroll
+          for (int q = 16; q < 32; ++q) v[q] = w[q] = 0.f;
+        }
+        tc_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc[i * 16 + q] = v[q] + w[q];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+      // Phase 2: split fp16 -> swizzled 128 x 16 tiles in shared memory -> TMA stores into
+      // T[env][v][k = rank * 240 + x].
+      uint8_t* ring = epi + half * (M2_OUT_BUFS * 2 * M2_OUT_TILE);
+      const uint32_t sw = (uint32_t)((row >> 2) & 1);                 // SWIZZLE_32B: 16-byte piece ^= address bit 7
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        if (c < c_end) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) split_pack2(acc[i * 16 + 2 * q], acc[i * 16 + 2 * q + 1], hi[q], lo[q]);
+          uint8_t* t_hi = ring + (out_seq % M2_OUT_BUFS) * (2 * M2_OUT_TILE);
+          uint8_t* t_lo = t_hi + M2_OUT_TILE;
+          *reinterpret_cast<uint4*>(t_hi + row * 32 + ((0u ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(t_hi + row * 32 + ((1u ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(t_lo + row * 32 + ((0u ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(t_lo + row * 32 + ((1u ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else           asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (lg == 0 && lane == 0) {
+            tma_store_2d(&tmO_hi, smem_u32(t_hi), (int)rank * TC_NP + c * 16, item * 128);
+            tma_store_2d(&tmO_lo, smem_u32(t_lo), (int)rank * TC_NP + c * 16, item * 128);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the store issued one chunk ago has left shared memory: with 3 buffers the slot written two
+            // chunks from now is free by the time its writers pass the next barrier
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
+          ++out_seq;
+        }
+      }
+    }
+    if (lg == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    // ===================== field warps: one pupil column x per thread =====================
+    const int t = (warp - 12) * 32 + lane;                 // B row within this CTA's half
+    const bool active = t < B_ROWS;
+    const int x = active ? (int)rank * B_ROWS + t : (int)rank * B_ROWS;
+    const uint32_t sw = (uint32_t)((t >> 1) & 3);          // SWIZZLE_64B: 16-byte piece ^= (row >> 1) & 3
+    const uint32_t b_full_leader0 = mapa_rank(smem_u32(&b_full[0]), 0);
+    uint32_t maskw[8];                                     // aperture bits of my column, two 16-pixel chunks per word
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t lo16 = __ldg(p.apmask + x * (TC_NP / 16) + 2 * j);
+      const uint32_t hi16 = (2 * j + 1 < TC_NP / 16) ? __ldg(p.apmask + x * (TC_NP / 16) + 2 * j + 1) : 0u;
+      maskw[j] = lo16 | (hi16 << 16);
+    }
+    int sb = 0, slot = 0;
+    uint32_t pb = 0, pphase = 0;
+    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+#pragma unroll
+      for (int kb = 0; kb < NUM_KB; ++kb) {                  // fully unrolled: kb indexes the mask registers
+        if (!(p.dbg & 64)) mbar_wait(&phi_full[slot], pphase, p.err_flag, 6);
+        mbar_wait(&b_empty[sb], pb ^ 1, p.err_flag, 7);
+        if (active && !(p.dbg & 32)) {
+          const uint32_t mask = (kb & 1) ? (maskw[kb >> 1] >> 16) : (maskw[kb >> 1] & 0xFFFFu);
+          uint8_t* b_hi = b_ring + sb * F1_SLOT_BYTES + t * 64;
+          uint8_t* b_lo = b_hi + A_TILE;
+          if (mask == 0) {                                  // outside the aperture: the field is zero
+            const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(b_hi + (j << 4)) = z;
+              *reinterpret_cast<uint4*>(b_lo + (j << 4)) = z;
+            }
+          } else {
+            const uint8_t* tile = phis + slot * F1_PHI_TILE + t * 64;
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {                // pixels [8 h8, 8 h8 + 8) of the chunk
+              const float4 q0 = *reinterpret_cast<const float4*>(tile + (((uint32_t)(2 * h8) ^ sw) << 4));
+              const float4 q1 = *reinterpret_cast<const float4*>(tile + (((uint32_t)(2 * h8 + 1) ^ sw) << 4));
+              const float ph[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+              float c[8], s[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s[j]) : "f"(ph[j]));
+                asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c[j]) : "f"(ph[j]));
+              }
+              if (mask != 0xFFFFu) {                        // aperture edge: clear the dark pixels
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (!((mask >> (8 * h8 + j)) & 1u)) { c[j] = 0.f; s[j] = 0.f; }
+              }
+              uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                split_pack2(c[2 * j], c[2 * j + 1], rh[j], rl[j]);
+                split_pack2(s[2 * j], s[2 * j + 1], ih[j], il[j]);
+              }
+              // row image: [16 y real | 16 y imaginary] = pieces {0, 1 | 2, 3}; this half fills piece h8 of each
+              *reinterpret_cast<uint4*>(b_hi + (((uint32_t)h8 ^ sw) << 4)) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+              *reinterpret_cast<uint4*>(b_hi + (((uint32_t)(2 + h8) ^ sw) << 4)) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
+              *reinterpret_cast<uint4*>(b_lo + (((uint32_t)h8 ^ sw) << 4)) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+              *reinterpret_cast<uint4*>(b_lo + (((uint32_t)(2 + h8) ^ sw) << 4)) = make_uint4(il[0], il[1], il[2], il[3]);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(b_full_leader0 + sb * 8);       // my rows of the B tile are in place
+          if (!(p.dbg & 64)) mbar_arrive(&phi_empty[slot]);   // the phase tile may be overwritten
+        }
+        if (++sb == F1_B_SLOTS) { sb = 0; pb ^= 1; }
+        if (++slot == F1_PHI_SLOTS) { slot = 0; pphase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  // neither CTA may exit (or free its TMEM) while the pair's MMAs, loads or barrier signals can still touch it
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -1146,39 +1231,38 @@ __global__ void k_act_pack(const double* __restrict__ act, __half* __restrict__ 
   a_lo[i] = __float2half_rn((float)(v - (double)__half2float(h)));
 }
 
-// screens FP64 [B][y][xp] -> tiled phase / pi at both wavelengths (layout: TensorState::hwt).
-// One thread per output float, output-ordered (coalesced writes, strided reads).
-__device__ __forceinline__ float reduce_halfturns(double S, double inv) {
-  double a = S * inv;
-  a -= 2.0 * rint(0.5 * a);
-  return (float)a;
+// screens FP64 [B][y][xp] -> tiled fixed-point phase at lambda_wfs (layout: TensorState::hwt).
+// One thread per output int, output-ordered (coalesced writes, strided reads).
+__device__ __forceinline__ int32_t phase_fixed(double S, double inv) {
+  double a = S * inv * (double)PHI_ONE;                  // half-turns x 2^22
+  a = fmin(fmax(a, -2147483000.0), 2147483000.0);        // +-512 half-turns (1600 rad) of range
+  return (int32_t)__double2ll_rn(a);
 }
-__global__ void k_screens_to_tiles(const double* __restrict__ src, float* __restrict__ hwt, int Np, int B,
-                                   size_t total, double inv_w, double inv_s) {
+__global__ void k_screens_to_tiles(const double* __restrict__ src, int32_t* __restrict__ hwt, int Np, int B,
+                                   size_t total, double inv_w) {
   const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= total) return;
-  const int e = o & 3, piece = (o >> 2) & 3, l = (o >> 4) & 31, arr = (o >> 9) & 1;
-  const size_t t = o >> 10;                       // ((eb32 * Np) + xp) * (Np / 16) + ci
+  const int e = o & 3, piece = (o >> 2) & 3, l = (o >> 4) & 31;
+  const size_t t = o >> 9;                        // ((eb32 * Np) + xp) * (Np / 16) + ci
   const int ci = (int)(t % (Np / 16));
   const size_t t2 = t / (Np / 16);
   const int xp = (int)(t2 % Np);
   const size_t env = (t2 / Np) * 32 + l;
   const int y = ci * 16 + ((piece ^ ((l >> 1) & 3)) << 2) + e;
-  float v = 0.f;
-  if (env < (size_t)B) v = reduce_halfturns(src[(env * Np + y) * Np + xp], arr ? inv_s : inv_w);
+  int32_t v = 0;
+  if (env < (size_t)B) v = phase_fixed(src[(env * Np + y) * Np + xp], inv_w);
   hwt[o] = v;
 }
 // one physical column refresh after an extrusion
-__global__ void k_column_to_tiles(const double* __restrict__ src, float* __restrict__ hwt, int Np, int B, int phys_col,
-                                  double inv_w, double inv_s) {
+__global__ void k_column_to_tiles(const double* __restrict__ src, int32_t* __restrict__ hwt, int Np, int B, int phys_col,
+                                  double inv_w) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over B * Np
   if (i >= B * Np) return;
   const int env = i / Np, y = i - env * Np;
   const double S = src[((size_t)env * Np + y) * Np + phys_col];
   const int l = env & 31, ci = y >> 4, piece = ((y >> 2) & 3) ^ ((l >> 1) & 3), e = y & 3;
-  const size_t tile = (((size_t)(env >> 5) * Np + phys_col) * (Np / 16) + ci) * (2 * 32 * 16);
-  hwt[tile + (size_t)l * 16 + piece * 4 + e] = reduce_halfturns(S, inv_w);
-  hwt[tile + 512 + (size_t)l * 16 + piece * 4 + e] = reduce_halfturns(S, inv_s);
+  const size_t tile = (((size_t)(env >> 5) * Np + phys_col) * (Np / 16) + ci) * (32 * 16);
+  hwt[tile + (size_t)l * 16 + piece * 4 + e] = phase_fixed(S, inv_w);
 }
 
 // ----------------------------------------------------------------------------- host helpers
@@ -1214,6 +1298,21 @@ int make_map(aog_env* env, CUtensorMap* map, const __half* ptr, uint64_t rows, u
                                    : (box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) AOG_FAIL(AOG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return AOG_OK;
+}
+
+// 2-D row-major [rows][inner] tensor of 32-bit words, box = 16 x box_rows (64-byte rows, SWIZZLE_64B)
+int make_map_32(aog_env* env, CUtensorMap* map, const void* ptr, uint64_t rows, uint32_t box_rows, uint64_t inner) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) AOG_FAIL(AOG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * sizeof(int32_t)};
+  cuuint32_t box[2] = {16, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) AOG_FAIL(AOG_ERR_CUDA, "cuTensorMapEncodeTiled (int32) failed: " + std::to_string((int)r));
   return AOG_OK;
 }
 
@@ -1258,8 +1357,8 @@ int aog_tensor_create(aog_env* env) {
   A(talloc(env, &ts->A1_lo, (size_t)256 * TC_K));
   A(talloc(env, &ts->B2_hi, (size_t)256 * TC_K));
   A(talloc(env, &ts->B2_lo, (size_t)256 * TC_K));
-  A(talloc(env, &ts->E_hi, ch * TC_NP * TC_K));
-  A(talloc(env, &ts->E_lo, ch * TC_NP * TC_K));
+  A(talloc(env, &ts->phi, ch * P));
+  AOG_CUDA(cudaMemset(ts->phi, 0, ch * P * sizeof(float)));   // out-of-aperture chunks are never written (nor used)
   // stage-2 reads env pairs: keep one spare env of rows so the last odd pair stays in bounds
   A(talloc(env, &ts->T_hi, (ch + 1) * 128 * TC_K));
   A(talloc(env, &ts->T_lo, (ch + 1) * 128 * TC_K));
@@ -1272,8 +1371,8 @@ int aog_tensor_create(aog_env* env) {
   ts->act_rows = (int)((ch + 127) / 128) * 128;
   {
     const size_t tiles = ((B + 127) / 128) * 4 * TC_NP * (TC_NP / 16);   // whole 128-env blocks: the prefetch reads them all
-    A(talloc(env, &ts->hwt, tiles * 1024));
-    AOG_CUDA(cudaMemset(ts->hwt, 0, tiles * 1024 * sizeof(float)));
+    A(talloc(env, &ts->hwt, tiles * 512));
+    AOG_CUDA(cudaMemset(ts->hwt, 0, tiles * 512 * sizeof(int32_t)));
   }
   A(talloc(env, &ts->modesK_hi, P * ts->kpad));
   A(talloc(env, &ts->modesK_lo, P * ts->kpad));
@@ -1282,18 +1381,12 @@ int aog_tensor_create(aog_env* env) {
   A(talloc(env, &ts->apmask, (size_t)TC_NP * (TC_NP / 16)));
   A(talloc(env, &ts->m1o32, (size_t)c.obs_dim * TC_NP));
   A(talloc(env, &ts->R4, ch * TC_NP * FK_PARTS * c.obs_dim));
-  // the field kernel only writes in-aperture chunks: everything else of E stays zero forever
-  AOG_CUDA(cudaMemset(ts->E_hi, 0, ch * TC_NP * TC_K * sizeof(__half)));
-  AOG_CUDA(cudaMemset(ts->E_lo, 0, ch * TC_NP * TC_K * sizeof(__half)));
   A(talloc(env, &ts->m2oT, (size_t)c.obs_dim * TC_NP));
   A(talloc(env, &ts->err_flag, 1));
   AOG_CUDA(cudaMemset(ts->err_flag, 0, sizeof(int)));
   A(make_map(env, &ts->tmA1_hi, ts->A1_hi, 256, 128));
   A(make_map(env, &ts->tmA1_lo, ts->A1_lo, 256, 128));
-  A(make_map(env, &ts->tmE_hi, ts->E_hi, ch * TC_NP, TC_NP / 2));   // each CTA of the cluster fetches half
-  A(make_map(env, &ts->tmE_lo, ts->E_lo, ch * TC_NP, TC_NP / 2));
-  A(make_map(env, &ts->tmT_hi, ts->T_hi, (ch + 1) * 128, 64));
-  A(make_map(env, &ts->tmT_lo, ts->T_lo, (ch + 1) * 128, 64));
+  A(make_map_32(env, &ts->tmPhi, ts->phi, ch * (TC_NP / 16) * TC_NP, TC_NP / 2, 16));   // box = 120 columns x 16 y, contiguous
   A(make_map(env, &ts->tmT128_hi, ts->T_hi, (ch + 1) * 128, 128));
   A(make_map(env, &ts->tmT128_lo, ts->T_lo, (ch + 1) * 128, 128));
   A(make_map(env, &ts->tmTout_hi, ts->T_hi, (ch + 1) * 128, 128, TC_K, 16));
@@ -1305,9 +1398,6 @@ int aog_tensor_create(aog_env* env) {
   A(make_map(env, &ts->tmModes_hi, ts->modesK_hi, P, TC_NP, ts->kpad, 64));
   A(make_map(env, &ts->tmModes_lo, ts->modesK_lo, P, TC_NP, ts->kpad, 64));
 #undef A
-  AOG_CUDA(cudaFuncSetAttribute(k_mft_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  AOG_CUDA(cudaFuncSetAttribute(k_mft_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  AOG_CUDA(cudaFuncSetAttribute(k_mft2<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
   AOG_CUDA(cudaFuncSetAttribute(k_mft2<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
   AOG_CUDA(cudaFuncSetAttribute(k_mft2<1, AOG_MAX_LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
   return AOG_OK;
@@ -1316,7 +1406,7 @@ int aog_tensor_create(aog_env* env) {
 void aog_tensor_destroy(aog_env* env) {
   TensorState* ts = TS(env);
   if (!ts) return;
-  void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->E_hi, ts->E_lo, ts->T_hi, ts->T_lo, ts->lpw, ts->lpwq,
+  void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->phi, ts->T_hi, ts->T_lo, ts->lpw, ts->lpwq,
                   ts->hwt, ts->modesK_hi, ts->modesK_lo, ts->act_hi, ts->act_lo, ts->apmask, ts->m1o32, ts->R4,
                   ts->m2oT, ts->err_flag};
   for (void* p : ptrs)
@@ -1338,10 +1428,12 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
     for (int v = 0; v < Nf; ++v)
       for (int y = 0; y < Np; ++y) {
         const double re = m[2 * ((size_t)v * Np + y)] / w, im = m[2 * ((size_t)v * Np + y) + 1] / w;
-        a[(size_t)v * TC_K + y] = re;               // Tr rows:  [M1r | -M1i]
-        a[(size_t)v * TC_K + Np + y] = -im;
-        a[(size_t)(128 + v) * TC_K + y] = im;       // Ti rows:  [M1i |  M1r]
-        a[(size_t)(128 + v) * TC_K + Np + y] = re;
+        // contraction order of stage 1: block y / 16 = [16 y against Er | the same 16 y against Ei]
+        const int kr = (y >> 4) * 32 + (y & 15), ki = kr + 16;
+        a[(size_t)v * TC_K + kr] = re;              // Tr rows:  M1r . Er - M1i . Ei
+        a[(size_t)v * TC_K + ki] = -im;
+        a[(size_t)(128 + v) * TC_K + kr] = im;      // Ti rows:  M1i . Er + M1r . Ei
+        a[(size_t)(128 + v) * TC_K + ki] = re;
       }
     int rc = upload_split(env, a, ts->A1_hi, ts->A1_lo);
     if (rc) return rc;
@@ -1427,10 +1519,9 @@ int aog_tensor_screens_updated(aog_env* env) {
   TensorState* ts = TS(env);
   const int Np = TC_NP, B = env->cfg.num_envs;
   const double pi = 3.14159265358979323846;
-  const size_t total = (size_t)((B + 127) / 128) * 4 * Np * (Np / 16) * 1024;
+  const size_t total = (size_t)((B + 127) / 128) * 4 * Np * (Np / 16) * 512;
   k_screens_to_tiles<<<(unsigned)((total + 255) / 256), 256>>>(env->screens, ts->hwt, Np, B, total,
-                                                              1.0 / (env->cfg.wavelength_wfs * pi),
-                                                              1.0 / (env->cfg.wavelength_sci * pi));
+                                                              1.0 / (env->cfg.wavelength_wfs * pi));
   AOG_LAUNCH_CHECK();
   AOG_CUDA(cudaDeviceSynchronize());
   return AOG_OK;
@@ -1441,8 +1532,7 @@ int aog_tensor_column_updated(aog_env* env, int phys_col, cudaStream_t st) {
   const int B = env->cfg.num_envs;
   const double pi = 3.14159265358979323846;
   k_column_to_tiles<<<cdiv(B * TC_NP, 256), 256, 0, st>>>(env->screens, ts->hwt, TC_NP, B, phys_col,
-                                                          1.0 / (env->cfg.wavelength_wfs * pi),
-                                                          1.0 / (env->cfg.wavelength_sci * pi));
+                                                          1.0 / (env->cfg.wavelength_wfs * pi));
   AOG_LAUNCH_CHECK();
   return AOG_OK;
 }
@@ -1455,28 +1545,32 @@ int aog_tensor_get_field(aog_env* env, int which, int env_in_chunk, double* host
   TensorState* ts = TS(env);
   if (!ts) AOG_FAIL(AOG_ERR_STATE, "handle has no tensor path");
   if (env_in_chunk < 0 || env_in_chunk >= env->chunk) AOG_FAIL(AOG_ERR_INVALID, "env index outside the chunk");
-  const int rows = (which == AOG_FIELD_TC_PUPIL) ? TC_NP : 128;
-  if (count != (size_t)2 * rows * TC_NP) AOG_FAIL(AOG_ERR_INVALID, "count");
-  const __half* dh = (which == AOG_FIELD_TC_PUPIL) ? ts->E_hi : ts->T_hi;
-  const __half* dl = (which == AOG_FIELD_TC_PUPIL) ? ts->E_lo : ts->T_lo;
-  const size_t nel = (size_t)rows * TC_K;
-  std::vector<__half> hi(nel), lo(nel);
-  AOG_CUDA(cudaMemcpy(hi.data(), dh + (size_t)env_in_chunk * nel, nel * sizeof(__half), cudaMemcpyDeviceToHost));
-  AOG_CUDA(cudaMemcpy(lo.data(), dl + (size_t)env_in_chunk * nel, nel * sizeof(__half), cudaMemcpyDeviceToHost));
-  auto val = [&](size_t i) { return (double)__half2float(hi[i]) + (double)__half2float(lo[i]); };
-  if (which == AOG_FIELD_TC_PUPIL) {          // stored [x][k = y | 240 + y]  ->  out [y][x]
+  if (which == AOG_FIELD_TC_PUPIL) {          // phi [y / 16][x][16] radians -> out [y][x] = aperture exp(i phi)
+    if (count != (size_t)2 * TC_NP * TC_NP) AOG_FAIL(AOG_ERR_INVALID, "count");
+    std::vector<float> ph((size_t)TC_NP * TC_NP);
+    std::vector<uint16_t> ap((size_t)TC_NP * (TC_NP / 16));
+    AOG_CUDA(cudaMemcpy(ph.data(), ts->phi + (size_t)env_in_chunk * ph.size(), ph.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    AOG_CUDA(cudaMemcpy(ap.data(), ts->apmask, ap.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     for (int x = 0; x < TC_NP; ++x)
       for (int y = 0; y < TC_NP; ++y) {
-        host_out[2 * ((size_t)y * TC_NP + x)] = val((size_t)x * TC_K + y);
-        host_out[2 * ((size_t)y * TC_NP + x) + 1] = val((size_t)x * TC_K + TC_NP + y);
+        const bool lit = (ap[(size_t)x * (TC_NP / 16) + y / 16] >> (y % 16)) & 1;
+        const double a = (double)ph[((size_t)(y / 16) * TC_NP + x) * 16 + y % 16];
+        host_out[2 * ((size_t)y * TC_NP + x)] = lit ? std::cos(a) : 0.0;
+        host_out[2 * ((size_t)y * TC_NP + x) + 1] = lit ? std::sin(a) : 0.0;
       }
-  } else {                                    // stored [v][k = x | 240 + x]  ->  out [v][x]
-    for (int v = 0; v < 128; ++v)
-      for (int x = 0; x < TC_NP; ++x) {
-        host_out[2 * ((size_t)v * TC_NP + x)] = val((size_t)v * TC_K + x);
-        host_out[2 * ((size_t)v * TC_NP + x) + 1] = val((size_t)v * TC_K + TC_NP + x);
-      }
+    return AOG_OK;
   }
+  if (count != (size_t)2 * 128 * TC_NP) AOG_FAIL(AOG_ERR_INVALID, "count");
+  const size_t nel = (size_t)128 * TC_K;
+  std::vector<__half> hi(nel), lo(nel);
+  AOG_CUDA(cudaMemcpy(hi.data(), ts->T_hi + (size_t)env_in_chunk * nel, nel * sizeof(__half), cudaMemcpyDeviceToHost));
+  AOG_CUDA(cudaMemcpy(lo.data(), ts->T_lo + (size_t)env_in_chunk * nel, nel * sizeof(__half), cudaMemcpyDeviceToHost));
+  auto val = [&](size_t i) { return (double)__half2float(hi[i]) + (double)__half2float(lo[i]); };
+  for (int v = 0; v < 128; ++v)                 // stored [v][k = x | 240 + x]  ->  out [v][x]
+    for (int x = 0; x < TC_NP; ++x) {
+      host_out[2 * ((size_t)v * TC_NP + x)] = val((size_t)v * TC_K + x);
+      host_out[2 * ((size_t)v * TC_NP + x) + 1] = val((size_t)v * TC_K + TC_NP + x);
+    }
   return AOG_OK;
 }
 
@@ -1491,29 +1585,29 @@ int aog_tensor_check(aog_env* env) {
 
 namespace {
 template <bool STREHL, int NOBS>
-int launch_field(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
+int launch_phase(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
   const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES + 1024 + FK_AUX_BAR + FK_PARTS * 128 * (int)sizeof(double2) +
                    NOBS * TC_NP * (int)sizeof(float2) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
   static bool configured = false;
   if (!configured) {
-    AOG_CUDA(cudaFuncSetAttribute(k_dm_field_tc<STREHL, NOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_dm_field_tc<STREHL, NOBS><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
+  k_dm_phase_tc<STREHL, NOBS><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
   AOG_LAUNCH_CHECK();
   return AOG_OK;
 }
 template <bool STREHL>
-int launch_field_n(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
-  switch (p.n) {
-    case 1: return launch_field<STREHL, 1>(env, ts, p, grid, st);
-    case 2: return launch_field<STREHL, 2>(env, ts, p, grid, st);
-    case 3: return launch_field<STREHL, 3>(env, ts, p, grid, st);
-    case 4: return launch_field<STREHL, 4>(env, ts, p, grid, st);
-    case 5: return launch_field<STREHL, 5>(env, ts, p, grid, st);
-    case 6: return launch_field<STREHL, 6>(env, ts, p, grid, st);
-    case 7: return launch_field<STREHL, 7>(env, ts, p, grid, st);
-    case 8: return launch_field<STREHL, 8>(env, ts, p, grid, st);
+int launch_phase_n(aog_env* env, TensorState* ts, const FieldParams& p, int n, int grid, cudaStream_t st) {
+  switch (n) {
+    case 1: return launch_phase<STREHL, 1>(env, ts, p, grid, st);
+    case 2: return launch_phase<STREHL, 2>(env, ts, p, grid, st);
+    case 3: return launch_phase<STREHL, 3>(env, ts, p, grid, st);
+    case 4: return launch_phase<STREHL, 4>(env, ts, p, grid, st);
+    case 5: return launch_phase<STREHL, 5>(env, ts, p, grid, st);
+    case 6: return launch_phase<STREHL, 6>(env, ts, p, grid, st);
+    case 7: return launch_phase<STREHL, 7>(env, ts, p, grid, st);
+    case 8: return launch_phase<STREHL, 8>(env, ts, p, grid, st);
   }
   AOG_FAIL(AOG_ERR_UNSUPPORTED, "obs_dim");
 }
@@ -1542,51 +1636,53 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       fp.num_items = cdiv(nB, 128) * Np;
       fp.items_per_cta = std::max(FK_MIN_ITEMS, cdiv(fp.num_items, ts->num_sms));
       fp.nkb = ts->kpad / 64;
-      fp.n = n;
       fp.col_origin = (int)env->cnt.column_origin;
-      fp.do_strehl = strehl ? 1 : 0;
       fp.env0 = e0;
       { const char* d = getenv("AOG_FK_DEBUG"); fp.dbg = d ? atoi(d) : 0; }
-      fp.sci_ratio = (float)(c.wavelength_wfs / c.wavelength_sci);
-      fp.hwt = ts->hwt; fp.apmask = ts->apmask; fp.m1o32 = ts->m1o32;
-      fp.E_hi = ts->E_hi; fp.E_lo = ts->E_lo; fp.R4 = ts->R4; fp.strehl_part = env->strehl_part;
+      fp.sci_ratio_q32 = (uint32_t)std::llround(c.wavelength_wfs / c.wavelength_sci * 4294967296.0);
+      fp.hwt = ts->hwt; fp.apmask = ts->apmask; fp.m1o32 = ts->m1o32; fp.phi = ts->phi; fp.R4 = ts->R4;
+      fp.strehl_part = env->strehl_part;
       fp.err_flag = ts->err_flag;
       const int grid = cdiv(fp.num_items, fp.items_per_cta);
       int rc;
       if (strehl) {
         AOG_CUDA(cudaMemsetAsync(env->strehl_part, 0, (size_t)nB * FK_SLOTS * sizeof(double2), st));
-        rc = launch_field_n<true>(env, ts, fp, grid, st);
+        rc = launch_phase_n<true>(env, ts, fp, n, grid, st);
       } else {
-        rc = launch_field_n<false>(env, ts, fp, grid, st);
+        rc = launch_phase_n<false>(env, ts, fp, n, grid, st);
       }
       if (rc) return rc;
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev0, st)); }
-    TcParams p{};
-    p.num_envs = nB;
-    p.err_flag = ts->err_flag;
-    { const char* d = getenv("AOG_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
-    p.T_hi = ts->T_hi; p.T_lo = ts->T_lo;
-    p.lpw = ts->lpw; p.lpwq = ts->lpwq; p.coef_raw = reinterpret_cast<double*>(env->coef); p.J = J;
-    p.num_items = nB;
     const int max_clusters = ts->num_sms / 2;
-    static const int mft_old = getenv("AOG_MFT_OLD") ? atoi(getenv("AOG_MFT_OLD")) : 0;   // bring-up A/B switch: bit 0 stage 1, bit 1 stage 2
-    if (mft_old & 1)
-      k_mft_tc<0><<<2 * std::min(max_clusters, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmE_hi,
-                                                                                      ts->tmE_lo, p);
-    else
-      k_mft2<0, 1><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmE_hi,
-                                                                                       ts->tmE_lo, ts->tmTout_hi, ts->tmTout_lo, p);
-    AOG_LAUNCH_CHECK();
+    int tc_dbg = 0;
+    { const char* d = getenv("AOG_TC_DEBUG"); tc_dbg = d ? atoi(d) : 0; }
+    {
+      F1Params f1{};
+      f1.num_items = nB;
+      f1.apmask = ts->apmask;
+      f1.dbg = tc_dbg; f1.err_flag = ts->err_flag;
+      static bool configured = false;
+      if (!configured) {
+        AOG_CUDA(cudaFuncSetAttribute(k_field_mft1, cudaFuncAttributeMaxDynamicSharedMemorySize, F1_SMEM_BYTES));
+        configured = true;
+      }
+      k_field_mft1<<<2 * std::min(max_clusters, nB), F1_THREADS, F1_SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmPhi,
+                                                                                   ts->tmTout_hi, ts->tmTout_lo, f1);
+      AOG_LAUNCH_CHECK();
+    }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->evm, st)); }
     if (with_reward) {
+      TcParams p{};
+      p.num_envs = nB;
+      p.err_flag = ts->err_flag;
+      p.dbg = tc_dbg;
+      p.T_hi = ts->T_hi; p.T_lo = ts->T_lo;
+      p.lpw = ts->lpw; p.lpwq = ts->lpwq; p.coef_raw = reinterpret_cast<double*>(env->coef); p.J = J;
       p.num_items = (nB + 1) / 2;
-      if (mft_old & 2)
-        k_mft_tc<1><<<2 * std::min(max_clusters, p.num_items), TC_THREADS, SMEM_BYTES, st>>>(ts->tmB2_hi, ts->tmB2_lo, ts->tmT_hi,
-                                                                                        ts->tmT_lo, p);
-      else if (J <= 3)
-        k_mft2<1, 3><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi,
-                                                                                            ts->tmT128_lo, ts->tmTout_hi, ts->tmTout_lo, p);
+      if (J <= 3)
+        k_mft2<1, 3><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(
+            ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi, ts->tmT128_lo, ts->tmTout_hi, ts->tmTout_lo, p);
       else
         k_mft2<1, AOG_MAX_LP><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(
             ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi, ts->tmT128_lo, ts->tmTout_hi, ts->tmTout_lo, p);
