@@ -27,7 +27,7 @@ static __global__ void k_actuators(const ActT* __restrict__ actions, const doubl
   double part = 0.0;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     double r = 0.0;
-    for (int j = 0; j < K; ++j) r += gram[(size_t)i * K + j] * sh_a[j];
+    for (int j = 0; j < K; ++j) r += gram[(size_t)j * K + i] * sh_a[j];   // G is symmetric: read it column-wise (coalesced)
     part += sh_a[i] * r;
   }
   part = warp_sum(part);

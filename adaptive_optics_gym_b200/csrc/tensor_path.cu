@@ -1,19 +1,25 @@
 // Tensor-core arithmetic of the AO-v0 step path (AOG_PRECISION_TENSOR), sm_100a only.
 //
-// The matrix Fourier transform F = M1 . E . M2 (reference AO_env.py:138 -> hcipy
-// FraunhoferPropagator / MatrixFourierTransform) runs as two real-embedded complex GEMMs on the
-// 5th-gen tensor cores (tcgen05.mma kind::f16, FP32 accumulators in TMEM), operands staged in
-// shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_64B) through a 3-stage mbarrier ring:
+// Three kernels per chunk of environments:
+//   k_dm_phase_tc   DM surface as a tcgen05 GEMM over blocks of 128 envs; epilogue = total wavefront phase
+//                   (atmosphere + DM) -> HBM as FP32 radians, obs-arm column sums, Strehl sums
+//   k_field_mft1    field warps turn that phase into the pupil field ON CHIP (sincos, aperture, fp16 hi/lo) as the
+//                   B operand of the first matrix-Fourier-transform product; epilogue = stage-1 product, split fp16
+//   k_mft2          second product with the fibre-mode projection in its epilogue
+//
+// The matrix Fourier transform F = M1 . E . M2 (reference AO_env.py:138 -> hcipy FraunhoferPropagator /
+// MatrixFourierTransform) runs as two real-embedded complex GEMMs on the 5th-gen tensor cores (tcgen05.mma
+// cta_group::2 kind::f16, M = 256 over a CTA pair, FP32 accumulators in TMEM), operands staged in shared memory
+// by TMA (cp.async.bulk.tensor, SWIZZLE_64B) through mbarrier rings:
 //
 //   stage 1  [Tr ; Ti] (256 x 240) = [[M1r, -M1i], [M1i, M1r]] (256 x 480) . [Er ; Ei] (480 x 240)
-//   stage 2  [Fr | Fi] (128 x 256) = [Tr | Ti] (128 x 480) . [[M2r, M2i], [-M2i, M2r]] (480 x 256)
+//   stage 2  [Fr ; Fi]^T (256 x 256) = [[M2r, -M2i], [M2i, M2r]]^T (256 x 480) . [T(env a) | T(env b)] (480 x 256)
 //
-// Precision: every operand is split x = hi + lo into two fp16 values (|x| <= 240, so the pair
-// carries ~22 bits) and each product is issued as hi.hi + hi.lo + lo.hi ("3x split"), which
-// keeps FP32-class accuracy at fp16 tensor throughput.  The unit-modulus twiddle tables are
-// split once on the host from their FP64 values; the pupil field is split by the field kernel,
-// the stage-1 product by the stage-1 epilogue.  The stage-2 epilogue never writes the focal
-// plane: it projects it on the fibre modes (AO_env.py:471) straight out of TMEM.
+// Precision: every operand is split x = hi + lo into two fp16 values (|x| <= 240, so the pair carries ~22 bits) and
+// each product is issued as hi.hi + hi.lo + lo.hi ("3x split"), which keeps FP32-class accuracy at fp16 tensor
+// throughput.  The unit-modulus twiddle tables are split once on the host from their FP64 values; the pupil field is
+// split by the field warps, the stage-1 product by the stage-1 epilogue.  The stage-2 epilogue never writes the focal
+// plane: it projects it on the fibre modes (AO_env.py:471) out of TMEM.
 #include "tensor_path.cuh"
 #include "kernels_f64.cuh"
 
@@ -31,7 +37,6 @@ constexpr int TC_K = 2 * TC_NP;     // real-embedded contraction length (480)
 constexpr int KB = 32;              // K elements per pipeline stage (64 B rows, SWIZZLE_64B)
 constexpr int NUM_KB = TC_K / KB;   // 15
 constexpr int A_TILE = 128 * KB * 2;            // 8 KB: 128 rows x 64 B
-constexpr int B_TILE = 256 * KB * 2;            // 16 KB slot (stage 1 uses 240 rows of it)
 constexpr float PHI_ONE = 4194304.f;   // 2^22 fixed-point units per half-turn of phase
 
 struct TensorState {
@@ -116,25 +121,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// multicast variant: the box lands at the same smem offset in both CTAs of the 2-CTA cluster and signals the
-// mbarrier at the same offset in each of them
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"((uint16_t)3)
-      : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-// commit that arrives on the barrier at this offset in BOTH CTAs of the cluster
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -190,26 +181,26 @@ struct TcParams {
   int* err_flag;
 };
 
-// ----------------------------------------------------------------------------- pair-MMA MFT kernel
-// k_mft2: both MFT stages as cta_group::2 MMAs (M = 256 over the CTA pair, each CTA holds 128 rows of A and
-// HALF of the B tile in its own shared memory, so no operand is multicast or duplicated and the per-SM
-// shared-memory traffic per MMA drops by a third against the cta_group::1 kernel above):
-//   MODE 0 (stage 1, item = env):      A = twiddle rows (CTA 0: Tr rows, CTA 1: Ti rows), B = the env's field,
-//                                      N = 240 pupil columns x (CTA r stages x in [120 r, 120 r + 120))
-//   MODE 1 (stage 2, item = env pair): F^T: A = twiddle rows (CTA 0: Fr, CTA 1: Fi; M = focal column u),
-//                                      B = the stage-1 products of the two envs stacked along N = 2 x 128
-//                                      focal rows v (CTA r stages env 2 item + r)
+// ----------------------------------------------------------------------------- MFT stage 2 (pair MMA)
+// k_mft2: the second MFT product with the fibre projection in its epilogue, as cta_group::2 MMAs (M = 256 over the
+// CTA pair; each CTA holds 128 rows of A and HALF of the B tile in its own shared memory, so no operand is
+// multicast or duplicated).  item = env pair; computes F^T:
+//   A = twiddle rows (CTA 0: Fr, CTA 1: Fi; M = focal column u), B = the stage-1 products of the two envs
+//   stacked along N = 2 x 128 focal rows v (CTA r stages env 2 item + r), K = 480 = (x | 240 + x).
 // Only the leader CTA (rank 0) issues MMAs; both CTAs' TMA loads complete on the leader's `full` barrier,
 // tcgen05.commit multicasts `empty` / `tmem_full` to both CTAs, and both CTAs' epilogue warps arrive on the
 // leader's `tmem_empty`.  8 epilogue warps per CTA (two per TMEM lane group, half of the columns each).
+// TMEM holds SEPARATE accumulators for the main hi.hi chain and for the hi.lo + lo.hi corrections: the tensor
+// core truncates its FP32 accumulation, so every accumulate onto a large sum costs ~ -0.5 ulp; keeping the
+// 2 x 30 tiny correction updates off the main accumulator cuts that bias 3x (tools/tensor_bias_probe.py).
 constexpr int M2_STAGES = 5;
 constexpr int M2_STAGE_BYTES = 4 * A_TILE;          // 32 KB: [A_hi][A_lo][B_hi slot][B_lo slot], 8 KB each
 constexpr int M2_EPI_WARPS = 8;
 constexpr int M2_THREADS = (2 + M2_EPI_WARPS) * 32; // 320
-constexpr int M2_OUT_TILE = 128 * 16 * 2;           // 4 KB: 128 rows x 16 fp16 of the stage-1 product (SWIZZLE_32B)
-constexpr int M2_OUT_BUFS = 3;                      // per column half: ring of (hi, lo) tile pairs for the TMA stores
+constexpr int M2_OUT_TILE = 128 * 16 * 2;           // stage-1 kernel: 4 KB, 128 rows x 16 fp16 of its product (SWIZZLE_32B)
+constexpr int M2_OUT_BUFS = 3;                      // stage-1 kernel: per column half, ring of (hi, lo) tile pairs for the TMA stores
 constexpr int M2_EPI_BYTES = 2 * M2_OUT_BUFS * 2 * M2_OUT_TILE;   // 48 KB
-constexpr int M2_SMEM_BYTES = M2_STAGES * M2_STAGE_BYTES + M2_EPI_BYTES + 1024 /*align*/ + 4096 /*barriers + reduction scratch*/;
+constexpr int M2_SMEM_BYTES = M2_STAGES * M2_STAGE_BYTES + 1024 /*align*/ + 4096 /*barriers + reduction scratch*/;
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
@@ -263,25 +254,23 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
 }
 
 // JT: compile-time bound on the fibre modes held in registers (3 = the reference's LP01 + 2 x LP11; 8 = generic)
-template <int MODE, int JT>
+template <int JT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(M2_THREADS, 1)
 k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-       const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo, const TcParams p) {
-  constexpr int N_MMA = (MODE == 0) ? TC_NP : 2 * TC_NF;             // 240 | 256
-  constexpr int B_ROWS = N_MMA / 2;                                  // rows of B each CTA stages: 120 | 128
+       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+  constexpr int N_MMA = 2 * TC_NF;                                   // 256
+  constexpr int B_ROWS = N_MMA / 2;                                  // rows of B each CTA stages: 128
   // bytes landing per stage over BOTH CTAs (all of them complete on the leader's barrier)
   constexpr uint32_t TX_BYTES = 2 * (2 * A_TILE + 2 * B_ROWS * KB * 2);
   constexpr uint32_t IDESC = umma_idesc_f16(256, N_MMA);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* epi = base + M2_STAGES * M2_STAGE_BYTES;      // MODE 0: output tile ring
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi + M2_EPI_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + M2_STAGES * M2_STAGE_BYTES);
   uint64_t* empty = full + M2_STAGES;
   uint64_t* tmem_full = empty + M2_STAGES;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  double* red = reinterpret_cast<double*>(epi + M2_EPI_BYTES + 256);   // [2 bufs][8 warps][2 envs][AOG_MAX_LP]
+  double* red = reinterpret_cast<double*>(base + M2_STAGES * M2_STAGE_BYTES + 256);   // [2 bufs][8 warps][2 envs][AOG_MAX_LP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t rank;
@@ -316,7 +305,7 @@ k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
       int stage = 0;
       uint32_t phase = 0;
       for (int item = cluster_id; item < p.num_items; item += num_clusters) {
-        const int b_row0 = (MODE == 0) ? item * TC_NP + (int)rank * B_ROWS : (2 * item + (int)rank) * TC_NF;
+        const int b_row0 = (2 * item + (int)rank) * TC_NF;
         for (int kb = 0; kb < NUM_KB; ++kb) {
           mbar_wait<32>(&empty[stage], phase ^ 1, p.err_flag, 1);
           if (p.dbg & 2) { if (rank == 0) mbar_arrive(&full[stage]); if (++stage == M2_STAGES) { stage = 0; phase ^= 1; } continue; }
@@ -371,7 +360,6 @@ k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
     const uint32_t tmem_empty_leader = mapa_rank(smem_u32(tmem_empty), 0);
     uint32_t tphase = 0;
     int it = 0;
-    uint32_t out_seq = 0;
     for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
       mbar_wait(tmem_full, tphase, p.err_flag, 4);
       tc_fence_after();
@@ -382,64 +370,7 @@ k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
         tphase ^= 1;
         continue;
       }
-      if constexpr (MODE == 0) {
-        // Phase 1: drain this warp's accumulator columns (main + corrections) into registers and hand the
-        // TMEM back, so the next env's MMAs run under phase 2.  The 4 warps of a column half own the
-        // 16-column chunks c = 8 half ... (8 | 7 of the 15).
-        const int c0 = half * 8, c_end = half ? TC_NP / 16 : 8;
-        float acc[128];
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          float v[32], w[32];
-          if (c0 + i + 1 < c_end) {
-            tc_ld32(lane_addr + (c0 + i) * 16, v);
-            tc_ld32(lane_addr + 256 + (c0 + i) * 16, w);
-          } else {
-            tc_ld16(lane_addr + (c0 + i) * 16, v);
-            tc_ld16(lane_addr + 256 + (c0 + i) * 16, w);
-#pragma unroll
-            for (int q = 16; q < 32; ++q) v[q] = w[q] = 0.f;
-          }
-          tc_wait_ld();
-#pragma unroll
-          for (int q = 0; q < 32; ++q) acc[i * 16 + q] = v[q] + w[q];
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
-        if (p.dbg & 8) { if (acc[0] == 1.2345f && acc[127] == 6.789f) p.T_hi[0] = __float2half(1.f); tphase ^= 1; continue; }
-        // Phase 2: split fp16 -> swizzled 128 x 16 tiles in shared memory -> TMA stores into
-        // T[env][v][k = rank * 240 + x].
-        uint8_t* ring = epi + half * (M2_OUT_BUFS * 2 * M2_OUT_TILE);
-        const uint32_t sw = (uint32_t)((row >> 2) & 1);                 // SWIZZLE_32B: 16-byte piece ^= address bit 7
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = c0 + i;
-          if (c < c_end) {
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) split_pack2(acc[i * 16 + 2 * q], acc[i * 16 + 2 * q + 1], hi[q], lo[q]);
-            uint8_t* t_hi = ring + (out_seq % M2_OUT_BUFS) * (2 * M2_OUT_TILE);
-            uint8_t* t_lo = t_hi + M2_OUT_TILE;
-            *reinterpret_cast<uint4*>(t_hi + row * 32 + ((0u ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(t_hi + row * 32 + ((1u ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            *reinterpret_cast<uint4*>(t_lo + row * 32 + ((0u ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<uint4*>(t_lo + row * 32 + ((1u ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-            else           asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (lg == 0 && lane == 0) {
-              tma_store_2d(&tmO_hi, smem_u32(t_hi), (int)rank * TC_NP + c * 16, item * 128);
-              tma_store_2d(&tmO_lo, smem_u32(t_lo), (int)rank * TC_NP + c * 16, item * 128);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              // the store issued one chunk ago has left shared memory: with 3 buffers the slot written two
-              // chunks from now is free by the time its writers pass the next barrier
-              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            }
-            ++out_seq;
-          }
-        }
-      } else {
+      {
         // Accumulator = F^T: lane = focal column u, TMEM column = env * 128 + focal row v; this warp takes
         // v in [64 half, 64 half + 64) of both envs of the pair.
         // Phase 1: drain those columns (main + corrections) into registers and hand the TMEM back.
@@ -532,7 +463,6 @@ k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
       }
       tphase ^= 1;
     }
-    if (MODE == 0 && lg == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
   }
   tc_fence_before();
   __syncthreads();
@@ -705,15 +635,23 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
           mbar_wait<100>(&full[stage], phase, p.err_flag, 13);
           tc_fence_after();
           const uint32_t s0 = smem_u32(base + stage * FK_STAGE_BYTES);
+          // The tensor core truncates its FP32 accumulation (~ -0.5 ulp of the running sum per MMA): issue the
+          // tiny hi.lo + lo.hi corrections FIRST, while the accumulator is still small, and the hi.hi chain last,
+          // so only the 4 main MMAs of a K block round at the magnitude of the result.
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t a_hi = umma_desc_sw128(s0 + ks * 32);
             const uint64_t a_lo = umma_desc_sw128(s0 + FK_A_TILE + ks * 32);
             const uint64_t b_hi = umma_desc_sw128(s0 + 2 * FK_A_TILE + ks * 32);
             const uint64_t b_lo = umma_desc_sw128(s0 + 2 * FK_A_TILE + FK_B_TILE + ks * 32);
-            tc_mma_f16(d, a_hi, b_hi, IDESC, (kb | ks) != 0);
-            tc_mma_f16(d, a_hi, b_lo, IDESC, 1);
+            tc_mma_f16(d, a_hi, b_lo, IDESC, (kb | ks) != 0);
             tc_mma_f16(d, a_lo, b_hi, IDESC, 1);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t a_hi = umma_desc_sw128(s0 + ks * 32);
+            const uint64_t b_hi = umma_desc_sw128(s0 + 2 * FK_A_TILE + ks * 32);
+            tc_mma_f16(d, a_hi, b_hi, IDESC, 1);
           }
           tc_commit(&empty[stage]);
           if (++stage == FK_STAGES) { stage = 0; phase ^= 1; }
@@ -920,16 +858,17 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
 //               field warps must not have global loads of their own in flight, because the release fence of
 //               their barrier arrival waits for them
 //   warps 12-15 field warps, one pupil column x per thread: phase -> sincos (SFU) -> aperture -> fp16 hi/lo
-//               split -> the B operand rows of a short ring (3 x 16 KB), written in the UMMA SWIZZLE_64B
-//               image; `b_full` collects one arrival per field warp of BOTH CTAs
+//               split -> the B operand rows, written in the UMMA SWIZZLE_64B image.  They work on PAIRS of
+//               K blocks (one B slot = 2 x 16 KB, ring of 2) so the fence + barrier traffic is paid once
+//               per 32 pixels; `b_full` collects one arrival per field warp of BOTH CTAs
 // Registers are re-partitioned with setmaxnreg: the epilogue warps hold 128 accumulator columns each.
-constexpr int F1_A_SLOTS = 5;
-constexpr int F1_B_SLOTS = 3;
-constexpr int F1_SLOT_BYTES = 2 * A_TILE;             // 16 KB: [hi 8 KB][lo 8 KB]
+constexpr int F1_A_SLOTS = 4;
+constexpr int F1_B_SLOTS = 2;                         // each holds a PAIR of K blocks
+constexpr int F1_SLOT_BYTES = 2 * A_TILE;             // 16 KB: [hi 8 KB][lo 8 KB] of one K block
 constexpr int F1_PHI_SLOTS = 6;
 constexpr int F1_PHI_TILE = 8192;                     // 120 rows x 64 B in an 8 KB slot
 constexpr int F1_THREADS = 512;
-constexpr int F1_SMEM_BYTES = (F1_A_SLOTS + F1_B_SLOTS) * F1_SLOT_BYTES + F1_PHI_SLOTS * F1_PHI_TILE + M2_EPI_BYTES +
+constexpr int F1_SMEM_BYTES = (F1_A_SLOTS + 2 * F1_B_SLOTS) * F1_SLOT_BYTES + F1_PHI_SLOTS * F1_PHI_TILE + M2_EPI_BYTES +
                               1024 /*align*/ + 1024 /*barriers*/;
 
 struct F1Params {
@@ -950,7 +889,7 @@ k_field_mft1(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = base;
   uint8_t* b_ring = base + F1_A_SLOTS * F1_SLOT_BYTES;
-  uint8_t* phis = b_ring + F1_B_SLOTS * F1_SLOT_BYTES;                 // phase tile ring
+  uint8_t* phis = b_ring + 2 * F1_B_SLOTS * F1_SLOT_BYTES;             // phase tile ring
   uint8_t* epi = phis + F1_PHI_SLOTS * F1_PHI_TILE;                    // output tile ring
   uint64_t* a_full = reinterpret_cast<uint64_t*>(epi + M2_EPI_BYTES);
   uint64_t* a_empty = a_full + F1_A_SLOTS;
@@ -1020,10 +959,10 @@ k_field_mft1(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         tc_fence_after();
         for (int kb = 0; kb < NUM_KB; ++kb) {
           mbar_wait(&a_full[sa], pa, p.err_flag, 3);
-          mbar_wait(&b_full[sb], pb, p.err_flag, 8);
+          if (!(kb & 1)) mbar_wait(&b_full[sb], pb, p.err_flag, 8);       // a B slot carries K blocks kb, kb + 1
           tc_fence_after();
           const uint32_t a0 = smem_u32(a_ring + sa * F1_SLOT_BYTES);
-          const uint32_t b0 = smem_u32(b_ring + sb * F1_SLOT_BYTES);
+          const uint32_t b0 = smem_u32(b_ring + (2 * sb + (kb & 1)) * F1_SLOT_BYTES);
           if (!(p.dbg & 1))
 #pragma unroll
           for (int ks = 0; ks < KB / 16; ++ks) {
@@ -1034,10 +973,12 @@ k_field_mft1(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             tc_mma_f16_pair(tmem_base + 256, a_hi, b_lo, IDESC, acc);        // corrections
             tc_mma_f16_pair(tmem_base + 256, a_lo, b_hi, IDESC, 1);
           }
-          tc_commit_pair(&a_empty[sa]);             // both slots are free in both CTAs when these MMAs retire
-          tc_commit_pair(&b_empty[sb]);
+          tc_commit_pair(&a_empty[sa]);             // the slot is free in both CTAs when these MMAs retire
           if (++sa == F1_A_SLOTS) { sa = 0; pa ^= 1; }
-          if (++sb == F1_B_SLOTS) { sb = 0; pb ^= 1; }
+          if ((kb & 1) || kb == NUM_KB - 1) {
+            tc_commit_pair(&b_empty[sb]);
+            if (++sb == F1_B_SLOTS) { sb = 0; pb ^= 1; }
+          }
         }
         tc_commit_pair(tmem_full);
         tphase ^= 1;
@@ -1154,10 +1095,10 @@ k_field_mft1(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
       for (int kb = 0; kb < NUM_KB; ++kb) {                  // fully unrolled: kb indexes the mask registers
         if (!(p.dbg & 64)) mbar_wait(&phi_full[slot], pphase, p.err_flag, 6);
-        mbar_wait(&b_empty[sb], pb ^ 1, p.err_flag, 7);
+        if (!(kb & 1)) mbar_wait(&b_empty[sb], pb ^ 1, p.err_flag, 7);
         if (active && !(p.dbg & 32)) {
           const uint32_t mask = (kb & 1) ? (maskw[kb >> 1] >> 16) : (maskw[kb >> 1] & 0xFFFFu);
-          uint8_t* b_hi = b_ring + sb * F1_SLOT_BYTES + t * 64;
+          uint8_t* b_hi = b_ring + (2 * sb + (kb & 1)) * F1_SLOT_BYTES + t * 64;
           uint8_t* b_lo = b_hi + A_TILE;
           if (mask == 0) {                                  // outside the aperture: the field is zero
             const uint4 z = make_uint4(0, 0, 0, 0);
@@ -1198,13 +1139,18 @@ k_field_mft1(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             }
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_cluster(b_full_leader0 + sb * 8);       // my rows of the B tile are in place
-          if (!(p.dbg & 64)) mbar_arrive(&phi_empty[slot]);   // the phase tile may be overwritten
+        if ((kb & 1) || kb == NUM_KB - 1) {                   // the pair is complete: publish it
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(b_full_leader0 + sb * 8);     // my rows of the B tiles are in place
+            if (!(p.dbg & 64)) {                              // the phase tiles may be overwritten
+              if (kb & 1) mbar_arrive(&phi_empty[slot == 0 ? F1_PHI_SLOTS - 1 : slot - 1]);
+              mbar_arrive(&phi_empty[slot]);
+            }
+          }
+          if (++sb == F1_B_SLOTS) { sb = 0; pb ^= 1; }
         }
-        if (++sb == F1_B_SLOTS) { sb = 0; pb ^= 1; }
         if (++slot == F1_PHI_SLOTS) { slot = 0; pphase ^= 1; }
       }
     }
@@ -1398,8 +1344,8 @@ int aog_tensor_create(aog_env* env) {
   A(make_map(env, &ts->tmModes_hi, ts->modesK_hi, P, TC_NP, ts->kpad, 64));
   A(make_map(env, &ts->tmModes_lo, ts->modesK_lo, P, TC_NP, ts->kpad, 64));
 #undef A
-  AOG_CUDA(cudaFuncSetAttribute(k_mft2<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
-  AOG_CUDA(cudaFuncSetAttribute(k_mft2<1, AOG_MAX_LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
+  AOG_CUDA(cudaFuncSetAttribute(k_mft2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
+  AOG_CUDA(cudaFuncSetAttribute(k_mft2<AOG_MAX_LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
   return AOG_OK;
 }
 
@@ -1681,11 +1627,11 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       p.lpw = ts->lpw; p.lpwq = ts->lpwq; p.coef_raw = reinterpret_cast<double*>(env->coef); p.J = J;
       p.num_items = (nB + 1) / 2;
       if (J <= 3)
-        k_mft2<1, 3><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(
-            ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi, ts->tmT128_lo, ts->tmTout_hi, ts->tmTout_lo, p);
+        k_mft2<3><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(
+            ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi, ts->tmT128_lo, p);
       else
-        k_mft2<1, AOG_MAX_LP><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(
-            ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi, ts->tmT128_lo, ts->tmTout_hi, ts->tmTout_lo, p);
+        k_mft2<AOG_MAX_LP><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(
+            ts->tmB2_hi, ts->tmB2_lo, ts->tmT128_hi, ts->tmT128_lo, p);
       AOG_LAUNCH_CHECK();
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev1, st)); env->ev_valid = true; }

@@ -73,7 +73,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(',')])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -159,7 +159,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=60)
+    ap.add_argument('--steps', type=int, default=300)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='environments per GPU')
@@ -260,11 +260,11 @@ def main():
     if sampler:
         sampler.start()
     ms, launches = timed(step_device, args.steps, args.warmup)
-    clocks = sampler.summary() if sampler else None
     value = world * B * args.steps / (ms * 1e-3)
 
     ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    clocks = sampler.summary() if sampler else None      # sampled over both timed regions
 
     # roofline of the dominant kernel sequence: MFT GEMMs, CUDA events inside the library
     env._h.set_timing(True)
@@ -298,8 +298,20 @@ def main():
         peak = 37.0
         peak_note = 'nominal B200 FP64 37 TFLOP/s (no measured FP64 peak in MEASURED_PEAKS.json)'
         issued = 1.0
+    # dram__bytes_read + dram__bytes_write of the two MFT kernels from the committed ncu --set full capture
+    # (profiles/), valid for the chunk size it was taken at
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'mft_dram_traffic.json')))
+        if precision == 'tensor' and tj.get('envs_per_launch') == last_chunk:
+            traffic = tj['bytes_per_launch']
+    except Exception:
+        pass
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'traffic': None, 'kernel': 'MFT stage-1 + stage-2 complex GEMMs', 'ms_per_launch': mft,
+                'traffic': traffic,
+                'kernel': ('matrix Fourier transform: k_field_mft1 (field formation + stage-1 product) + k_mft2 (stage-2 '
+                           'product + fibre projection)') if precision == 'tensor' else 'MFT stage-1 + stage-2 complex GEMMs (FP64)',
+                'ms_per_launch': mft,
                 'envs_per_launch': last_chunk, 'algorithmic_flop_per_env': MFT_FLOP_PER_ENV(Np, Nf),
                 'issued_over_algorithmic': issued, 'peak_source': peak_note}
     if kms:
@@ -324,7 +336,10 @@ def main():
         'vs_baseline': None, 'dtype': 'f64' if precision == 'f64' else 'f16x3(tcgen05)+f32/f64',
         'data': 'synthetic',
         'config': {'workload': describe(args.workload, B, world), 'precision': precision, 'envs_per_gpu': B,
-                   'l2_policy': f'inputs larger than L2: {B * Np * Np * 8 / 1e6:.0f} MB of screens read per step',
+                   'l2_policy': (f'inputs larger than L2: {B * Np * Np * 4 / 1e6:.0f} MB of phase-screen tiles read per step, '
+                                 f'plus {B * Np * Np * 4 / 1e6:.0f} MB of phase and {B * 128 * 480 * 4 / 1e6:.0f} MB of stage-1 product '
+                                 'written and re-read (126 MB L2)') if precision == 'tensor' else
+                                f'inputs larger than L2: {B * Np * Np * 8 / 1e6:.0f} MB of screens read per step',
                    'timing': 'CUDA events on the launch stream, max over ranks'},
         'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': B * K * 4,
                 'd2h_bytes_per_step': B * (n2 * 2 + 16), 'ms_per_step': ms_e2e / args.steps},

@@ -7,6 +7,11 @@ itself: they pin the oracle and the CUDA path against regressions and against ea
 against real hcipy ("parity unpinned").  On a machine WITH hcipy, tools/export_hcipy_tables.py
 is the script to run instead.
 
+The autoregressive extrusion matrices A, B (hcipy `InfiniteAtmosphericLayer`) come out of a Tikhonov inverse
+and an SVD of near-singular covariances: their low bits differ between LAPACK builds / CPUs, and that shows up at
+the 1e-5 level in the extruded screens.  The dynamic cases therefore use ONE committed copy of the tables, rounded to
+float32 (tests/golden/ar_tables.npz), injected into the oracle and into the CUDA path alike.
+
     python tools/make_golden.py            # rewrites tests/golden/*.npz
 """
 import json
@@ -38,7 +43,7 @@ CASES = {
     'config4_dynamic_v20_shack_hartmann': dict(
         kw=dict(atm_type='dynamic', atm_vel=20, atm_fried=0.10, act_type='zernike', act_dim=10, obs_dim=2,
                 rew_type='strehl_ratio', timesteps_per_episode=3, SH_operation=True), screen_seed=103, action='sh',
-        episodes=1, env_seed=22),
+        episodes=1, env_seed=21),
 }
 
 
@@ -48,10 +53,40 @@ def screen(seed, r0):
     return O.von_karman_screen(g, cn2, 10.0, np.random.default_rng(seed)).astype(np.float32)
 
 
+AR_TABLES = os.path.join(ROOT, 'tests', 'golden', 'ar_tables.npz')
+AR_SEED = 21
+
+
+def make_ar_tables():
+    """A, B, stencil of the 240 x 240 pupil grid (L0 = 10 m, unit Cn^2), rounded to float32."""
+    env = O.OracleAOEnv(atm_type='dynamic', atm_vel=5, act_type='zernike', act_dim=3, seed=AR_SEED,
+                        initial_screen=np.zeros(57600))
+    lay = env.layer
+    np.savez_compressed(AR_TABLES, ar_A=lay.A_horizontal.astype(np.float32), ar_B=lay.B_horizontal.astype(np.float32),
+                        ar_stencil=np.flatnonzero(lay.stencil_left).astype(np.int32))
+
+
+def load_ar_tables():
+    z = np.load(AR_TABLES)
+    return dict(ar_stencil=z['ar_stencil'], ar_A=z['ar_A'].astype(np.float64), ar_B=z['ar_B'].astype(np.float64))
+
+
+def oracle_env(case, scr):
+    """The oracle env of a case; dynamic cases get the committed AR tables."""
+    kw = case['kw']
+    env = O.OracleAOEnv(**kw, initial_screen=np.asarray(scr, dtype=np.float64), seed=case.get('env_seed', 0))
+    if kw['atm_type'] == 'dynamic':
+        t = load_ar_tables()
+        st = np.zeros(env.layer.stencil_left.size, dtype=bool)
+        st[t['ar_stencil']] = True
+        env.layer.stencil_left, env.layer.A_horizontal, env.layer.B_horizontal = st, t['ar_A'], t['ar_B']
+    return env
+
+
 def run_case(case, scr):
     """-> dict of arrays.  Shared by this script and tests/test_golden.py (oracle side)."""
     kw = case['kw']
-    env = O.OracleAOEnv(**kw, initial_screen=scr.astype(np.float64), seed=case.get('env_seed', 0))
+    env = oracle_env(case, scr)
     rng = np.random.default_rng(case['screen_seed'] + 1000)
     K, T = kw['act_dim'], kw['timesteps_per_episode']
     rec = {k: [] for k in ('actions', 'noise', 'reset_obs', 'obs', 'obs_f16', 'reward', 'power', 'aux', 'done')}
@@ -87,6 +122,7 @@ def run_case(case, scr):
 def main():
     outdir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(outdir, exist_ok=True)
+    make_ar_tables()
     for name, case in CASES.items():
         scr = screen(case['screen_seed'], case['kw'].get('atm_fried', 0.15))
         out = run_case(case, scr)

@@ -1,5 +1,5 @@
 import numpy as np, sys
-sys.path.insert(0,'/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adaptive_optics_gym_b200 import AOEnv
 from oracle.ao_oracle import OracleAOEnv
 from tests.test_parity_gpu import _screen
