@@ -275,11 +275,11 @@ static __global__ void k_obs_rows_f64(const double2* __restrict__ E, const doubl
 // reward, threshold (AO_env.py:142-153, 468-503).  Block per env.
 // --------------------------------------------------------------------------------------
 struct FinalizeArgs {
-  const double2* R; const float2* R4; const double2* m1o; const double2* coef; const double2* lpphase; const double* lpgram;
+  const double2* R; const float2* R4; const double2* m1o; const double2* coef; const double* coef4; const double2* lpphase; const double* lpgram;
   const double2* strehl_part; int strehl_blocks;
   int Np, n, J, rew_type, has_thr, compute_reward;
   int r4_parts;        // partial sums per contraction index in R4
-  int coef_is_raw;     // coef holds unscaled (re, im) projection sums: multiply by coef_scale
+  int coef_is_raw;     // 1: coef holds unscaled (re, im) projection sums; 2: coef4 holds [re|im][2 partials]; x coef_scale
   double2 coef_scale;
   int transpose_out;   // R / table hold the transposed contraction: result (a, b) is obs pixel (v = b, u = a)
   double thr, obs_weight, strehl_scale, ssim_peak;
@@ -352,7 +352,13 @@ static __global__ void k_finalize(FinalizeArgs a) {
   // fibre: out = M (c e^{i beta L});  total power = c'^H G c'
   double2 c[AOG_MAX_LP];
   for (int j = 0; j < a.J; ++j) {
-    double2 cj = a.coef[(size_t)b * a.J + j];
+    double2 cj;
+    if (a.coef_is_raw == 2) {
+      const double* c4 = a.coef4 + ((size_t)b * a.J + j) * 4;
+      cj = make_double2(c4[0] + c4[1], c4[2] + c4[3]);
+    } else {
+      cj = a.coef[(size_t)b * a.J + j];
+    }
     if (a.coef_is_raw) cj = make_double2(cj.x * a.coef_scale.x - cj.y * a.coef_scale.y, cj.x * a.coef_scale.y + cj.y * a.coef_scale.x);
     const double2 ph = a.lpphase[j];
     c[j] = make_double2(cj.x * ph.x - cj.y * ph.y, cj.x * ph.y + cj.y * ph.x);

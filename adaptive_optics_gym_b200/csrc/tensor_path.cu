@@ -45,7 +45,8 @@ struct TensorState {
   __half* B2_hi = nullptr; __half* B2_lo = nullptr;   // [256][480]  stage-2 constant (N-major rows, K contiguous)
   __half* T_hi = nullptr; __half* T_lo = nullptr;     // [chunk][128][480]  stage-1 product
   float* lpw = nullptr;                               // [J][128][128] fibre modes * weight / max
-  float* lpwq = nullptr;                              // the same, [J][v / 4][u][4 v] (coalesced epilogue reads)
+  float* lpwr = nullptr;                              // the same, [rank][v / 16][J][(v / 4) % 4][64 u][4 v] (stage-2 epilogue tiles)
+  double* coef4 = nullptr;                            // [chunk][J][re|im][rank] raw projection sums
   // atmospheric phase at lambda_wfs, UNREDUCED, int32 fixed point in units of 2^-22 half-turns (PHI_ONE per
   // half-turn; +-512 half-turns of range), tiled for the phase kernel's bulk prefetch:
   // [env / 32][Np xp][Np / 16 chunks][32 envs][16 pixels], ring-buffered in xp, the four 16-byte pieces of
@@ -174,8 +175,8 @@ struct TcParams {
   __half* T_hi; __half* T_lo;
   // MODE 1 epilogue: fibre projection, raw sums [env][J][2] (re from cluster rank 0, im from rank 1)
   const float* lpw;     // [J][128][128]
-  const float* lpwq;    // same weights as [J][128 / 4 (v)][128 (u)][4 (v)]
-  double* coef_raw;
+  const float* lpwr;    // same weights as [rank 2][v / 16][J][(v / 4) % 4][64 u][4 v]: one contiguous tile per (rank, 16 rows)
+  double* coef_raw;     // [env][J][part re|im][rank] partial projection sums
   int J;
   int dbg;              // AOG_TC_DEBUG bits (tuning experiments only): 1 no MMA, 2 no TMA, 4 no epilogue work
   int* err_flag;
@@ -196,11 +197,11 @@ struct TcParams {
 constexpr int M2_STAGES = 5;
 constexpr int M2_STAGE_BYTES = 4 * A_TILE;          // 32 KB: [A_hi][A_lo][B_hi slot][B_lo slot], 8 KB each
 constexpr int M2_EPI_WARPS = 8;
-constexpr int M2_THREADS = (2 + M2_EPI_WARPS) * 32; // 320
+constexpr int M2_THREADS = (3 + M2_EPI_WARPS) * 32; // 352: TMA, MMA, 8 epilogue, fibre-weight loader
 constexpr int M2_OUT_TILE = 128 * 16 * 2;           // stage-1 kernel: 4 KB, 128 rows x 16 fp16 of its product (SWIZZLE_32B)
 constexpr int M2_OUT_BUFS = 3;                      // stage-1 kernel: per column half, ring of (hi, lo) tile pairs for the TMA stores
 constexpr int M2_EPI_BYTES = 2 * M2_OUT_BUFS * 2 * M2_OUT_TILE;   // 48 KB
-constexpr int M2_SMEM_BYTES = M2_STAGES * M2_STAGE_BYTES + 1024 /*align*/ + 4096 /*barriers + reduction scratch*/;
+constexpr int M2_SMEM_BYTES = M2_STAGES * M2_STAGE_BYTES + 4 * 3 * 4096 /*fibre-weight ring*/ + 1024 /*align*/ + 4096 /*barriers + reduction scratch*/;
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
@@ -253,24 +254,36 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// JT: compile-time bound on the fibre modes held in registers (3 = the reference's LP01 + 2 x LP11; 8 = generic)
+// JT: compile-time bound on the fibre modes held in registers (3 = the reference's LP01 + 2 x LP11; 8 = generic).
+// Row split: CTA r owns the focal columns u in [64 r, 64 r + 64) for BOTH parts of F^T -- its A rows are
+// [Fr rows of those u | Fi rows of those u] (TMEM lanes 0-63 | 64-127) -- so the real fibre weights of a
+// (u, v) are shared by the Fr and Fi lanes and each CTA streams half of the weight table: per 16 focal rows v
+// one contiguous tile [j][v / 4][64 u][4 v] (4 KB per mode), fetched by a dedicated warp with cp.async.bulk
+// into a 4-slot ring (JT <= 3) and read conflict-free (lane = u).  Epilogue warp (lane group lg, env e):
+// part = lg / 2 (Fr | Fi), all 128 focal rows v of env e.
+constexpr int M2_W_SLOTS = 4;
+constexpr int M2_W_SLOT_BYTES = 3 * 4096;                            // up to 3 modes x [4][64][4] floats
 template <int JT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(M2_THREADS, 1)
 k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
   constexpr int N_MMA = 2 * TC_NF;                                   // 256
   constexpr int B_ROWS = N_MMA / 2;                                  // rows of B each CTA stages: 128
+  constexpr bool W_RING = JT <= 3;
   // bytes landing per stage over BOTH CTAs (all of them complete on the leader's barrier)
   constexpr uint32_t TX_BYTES = 2 * (2 * A_TILE + 2 * B_ROWS * KB * 2);
   constexpr uint32_t IDESC = umma_idesc_f16(256, N_MMA);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(base + M2_STAGES * M2_STAGE_BYTES);
+  uint8_t* wring = base + M2_STAGES * M2_STAGE_BYTES;                // fibre-weight tile ring
+  uint64_t* full = reinterpret_cast<uint64_t*>(wring + M2_W_SLOTS * M2_W_SLOT_BYTES);
   uint64_t* empty = full + M2_STAGES;
-  uint64_t* tmem_full = empty + M2_STAGES;
+  uint64_t* w_full = empty + M2_STAGES;
+  uint64_t* w_empty = w_full + M2_W_SLOTS;
+  uint64_t* tmem_full = w_empty + M2_W_SLOTS;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  double* red = reinterpret_cast<double*>(base + M2_STAGES * M2_STAGE_BYTES + 256);   // [2 bufs][8 warps][2 envs][AOG_MAX_LP]
+  double* red = reinterpret_cast<double*>(wring + M2_W_SLOTS * M2_W_SLOT_BYTES + 256);   // [2 bufs][8 warps][AOG_MAX_LP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t rank;
@@ -283,6 +296,7 @@ k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB_lo)) : "memory");
     for (int s = 0; s < M2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < M2_W_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], M2_EPI_WARPS); }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 2 * M2_EPI_WARPS);          // every epilogue warp of both CTAs (used in the leader only)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -351,117 +365,120 @@ k_mft2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUten
         tphase ^= 1;
       }
     }
+  } else if (warp == 2 + M2_EPI_WARPS) {
+    // ===================== fibre-weight tiles: the same 8 tiles for every env pair =====================
+    if (W_RING && lane == 0 && !(p.dbg & 4)) {
+      int slot = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = (uint32_t)p.J * 4096u;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        for (int c = 0; c < TC_NF / 16; ++c) {
+          mbar_wait<64>(&w_empty[slot], phase ^ 1, p.err_flag, 9);
+          mbar_expect_tx(&w_full[slot], bytes);
+          const float* src = p.lpwr + ((size_t)((int)rank * (TC_NF / 16) + c) * p.J) * 1024;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(wring + slot * M2_W_SLOT_BYTES)), "l"(src), "r"(bytes), "r"(smem_u32(&w_full[slot])) : "memory");
+          if (++slot == M2_W_SLOTS) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
   } else {
-    // ===================== epilogue: 8 warps, TMEM lane group = warp % 4, column half = (warp - 2) / 4 =========
+    // ===================== epilogue: 8 warps, TMEM lane group = warp % 4, env of the pair = (warp - 2) / 4 ========
     const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int e = (warp - 2) >> 2;
     const int row = lg * 32 + lane;
+    const int ul = row & 63;                           // focal column within my CTA's 64
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     const uint32_t tmem_empty_leader = mapa_rank(smem_u32(tmem_empty), 0);
-    uint32_t tphase = 0;
+    uint32_t tphase = 0, wphase = 0;
+    int wslot = 0;
     int it = 0;
     for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
       mbar_wait(tmem_full, tphase, p.err_flag, 4);
       tc_fence_after();
+      tphase ^= 1;
       if (p.dbg & 4) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
-        tphase ^= 1;
         continue;
       }
-      {
-        // Accumulator = F^T: lane = focal column u, TMEM column = env * 128 + focal row v; this warp takes
-        // v in [64 half, 64 half + 64) of both envs of the pair.
-        // Phase 1: drain those columns (main + corrections) into registers and hand the TMEM back.
-        float f0[64], f1[64];
+      // Phase 1: drain env e's 128 columns (main + corrections) into registers and hand the TMEM back.
+      float f[128];
 #pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          const int col = half * 64 + c * 16;
-          float a[32], b[32];
-          tc_ld32(lane_addr + col, a);
-          tc_ld32(lane_addr + 256 + col, b);
-          tc_wait_ld();
+      for (int c = 0; c < 8; c += 2) {
+        float a[32], b[32];
+        tc_ld32(lane_addr + e * 128 + c * 16, a);
+        tc_ld32(lane_addr + 256 + e * 128 + c * 16, b);
+        tc_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 32; ++q) f0[c * 16 + q] = a[q] + b[q];
-          tc_ld32(lane_addr + 128 + col, a);
-          tc_ld32(lane_addr + 256 + 128 + col, b);
-          tc_wait_ld();
+        for (int q = 0; q < 32; ++q) f[c * 16 + q] = a[q] + b[q];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);   // TMEM is free: the next pair's MMAs may start
+      // Phase 2: fibre projection of my part (Fr | Fi) of my 64 focal columns: FP32 per 16 rows, FP64 across.
+      double acc[JT];
 #pragma unroll
-          for (int q = 0; q < 32; ++q) f1[c * 16 + q] = a[q] + b[q];
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);   // TMEM is free: the next tile's MMAs may start
-        // Phase 2: fibre projection of my half (rank 0: sum Fr w, rank 1: sum Fi w); one weight load serves
-        // both envs.
-        double acc[2][JT];
+      for (int j = 0; j < JT; ++j) acc[j] = 0.0;
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
+      for (int c = 0; c < 8; ++c) {
+        float s[JT];
 #pragma unroll
-          for (int j = 0; j < JT; ++j) acc[e][j] = 0.0;
-        const bool env1_ok = 2 * item + 1 < p.num_envs;
-        // weights lpwq[j][v / 4][u][4 v]: a warp's 32 focal columns u read 512 contiguous bytes per load
-        const float4* wbase = reinterpret_cast<const float4*>(p.lpwq) + (size_t)(half * 16) * TC_NF + row;
-        float4 wq[JT][4];
-        auto load_w = [&](int c) {
+        for (int j = 0; j < JT; ++j) s[j] = 0.f;
+        if constexpr (W_RING) {
+          mbar_wait(&w_full[wslot], wphase, p.err_flag, 10);
+          const float4* wt = reinterpret_cast<const float4*>(wring + wslot * M2_W_SLOT_BYTES) + ul;
 #pragma unroll
           for (int j = 0; j < JT; ++j)
-            if (j < p.J) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                wq[j][q] = (p.dbg & 16) ? make_float4(1.f, 2.f, 3.f, (float)c)
-                                        : __ldg(wbase + ((size_t)j * (TC_NF / 4) + c * 4 + q) * TC_NF);
-            }
-        };
-        load_w(0);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float s0[JT], s1[JT];
-#pragma unroll
-          for (int j = 0; j < JT; ++j) {
-            s0[j] = 0.f; s1[j] = 0.f;
             if (j < p.J) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float4 w = wq[j][q];
-                s0[j] = fmaf(f0[c * 16 + 4 * q + 0], w.x, s0[j]); s1[j] = fmaf(f1[c * 16 + 4 * q + 0], w.x, s1[j]);
-                s0[j] = fmaf(f0[c * 16 + 4 * q + 1], w.y, s0[j]); s1[j] = fmaf(f1[c * 16 + 4 * q + 1], w.y, s1[j]);
-                s0[j] = fmaf(f0[c * 16 + 4 * q + 2], w.z, s0[j]); s1[j] = fmaf(f1[c * 16 + 4 * q + 2], w.z, s1[j]);
-                s0[j] = fmaf(f0[c * 16 + 4 * q + 3], w.w, s0[j]); s1[j] = fmaf(f1[c * 16 + 4 * q + 3], w.w, s1[j]);
+                const float4 w = wt[(j * 4 + q) * 64];
+                s[j] = fmaf(f[c * 16 + 4 * q + 0], w.x, s[j]);
+                s[j] = fmaf(f[c * 16 + 4 * q + 1], w.y, s[j]);
+                s[j] = fmaf(f[c * 16 + 4 * q + 2], w.z, s[j]);
+                s[j] = fmaf(f[c * 16 + 4 * q + 3], w.w, s[j]);
               }
             }
-          }
-          if (c + 1 < 4) load_w(c + 1);            // next chunk's weights fly while the sums are folded
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&w_empty[wslot]);
+          if (++wslot == M2_W_SLOTS) { wslot = 0; wphase ^= 1; }
+        } else {
+          const float4* wt = reinterpret_cast<const float4*>(p.lpwr) + ((size_t)((int)rank * (TC_NF / 16) + c) * p.J) * 256 + ul;
 #pragma unroll
           for (int j = 0; j < JT; ++j)
             if (j < p.J) {
-              acc[0][j] += (double)s0[j];
-              if (env1_ok) acc[1][j] += (double)s1[j];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w = __ldg(wt + (j * 4 + q) * 64);
+                s[j] = fmaf(f[c * 16 + 4 * q + 0], w.x, s[j]);
+                s[j] = fmaf(f[c * 16 + 4 * q + 1], w.y, s[j]);
+                s[j] = fmaf(f[c * 16 + 4 * q + 2], w.z, s[j]);
+                s[j] = fmaf(f[c * 16 + 4 * q + 3], w.w, s[j]);
+              }
             }
         }
-        double* rbuf = red + (it & 1) * (M2_EPI_WARPS * 2 * AOG_MAX_LP);
-        const int ew = warp - 2;
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-          for (int j = 0; j < JT; ++j)
-            if (j < p.J) {
-              const double a = warp_sum(acc[e][j]);
-              if (lane == 0) rbuf[(ew * 2 + e) * AOG_MAX_LP + j] = a;
-            }
-        asm volatile("bar.sync 1, %0;" ::"n"(M2_EPI_WARPS * 32) : "memory");
-        if (warp == 2 && lane < 2 * p.J) {
-          const int e = lane / p.J, j = lane - e * p.J;
-          const int env = 2 * item + e;
-          if (env < p.num_envs) {
-            double s = 0.0;
-            for (int g4 = 0; g4 < M2_EPI_WARPS; ++g4) s += rbuf[(g4 * 2 + e) * AOG_MAX_LP + j];
-            p.coef_raw[((size_t)env * p.J + j) * 2 + rank] = s;
-          }
-        }
+        for (int j = 0; j < JT; ++j) acc[j] += (double)s[j];
       }
-      tphase ^= 1;
+      double* rbuf = red + (it & 1) * (M2_EPI_WARPS * AOG_MAX_LP);
+      const int ew = warp - 2;                          // = e * 4 + lg
+#pragma unroll
+      for (int j = 0; j < JT; ++j)
+        if (j < p.J) {
+          const double a = warp_sum(acc[j]);
+          if (lane == 0) rbuf[ew * AOG_MAX_LP + j] = a;
+        }
+      asm volatile("bar.sync 1, %0;" ::"n"(M2_EPI_WARPS * 32) : "memory");
+      if (warp == 2 && lane < 4 * p.J) {
+        // (env of the pair, part, mode): sum of the two lane groups of that part
+        const int j = lane % p.J, pe = lane / p.J, part = pe & 1, ee = pe >> 1;
+        const int env = 2 * item + ee;
+        if (env < p.num_envs)
+          p.coef_raw[(((size_t)env * p.J + j) * 2 + part) * 2 + rank] =
+              rbuf[(ee * 4 + 2 * part) * AOG_MAX_LP + j] + rbuf[(ee * 4 + 2 * part + 1) * AOG_MAX_LP + j];
+      }
     }
   }
   tc_fence_before();
@@ -1311,7 +1328,8 @@ int aog_tensor_create(aog_env* env) {
   AOG_CUDA(cudaMemset(ts->T_hi, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
   AOG_CUDA(cudaMemset(ts->T_lo, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
   A(talloc(env, &ts->lpw, (size_t)c.num_lp_modes * env->NF2));
-  A(talloc(env, &ts->lpwq, (size_t)c.num_lp_modes * env->NF2));
+  A(talloc(env, &ts->lpwr, (size_t)c.num_lp_modes * env->NF2));
+  A(talloc(env, &ts->coef4, ch * (size_t)c.num_lp_modes * 4));
   if (c.obs_dim > 8) AOG_FAIL(AOG_ERR_UNSUPPORTED, "tensor precision path supports obs_dim <= 8");
   ts->kpad = ((c.num_modes + 63) / 64) * 64;
   ts->act_rows = (int)((ch + 127) / 128) * 128;
@@ -1352,7 +1370,7 @@ int aog_tensor_create(aog_env* env) {
 void aog_tensor_destroy(aog_env* env) {
   TensorState* ts = TS(env);
   if (!ts) return;
-  void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->phi, ts->T_hi, ts->T_lo, ts->lpw, ts->lpwq,
+  void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->phi, ts->T_hi, ts->T_lo, ts->lpw, ts->lpwr, ts->coef4,
                   ts->hwt, ts->modesK_hi, ts->modesK_lo, ts->act_hi, ts->act_lo, ts->apmask, ts->m1o32, ts->R4,
                   ts->m2oT, ts->err_flag};
   for (void* p : ptrs)
@@ -1392,10 +1410,12 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
     for (int x = 0; x < Np; ++x)
       for (int u = 0; u < Nf; ++u) {
         const double re = m[2 * ((size_t)x * Nf + u)], im = m[2 * ((size_t)x * Nf + u) + 1];
-        b[(size_t)u * TC_K + x] = re;
-        b[(size_t)u * TC_K + Np + x] = -im;
-        b[(size_t)(128 + u) * TC_K + x] = im;
-        b[(size_t)(128 + u) * TC_K + Np + x] = re;
+        // operand rows: CTA r = u / 64 owns rows [128 r, 128 r + 128) = [Fr rows of its 64 u | Fi rows of its 64 u]
+        const size_t rr = (size_t)(u / 64) * 128 + u % 64, ri = rr + 64;
+        b[rr * TC_K + x] = re;
+        b[rr * TC_K + Np + x] = -im;
+        b[ri * TC_K + x] = im;
+        b[ri * TC_K + Np + x] = re;
       }
     int rc = upload_split(env, b, ts->B2_hi, ts->B2_lo);
     if (rc) return rc;
@@ -1415,11 +1435,14 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
           f[((size_t)j * Nf + u) * Nf + v] = (float)(m[((size_t)j * Nf + v) * Nf + u] / mx);
     AOG_CUDA(cudaMemcpy(ts->lpw, f.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<float> g(cnt);
-    for (int j = 0; j < c.num_lp_modes; ++j)
+    const int J = c.num_lp_modes;
+    for (int j = 0; j < J; ++j)
       for (int v = 0; v < Nf; ++v)
-        for (int u = 0; u < Nf; ++u)
-          g[(((size_t)j * (Nf / 4) + v / 4) * Nf + u) * 4 + (v & 3)] = (float)(m[((size_t)j * Nf + v) * Nf + u] / mx);
-    AOG_CUDA(cudaMemcpy(ts->lpwq, g.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
+        for (int u = 0; u < Nf; ++u) {
+          const size_t tile = ((size_t)(u / 64) * (Nf / 16) + v / 16) * J + j;
+          g[((tile * 4 + (v / 4) % 4) * 64 + u % 64) * 4 + (v & 3)] = (float)(m[((size_t)j * Nf + v) * Nf + u] / mx);
+        }
+    AOG_CUDA(cudaMemcpy(ts->lpwr, g.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
     ts->have_lp = true;
   } else if (which == AOG_TABLE_DM_MODES) {
     // modes [K][y][x] FP64 -> GEMM B operand [x][y][KPAD] split fp16 (k contiguous, zero padded)
@@ -1624,7 +1647,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       p.err_flag = ts->err_flag;
       p.dbg = tc_dbg;
       p.T_hi = ts->T_hi; p.T_lo = ts->T_lo;
-      p.lpw = ts->lpw; p.lpwq = ts->lpwq; p.coef_raw = reinterpret_cast<double*>(env->coef); p.J = J;
+      p.lpw = ts->lpw; p.lpwr = ts->lpwr; p.coef_raw = ts->coef4; p.J = J;
       p.num_items = (nB + 1) / 2;
       if (J <= 3)
         k_mft2<3><<<2 * std::min(max_clusters, p.num_items), M2_THREADS, M2_SMEM_BYTES, st>>>(
@@ -1641,8 +1664,8 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       // coef holds the raw projection sums (re, im): scale = norm * amp * pupil weight * table scale
       const double sc = c.amp_fiber * ts->pupil_weight * ts->lpw_scale;
       a.coef_scale = make_double2(c.mft_norm_re * sc, c.mft_norm_im * sc);
-      a.coef_is_raw = 1;
-    } a.coef = env->coef; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
+      a.coef_is_raw = 2;
+    } a.coef = nullptr; a.coef4 = ts->coef4; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
     a.strehl_part = env->strehl_part; a.strehl_blocks = FK_SLOTS;
     a.Np = Np; a.n = n; a.J = J; a.rew_type = c.rew_type; a.has_thr = c.has_rew_threshold;
     a.compute_reward = with_reward ? 1 : 0;
