@@ -530,8 +530,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 
 // sin / cos of a fixed-point phase (PHI_ONE units per half-turn): the low 23 bits are the phase mod one turn,
 // exactly; the SFU (MUFU.SIN / MUFU.COS) has abs error 2^-21.4 on [-pi, pi].
+// int -> float for |v| < 2^22 without the conversion (XU) pipe: 1.5 * 2^23 + v is exact in FP32
+__device__ __forceinline__ float small_int_to_float(int32_t v) {
+  return __int_as_float(v + 0x4B400000) - 12582912.f;
+}
 __device__ __forceinline__ void sincos_fixed(int32_t t, float* s, float* c) {
-  const float x = (float)((t << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
+  const float x = small_int_to_float((t << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(x));
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(x));
 }
@@ -784,7 +788,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           t[j] += __float2int_rn(d[j] * PHI_ONE);                         // atmosphere + DM, fixed point, unreduced
-          ph[j] = (float)((t[j] << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
+          ph[j] = small_int_to_float((t[j] << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
         }
         if (!(p.dbg & 1)) {
           // Full-sector stores: a lane's 16 pixels are 64 contiguous bytes, but a thread stores at most 16 per
@@ -818,7 +822,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
             float c0, s0;
             asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(ph[j]));
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(ph[j]));
-            if (!((mask >> j) & 1u)) { c0 = 0.f; s0 = 0.f; }
+            if (mask != 0xFFFFu && !((mask >> j) & 1u)) { c0 = 0.f; s0 = 0.f; }
 #pragma unroll
             for (int v = 0; v < NOBS; ++v) {
               const float2 m = m1o_s[v * Np + y0 + j];
@@ -836,7 +840,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
             const int32_t ts = (int32_t)(((long long)t[j] * (long long)p.sci_ratio_q32) >> 32);
             float c0, s0;
             sincos_fixed(ts, &s0, &c0);
-            if ((mask >> j) & 1u) { sre += c0; sim += s0; }
+            if (mask == 0xFFFFu || ((mask >> j) & 1u)) { sre += c0; sim += s0; }
           }
         }
       }

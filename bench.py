@@ -341,8 +341,8 @@ def main():
                                  'written and re-read (126 MB L2)') if precision == 'tensor' else
                                 f'inputs larger than L2: {B * Np * Np * 8 / 1e6:.0f} MB of screens read per step',
                    'timing': 'CUDA events on the launch stream, max over ranks'},
-        'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': B * K * 4,
-                'd2h_bytes_per_step': B * (n2 * 2 + 16), 'ms_per_step': ms_e2e / args.steps},
+        'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': world * B * K * 4,
+                'd2h_bytes_per_step': world * B * (n2 * 2 + 16), 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
         'roofline': roofline,
         'cpu_baseline': cpu,
