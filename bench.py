@@ -41,6 +41,10 @@ WORKLOADS = {
     'dynamic_v20': dict(atm_type='dynamic', atm_vel=20, atm_fried=0.10, act_type='num_actuators', act_dim=64,
                         obs_dim=2, rew_type='strehl_ratio', timesteps_per_episode=20,
                         flat_mirror_start_per_episode=True),
+    # BASELINE.json configs[3]: the Shack-Hartmann integrator drives the mirror (SH_step + step every step)
+    'dynamic_v20_sh': dict(atm_type='dynamic', atm_vel=20, atm_fried=0.10, act_type='num_actuators', act_dim=64,
+                           obs_dim=2, rew_type='strehl_ratio', timesteps_per_episode=20,
+                           flat_mirror_start_per_episode=True, SH_operation=True),
 }
 
 MFT_FLOP_PER_ENV = lambda Np, Nf: 8.0 * (Nf * Np * Np + Nf * Np * Nf)   # 90.44 MFLOP @ 240/128
@@ -214,16 +218,21 @@ def main():
 
     state = {'t': 0}
 
+    sh_loop = bool(w.get('SH_operation'))
+
     def step_device(i):
         if state['t'] % T == 0:
             env.reset()
-        _, _, done, _, _ = env.step(act_dev[i % pool])
+        a = env.SH_step()[0] if sh_loop else act_dev[i % pool]
+        _, _, done, _, _ = env.step(a)
         state['t'] += 1
 
     def step_e2e(i):
         if state['t'] % T == 0:
             env.reset()
         a = act_host[i % pool].to(dev, non_blocking=True)
+        if sh_loop:
+            a = env.SH_step()[0]
         obs, rew, done, _, info = env.step(a)
         obs_h.copy_(obs, non_blocking=True)
         rew_h.copy_(rew, non_blocking=True)
