@@ -11,14 +11,14 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libaogym.so')
+LIB_PATH = os.environ.get('AOG_LIB') or os.path.join(_HERE, 'libaogym.so')   # AOG_LIB: tuning builds only
 
 ABI_VERSION = 1
 
 ATM = {'quasi_static': 0, 'semi_dynamic': 1, 'dynamic': 2}
 REW = {'strehl_ratio': 0, 'smf_ssim': 1}
 DTYPE_F32, DTYPE_F64 = 0, 1
-PRECISION = {'f64': 0, 'tensor': 1}
+PRECISION = {'f64': 0, 'tensor': 1, 'fused': 2}
 
 TABLE_IDS = {
     'aperture': 0, 'dm_modes': 1, 'dm_gram': 2, 'mft_fib_1': 3, 'mft_fib_2': 4, 'mft_obs_1': 5,

@@ -70,7 +70,7 @@ int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long
     k_ar_scatter<<<g3, 128, 0, st>>>(env->screens, env->arNew, env->P, Np, e0, phys, flipped);
     AOG_LAUNCH_CHECK();
   }
-  if (c.precision == AOG_PRECISION_TENSOR) {
+  if (c.precision != AOG_PRECISION_F64) {
     int rc = aog_tensor_column_updated(env, phys, st);
     if (rc) return rc;
   }
@@ -153,7 +153,7 @@ int optics_chunk_f64(aog_env* env, int e0, int nB, bool flat_dm, bool with_rewar
 
 int optics_all(aog_env* env, bool flat_dm, bool with_reward, const aog_outputs& out, cudaStream_t st) {
   const int B = env->cfg.num_envs;
-  if (env->cfg.precision == AOG_PRECISION_TENSOR) return aog_tensor_optics(env, flat_dm, with_reward, out, st);
+  if (env->cfg.precision != AOG_PRECISION_F64) return aog_tensor_optics(env, flat_dm, with_reward, out, st);
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     int rc = optics_chunk_f64(env, e0, std::min(env->chunk, B - e0), flat_dm, with_reward, out, st);
     if (rc) return rc;
@@ -307,7 +307,7 @@ int aog_create(const aog_config* cfg, aog_env** out) {
     A(dev_alloc(env, &env->arNew, ch * (size_t)Np));
   }
   A(alloc_host_outputs(env));
-  if (c.precision == AOG_PRECISION_TENSOR) A(aog_tensor_create(env));
+  if (c.precision != AOG_PRECISION_F64) A(aog_tensor_create(env));
 #undef A
   AOG_CUDA(cudaStreamCreate(&env->own_stream));   // blocking: ordered with the default stream
   AOG_CUDA(cudaEventCreate(&env->ev0));
@@ -405,7 +405,7 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
     k_transpose_z<<<cdiv((int)(Np * N2), 256), 256>>>(env->t_scrW2, env->t_scrW2T, (int)Np, (int)N2);
     AOG_LAUNCH_CHECK();
   }
-  if (c.precision == AOG_PRECISION_TENSOR) {
+  if (c.precision != AOG_PRECISION_F64) {
     int rc = aog_tensor_table_updated(env, which, host);
     if (rc) return rc;
   }
@@ -440,7 +440,7 @@ int aog_set_screens(aog_env* env, const void* src, int dtype, int src_on_device,
   } else {
     AOG_FAIL(AOG_ERR_INVALID, "dtype");
   }
-  if (c.precision == AOG_PRECISION_TENSOR) return aog_tensor_screens_updated(env);
+  if (c.precision != AOG_PRECISION_F64) return aog_tensor_screens_updated(env);
   return AOG_OK;
 }
 
@@ -504,7 +504,7 @@ int aog_generate_screens(aog_env* env, void* stream) {
     AOG_LAUNCH_CHECK();
   }
   env->cnt.column_origin = 0;
-  if (c.precision == AOG_PRECISION_TENSOR) return aog_tensor_screens_updated(env);
+  if (c.precision != AOG_PRECISION_F64) return aog_tensor_screens_updated(env);
   return AOG_OK;
 }
 
@@ -785,7 +785,7 @@ int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size
     return AOG_OK;
   }
   if (which == AOG_FIELD_TC_PUPIL || which == AOG_FIELD_TC_STAGE1) {
-    if (c.precision != AOG_PRECISION_TENSOR) AOG_FAIL(AOG_ERR_INVALID, "tensor-path field on an FP64 handle");
+    if (c.precision != AOG_PRECISION_TENSOR) AOG_FAIL(AOG_ERR_INVALID, "tensor-path field: the handle has no matrix-Fourier-transform GEMM stages");
     return aog_tensor_get_field(env, which, env_index % env->chunk, host_out, count);
   }
   // optical fields: recompute the FP64 chain for that one env from the current state
@@ -843,7 +843,7 @@ int aog_set_timing(aog_env* env, int enabled) {
 
 int aog_last_kernel_ms(aog_env* env, double* field_ms, double* stage1_ms, double* stage2_ms) {
   if (!env) return AOG_ERR_INVALID;
-  if (!env->ev_valid || env->cfg.precision != AOG_PRECISION_TENSOR) AOG_FAIL(AOG_ERR_STATE, "no timed tensor-path step yet");
+  if (!env->ev_valid || env->cfg.precision == AOG_PRECISION_F64) AOG_FAIL(AOG_ERR_STATE, "no timed tensor-path step yet");
   AOG_CUDA(cudaEventSynchronize(env->ev1));
   float a = 0.f, b = 0.f, c = 0.f;
   AOG_CUDA(cudaEventElapsedTime(&a, env->evf, env->ev0));

@@ -279,7 +279,9 @@ struct FinalizeArgs {
   const double2* strehl_part; int strehl_blocks;
   int Np, n, J, rew_type, has_thr, compute_reward;
   int r4_parts;        // partial sums per contraction index in R4
-  int coef_is_raw;     // 1: coef holds unscaled (re, im) projection sums; 2: coef4 holds [re|im][2 partials]; x coef_scale
+  int coef_is_raw;     // 1: coef holds unscaled (re, im) projection sums; 2: coef4 holds [re|im][2 partials];
+                       // 3: fib_part holds [fib_slots][fib_stride] partial sums per env;  all x coef_scale
+  const double2* fib_part; int fib_slots, fib_stride;
   double2 coef_scale;
   int transpose_out;   // R / table hold the transposed contraction: result (a, b) is obs pixel (v = b, u = a)
   double thr, obs_weight, strehl_scale, ssim_peak;
@@ -356,6 +358,10 @@ static __global__ void k_finalize(FinalizeArgs a) {
     if (a.coef_is_raw == 2) {
       const double* c4 = a.coef4 + ((size_t)b * a.J + j) * 4;
       cj = make_double2(c4[0] + c4[1], c4[2] + c4[3]);
+    } else if (a.coef_is_raw == 3) {
+      cj = make_double2(0.0, 0.0);
+      const double2* fp = a.fib_part + (size_t)b * a.fib_slots * a.fib_stride + j;
+      for (int i = 0; i < a.fib_slots; ++i) { cj.x += fp[i * a.fib_stride].x; cj.y += fp[i * a.fib_stride].y; }
     } else {
       cj = a.coef[(size_t)b * a.J + j];
     }

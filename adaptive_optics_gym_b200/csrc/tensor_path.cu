@@ -67,6 +67,14 @@ struct TensorState {
   int act_rows = 128;
   double2* m2oT = nullptr;                            // [n][Np] transposed obs table
   int* err_flag = nullptr;                            // device flag set by a timed-out barrier wait
+  // AOG_PRECISION_FUSED: fibre modes propagated back to the pupil, G_j = M1^T (mode_j w) M2^T / max|G| (FP32),
+  // [Np x][Np / 16][16 y][J]: the 16-pixel chunk of a column is one contiguous 128 J-byte run for the bulk prefetch
+  bool fused = false;
+  float2* gfib = nullptr;
+  double gfib_scale = 0.0;
+  double2* fib_part = nullptr;                        // [chunk][FK_SLOTS][J] partial projection sums
+  bool have_gfib = false;
+  std::vector<double> h_m1, h_m2, h_lp;               // host copies of the tables G is built from
   CUtensorMap tmA1_hi, tmA1_lo, tmB2_hi, tmB2_lo;
   CUtensorMap tmT128_hi, tmT128_lo;
   CUtensorMap tmTout_hi, tmTout_lo;                   // stage-1 epilogue stores: 128 rows x 16 columns, SWIZZLE_32B                   // stage-1 product, one env (128 rows) per box
@@ -515,7 +523,10 @@ constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
 constexpr int FK_SLOTS = 16;                            // Strehl partial slots per env (>= CTAs touching an env block)
 constexpr int FK_MIN_ITEMS = 16;                        // items per CTA at least (bounds the slots)
 constexpr int FK_PF_TILE = 32 * 16 * 4;                 // 2 KB: 32 envs x 16 pixels of phase (one bulk copy)
-constexpr int FK_PF_BYTES = FK_EPI_WARPS * 2 * FK_PF_TILE;   // per warp: 2 buffers
+constexpr int FK_JT = 3;                                // fibre modes of the fused kernel (LP01 + 2 x LP11, AO_env.py:393)
+constexpr int FK_G_TILE = 16 * FK_JT * 8;               // 384 B: back-projected fibre modes of 16 pixels
+constexpr int FK_PF_SLOT = FK_PF_TILE + 512;            // phase tile + fibre-mode chunk (fused kernel)
+constexpr int FK_PF_BYTES = FK_EPI_WARPS * 2 * FK_PF_SLOT;   // per warp: 2 buffers
 constexpr int FK_AUX_BAR = 256;
 
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -563,10 +574,12 @@ struct FieldParams {
   float* phi;            // [env][Np / 16][Np x][16 y] total phase out, radians in [-pi, pi)
   float2* R4;            // [env][Np x][FK_PARTS][n] obs-arm column partial sums out
   double2* strehl_part;  // [env][FK_SLOTS]
+  const float2* gfib;    // fused kernel: [Np x][Np / 16][16 y][FK_JT] back-projected fibre modes
+  double2* fib_part;     // fused kernel: [env][FK_SLOTS][FK_JT] partial projection sums out
   int* err_flag;
 };
 
-template <bool STREHL, int NOBS>
+template <bool STREHL, int NOBS, bool FUSED>
 __global__ void __launch_bounds__(FK_THREADS, 1)
 k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constant__ CUtensorMap tmAct_lo,
               const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
@@ -584,8 +597,9 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint64_t* pfbar = tmem_empty + 2;              // [FK_EPI_WARPS][2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pfbar + 2 * FK_EPI_WARPS);
-  double2* sred = reinterpret_cast<double2*>(aux + FK_AUX_BAR);          // [FK_PARTS][128 envs]
-  float2* m1o_s = reinterpret_cast<float2*>(sred + FK_PARTS * 128);      // [n][Np]
+  constexpr int NRED = FUSED ? 1 + FK_JT : 1;                            // Strehl sum + fibre projections
+  double2* sred = reinterpret_cast<double2*>(aux + FK_AUX_BAR);          // [NRED][FK_PARTS][128 envs]
+  float2* m1o_s = reinterpret_cast<float2*>(sred + NRED * FK_PARTS * 128);   // [n][Np]
   uint16_t* apmask_s = reinterpret_cast<uint16_t*>(m1o_s + NOBS * Np);  // [Np][Np / 16]
   uint8_t* run_s = reinterpret_cast<uint8_t*>(apmask_s + Np * (Np / 16));   // [Np][2]: first lit chunk, lit count
 
@@ -688,13 +702,16 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
     const int row = lg * 32 + lane;           // env within the block
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     double st_re = 0.0, st_im = 0.0;
+    double fb_re[FK_JT], fb_im[FK_JT];                 // fused kernel: fibre projection sums of my env
+#pragma unroll
+    for (int j = 0; j < FK_JT; ++j) fb_re[j] = fb_im[j] = 0.0;
     int cur_eb = -1;
     int it = 0;
 
     // Phase prefetch: the warp's 32 envs x 16 pixels of atmospheric phase are one contiguous, pre-swizzled
     // 2 KB tile: a single cp.async.bulk one chunk ahead of the arithmetic.
-    const uint32_t pf_warp = smem_u32(pf + ew * (2 * FK_PF_TILE));
-    const uint8_t* pf_warp_ptr = pf + ew * (2 * FK_PF_TILE);
+    const uint32_t pf_warp = smem_u32(pf + ew * (2 * FK_PF_SLOT));
+    const uint8_t* pf_warp_ptr = pf + ew * (2 * FK_PF_SLOT);
     uint64_t* pbar = pfbar + 2 * ew;
     uint32_t pphase0 = 0, pphase1 = 0;
     int buf = 0;
@@ -717,9 +734,14 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
         const size_t eb32 = (size_t)(p.env0 + eb2 * 128 + lg * 32) >> 5;
         const int32_t* src = p.hwt + ((eb32 * Np + xp2) * (Np / 16) + n_ci) * (32 * 16);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&pbar[b], FK_PF_TILE);
+        mbar_expect_tx(&pbar[b], FUSED ? FK_PF_TILE + FK_G_TILE : FK_PF_TILE);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(pf_warp + b * FK_PF_TILE), "l"(src), "r"((uint32_t)FK_PF_TILE), "r"(smem_u32(&pbar[b])) : "memory");
+                     ::"r"(pf_warp + b * FK_PF_SLOT), "l"(src), "r"((uint32_t)FK_PF_TILE), "r"(smem_u32(&pbar[b])) : "memory");
+        if (FUSED) {
+          const float2* gsrc = p.gfib + ((size_t)x2 * (Np / 16) + n_ci) * (16 * FK_JT);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(pf_warp + b * FK_PF_SLOT + FK_PF_TILE), "l"(gsrc), "r"((uint32_t)FK_G_TILE), "r"(smem_u32(&pbar[b])) : "memory");
+        }
       }
     };
     bool n_ok = next_lit();
@@ -727,24 +749,43 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
 
     auto flush_strehl = [&](int eb) {
       // combine the thirds of every env, one partial per (env, CTA slot)
-      sred[q * 128 + row] = make_double2(st_re, st_im);
+      if (STREHL) sred[q * 128 + row] = make_double2(st_re, st_im);
+      if (FUSED) {
+#pragma unroll
+        for (int j = 0; j < FK_JT; ++j) sred[((1 + j) * FK_PARTS + q) * 128 + row] = make_double2(fb_re[j], fb_im[j]);
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(FK_EPI_WARPS * 32) : "memory");
       if (q == 0) {
         const int env = eb * 128 + row;
         if (env < p.num_envs) {
-          double2 a = sred[row];
-          for (int k = 1; k < FK_PARTS; ++k) { a.x += sred[k * 128 + row].x; a.y += sred[k * 128 + row].y; }
           const int slot = blockIdx.x - (eb * Np) / p.items_per_cta;
-          p.strehl_part[(size_t)env * FK_SLOTS + slot] = a;
+          if (STREHL) {
+            double2 a = sred[row];
+            for (int k = 1; k < FK_PARTS; ++k) { a.x += sred[k * 128 + row].x; a.y += sred[k * 128 + row].y; }
+            p.strehl_part[(size_t)env * FK_SLOTS + slot] = a;
+          }
+          if (FUSED) {
+#pragma unroll
+            for (int j = 0; j < FK_JT; ++j) {
+              double2 a = sred[(1 + j) * FK_PARTS * 128 + row];
+              for (int k = 1; k < FK_PARTS; ++k) {
+                a.x += sred[((1 + j) * FK_PARTS + k) * 128 + row].x;
+                a.y += sred[((1 + j) * FK_PARTS + k) * 128 + row].y;
+              }
+              p.fib_part[((size_t)env * FK_SLOTS + slot) * FK_JT + j] = a;
+            }
+          }
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(FK_EPI_WARPS * 32) : "memory");
       st_re = st_im = 0.0;
+#pragma unroll
+      for (int j = 0; j < FK_JT; ++j) fb_re[j] = fb_im[j] = 0.0;
     };
 
     for (int item = item_lo; item < item_hi; ++item, ++it) {
       const int eb = item / Np, x = item - eb * Np;
-      if (STREHL && eb != cur_eb) {
+      if ((STREHL || FUSED) && eb != cur_eb) {
         if (cur_eb >= 0) flush_strehl(cur_eb);
         cur_eb = eb;
       }
@@ -775,7 +816,8 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
           else         { mbar_wait(&pbar[1], pphase1, p.err_flag, 16); pphase1 ^= 1; }
         }
         buf ^= 1;
-        const uint8_t* tile = pf_warp_ptr + cb * FK_PF_TILE + lane * 64;
+        const uint8_t* tile = pf_warp_ptr + cb * FK_PF_SLOT + lane * 64;
+        const float2* gt = reinterpret_cast<const float2*>(pf_warp_ptr + cb * FK_PF_SLOT + FK_PF_TILE);   // [16 y][FK_JT]
         const int sw = (lane >> 1) & 3;                                   // pieces were stored at j ^ ((env >> 1) & 3)
         int32_t t[16];
 #pragma unroll
@@ -790,7 +832,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
           t[j] += __float2int_rn(d[j] * PHI_ONE);                         // atmosphere + DM, fixed point, unreduced
           ph[j] = small_int_to_float((t[j] << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
         }
-        if (!(p.dbg & 1)) {
+        if (!FUSED && !(p.dbg & 1)) {
           // Full-sector stores: a lane's 16 pixels are 64 contiguous bytes, but a thread stores at most 16 per
           // instruction.  Lane pairs swap halves so that each store instruction writes whole 32-byte sectors
           // (lanes 2i, 2i+1 -> the two halves of a sector of env 2i, then of env 2i+1).
@@ -817,6 +859,9 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
           float ore[NOBS], oim[NOBS];
 #pragma unroll
           for (int v = 0; v < NOBS; ++v) ore[v] = oim[v] = 0.f;
+          float fre[FK_JT], fim[FK_JT];               // fused kernel: fibre projections, same 16-pixel FP32 partials
+#pragma unroll
+          for (int k = 0; k < FK_JT; ++k) fre[k] = fim[k] = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float c0, s0;
@@ -829,9 +874,22 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
               ore[v] = fmaf(m.x, c0, fmaf(-m.y, s0, ore[v]));
               oim[v] = fmaf(m.x, s0, fmaf(m.y, c0, oim[v]));
             }
+            if (FUSED) {
+              // c_j = sum_pixels E . G_j (AO_env.py:471 through the back-projected mode)
+#pragma unroll
+              for (int k = 0; k < FK_JT; ++k) {
+                const float2 g = gt[j * FK_JT + k];
+                fre[k] = fmaf(g.x, c0, fmaf(-g.y, s0, fre[k]));
+                fim[k] = fmaf(g.x, s0, fmaf(g.y, c0, fim[k]));
+              }
+            }
           }
 #pragma unroll
           for (int v = 0; v < NOBS; ++v) { obs_re[v] += (double)ore[v]; obs_im[v] += (double)oim[v]; }
+          if (FUSED) {
+#pragma unroll
+            for (int k = 0; k < FK_JT; ++k) { fb_re[k] += (double)fre[k]; fb_im[k] += (double)fim[k]; }
+          }
         }
         if (STREHL) {
 #pragma unroll
@@ -854,7 +912,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       }
       if (STREHL) { st_re += (double)sre; st_im += (double)sim; }
     }
-    if (STREHL && cur_eb >= 0) flush_strehl(cur_eb);
+    if ((STREHL || FUSED) && cur_eb >= 0) flush_strehl(cur_eb);
   }
   tc_fence_before();
   __syncthreads();
@@ -883,10 +941,19 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
 //               K blocks (one B slot = 2 x 16 KB, ring of 2) so the fence + barrier traffic is paid once
 //               per 32 pixels; `b_full` collects one arrival per field warp of BOTH CTAs
 // Registers are re-partitioned with setmaxnreg: the epilogue warps hold 128 accumulator columns each.
-constexpr int F1_A_SLOTS = 4;
-constexpr int F1_B_SLOTS = 2;                         // each holds a PAIR of K blocks
+#ifndef AOG_F1_A_SLOTS        // ring depths: overridable for tuning builds (make EXTRA=-DAOG_F1_A_SLOTS=...)
+#define AOG_F1_A_SLOTS 4
+#endif
+#ifndef AOG_F1_B_SLOTS
+#define AOG_F1_B_SLOTS 2
+#endif
+#ifndef AOG_F1_PHI_SLOTS
+#define AOG_F1_PHI_SLOTS 6
+#endif
+constexpr int F1_A_SLOTS = AOG_F1_A_SLOTS;
+constexpr int F1_B_SLOTS = AOG_F1_B_SLOTS;            // each holds a PAIR of K blocks
 constexpr int F1_SLOT_BYTES = 2 * A_TILE;             // 16 KB: [hi 8 KB][lo 8 KB] of one K block
-constexpr int F1_PHI_SLOTS = 6;
+constexpr int F1_PHI_SLOTS = AOG_F1_PHI_SLOTS;
 constexpr int F1_PHI_TILE = 8192;                     // 120 rows x 64 B in an 8 KB slot
 constexpr int F1_THREADS = 512;
 constexpr int F1_SMEM_BYTES = (F1_A_SLOTS + 2 * F1_B_SLOTS) * F1_SLOT_BYTES + F1_PHI_SLOTS * F1_PHI_TILE + M2_EPI_BYTES +
@@ -1314,26 +1381,35 @@ int aog_tensor_create(aog_env* env) {
                                   "use precision='f64' for other grids");
   TensorState* ts = new TensorState();
   env->tensor_state = ts;
+  ts->fused = c.precision == AOG_PRECISION_FUSED;
+  if (ts->fused && c.num_lp_modes > FK_JT)
+    AOG_FAIL(AOG_ERR_UNSUPPORTED, "fused precision path holds at most 3 guided fibre modes; use precision='tensor'");
   cudaDeviceProp prop;
   AOG_CUDA(cudaGetDeviceProperties(&prop, c.device));
   ts->num_sms = prop.multiProcessorCount;
   const size_t ch = env->chunk, B = c.num_envs, P = env->P;
   int rc;
 #define A(expr) if ((rc = (expr))) return rc
-  A(talloc(env, &ts->A1_hi, (size_t)256 * TC_K));
-  A(talloc(env, &ts->A1_lo, (size_t)256 * TC_K));
-  A(talloc(env, &ts->B2_hi, (size_t)256 * TC_K));
-  A(talloc(env, &ts->B2_lo, (size_t)256 * TC_K));
-  A(talloc(env, &ts->phi, ch * P));
-  AOG_CUDA(cudaMemset(ts->phi, 0, ch * P * sizeof(float)));   // out-of-aperture chunks are never written (nor used)
-  // stage-2 reads env pairs: keep one spare env of rows so the last odd pair stays in bounds
-  A(talloc(env, &ts->T_hi, (ch + 1) * 128 * TC_K));
-  A(talloc(env, &ts->T_lo, (ch + 1) * 128 * TC_K));
-  AOG_CUDA(cudaMemset(ts->T_hi, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
-  AOG_CUDA(cudaMemset(ts->T_lo, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
-  A(talloc(env, &ts->lpw, (size_t)c.num_lp_modes * env->NF2));
-  A(talloc(env, &ts->lpwr, (size_t)c.num_lp_modes * env->NF2));
-  A(talloc(env, &ts->coef4, ch * (size_t)c.num_lp_modes * 4));
+  if (!ts->fused) {
+    A(talloc(env, &ts->A1_hi, (size_t)256 * TC_K));
+    A(talloc(env, &ts->A1_lo, (size_t)256 * TC_K));
+    A(talloc(env, &ts->B2_hi, (size_t)256 * TC_K));
+    A(talloc(env, &ts->B2_lo, (size_t)256 * TC_K));
+    A(talloc(env, &ts->phi, ch * P));
+    AOG_CUDA(cudaMemset(ts->phi, 0, ch * P * sizeof(float)));   // out-of-aperture chunks are never written (nor used)
+    // stage-2 reads env pairs: keep one spare env of rows so the last odd pair stays in bounds
+    A(talloc(env, &ts->T_hi, (ch + 1) * 128 * TC_K));
+    A(talloc(env, &ts->T_lo, (ch + 1) * 128 * TC_K));
+    AOG_CUDA(cudaMemset(ts->T_hi, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
+    AOG_CUDA(cudaMemset(ts->T_lo, 0, (ch + 1) * 128 * TC_K * sizeof(__half)));
+    A(talloc(env, &ts->lpw, (size_t)c.num_lp_modes * env->NF2));
+    A(talloc(env, &ts->lpwr, (size_t)c.num_lp_modes * env->NF2));
+    A(talloc(env, &ts->coef4, ch * (size_t)c.num_lp_modes * 4));
+  } else {
+    A(talloc(env, &ts->gfib, (size_t)P * FK_JT));
+    AOG_CUDA(cudaMemset(ts->gfib, 0, (size_t)P * FK_JT * sizeof(float2)));
+    A(talloc(env, &ts->fib_part, ch * (size_t)FK_SLOTS * FK_JT));
+  }
   if (c.obs_dim > 8) AOG_FAIL(AOG_ERR_UNSUPPORTED, "tensor precision path supports obs_dim <= 8");
   ts->kpad = ((c.num_modes + 63) / 64) * 64;
   ts->act_rows = (int)((ch + 127) / 128) * 128;
@@ -1352,15 +1428,17 @@ int aog_tensor_create(aog_env* env) {
   A(talloc(env, &ts->m2oT, (size_t)c.obs_dim * TC_NP));
   A(talloc(env, &ts->err_flag, 1));
   AOG_CUDA(cudaMemset(ts->err_flag, 0, sizeof(int)));
-  A(make_map(env, &ts->tmA1_hi, ts->A1_hi, 256, 128));
-  A(make_map(env, &ts->tmA1_lo, ts->A1_lo, 256, 128));
-  A(make_map_32(env, &ts->tmPhi, ts->phi, ch * (TC_NP / 16) * TC_NP, TC_NP / 2, 16));   // box = 120 columns x 16 y, contiguous
-  A(make_map(env, &ts->tmT128_hi, ts->T_hi, (ch + 1) * 128, 128));
-  A(make_map(env, &ts->tmT128_lo, ts->T_lo, (ch + 1) * 128, 128));
-  A(make_map(env, &ts->tmTout_hi, ts->T_hi, (ch + 1) * 128, 128, TC_K, 16));
-  A(make_map(env, &ts->tmTout_lo, ts->T_lo, (ch + 1) * 128, 128, TC_K, 16));
-  A(make_map(env, &ts->tmB2_hi, ts->B2_hi, 256, 128));
-  A(make_map(env, &ts->tmB2_lo, ts->B2_lo, 256, 128));
+  if (!ts->fused) {
+    A(make_map(env, &ts->tmA1_hi, ts->A1_hi, 256, 128));
+    A(make_map(env, &ts->tmA1_lo, ts->A1_lo, 256, 128));
+    A(make_map_32(env, &ts->tmPhi, ts->phi, ch * (TC_NP / 16) * TC_NP, TC_NP / 2, 16));   // box = 120 columns x 16 y, contiguous
+    A(make_map(env, &ts->tmT128_hi, ts->T_hi, (ch + 1) * 128, 128));
+    A(make_map(env, &ts->tmT128_lo, ts->T_lo, (ch + 1) * 128, 128));
+    A(make_map(env, &ts->tmTout_hi, ts->T_hi, (ch + 1) * 128, 128, TC_K, 16));
+    A(make_map(env, &ts->tmTout_lo, ts->T_lo, (ch + 1) * 128, 128, TC_K, 16));
+    A(make_map(env, &ts->tmB2_hi, ts->B2_hi, 256, 128));
+    A(make_map(env, &ts->tmB2_lo, ts->B2_lo, 256, 128));
+  }
   A(make_map(env, &ts->tmAct_hi, ts->act_hi, ts->act_rows, 128, ts->kpad, 64));
   A(make_map(env, &ts->tmAct_lo, ts->act_lo, ts->act_rows, 128, ts->kpad, 64));
   A(make_map(env, &ts->tmModes_hi, ts->modesK_hi, P, TC_NP, ts->kpad, 64));
@@ -1376,17 +1454,75 @@ void aog_tensor_destroy(aog_env* env) {
   if (!ts) return;
   void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->phi, ts->T_hi, ts->T_lo, ts->lpw, ts->lpwr, ts->coef4,
                   ts->hwt, ts->modesK_hi, ts->modesK_lo, ts->act_hi, ts->act_lo, ts->apmask, ts->m1o32, ts->R4,
-                  ts->m2oT, ts->err_flag};
+                  ts->m2oT, ts->err_flag, ts->gfib, ts->fib_part};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ts;
   env->tensor_state = nullptr;
 }
 
+namespace {
+// Fibre modes propagated back to the pupil plane (FP64 on the host):
+//   c_j = norm sum_{v,u} (mode_j w)[v][u] F[v][u],   F = M1 . E . M2   (AO_env.py:138, :471)
+//       = norm sum_{y,x} E[y][x] G_j[y][x],          G_j = M1^T (mode_j w) M2^T
+// so the coupling coefficients are J inner products over the pupil and the focal plane is never formed.
+int build_backprojected_modes(aog_env* env, TensorState* ts) {
+  const int Np = TC_NP, Nf = TC_NF, J = env->cfg.num_lp_modes;
+  const std::vector<double>&m1 = ts->h_m1, &m2 = ts->h_m2, &lp = ts->h_lp;
+  std::vector<double> H((size_t)2 * Nf * Np), G((size_t)2 * J * Np * Np);
+  double gmax = 0.0;
+  for (int j = 0; j < J; ++j) {
+    for (int v = 0; v < Nf; ++v)                       // H[v][x] = sum_u lp[j][v][u] M2[x][u]
+      for (int x = 0; x < Np; ++x) {
+        double re = 0.0, im = 0.0;
+        const double* w = &lp[((size_t)j * Nf + v) * Nf];
+        const double* b = &m2[(size_t)2 * x * Nf];
+        for (int u = 0; u < Nf; ++u) { re += w[u] * b[2 * u]; im += w[u] * b[2 * u + 1]; }
+        H[2 * ((size_t)v * Np + x)] = re;
+        H[2 * ((size_t)v * Np + x) + 1] = im;
+      }
+    for (int y = 0; y < Np; ++y)                       // G[y][x] = sum_v M1[v][y] H[v][x]
+      for (int x = 0; x < Np; ++x) {
+        double re = 0.0, im = 0.0;
+        for (int v = 0; v < Nf; ++v) {
+          const double ar = m1[2 * ((size_t)v * Np + y)], ai = m1[2 * ((size_t)v * Np + y) + 1];
+          const double hr = H[2 * ((size_t)v * Np + x)], hi = H[2 * ((size_t)v * Np + x) + 1];
+          re += ar * hr - ai * hi;
+          im += ar * hi + ai * hr;
+        }
+        G[2 * (((size_t)j * Np + y) * Np + x)] = re;
+        G[2 * (((size_t)j * Np + y) * Np + x) + 1] = im;
+        gmax = std::max(gmax, std::max(std::fabs(re), std::fabs(im)));
+      }
+  }
+  if (gmax == 0.0) gmax = 1.0;
+  ts->gfib_scale = gmax;
+  std::vector<float2> g((size_t)Np * Np * FK_JT, make_float2(0.f, 0.f));
+  for (int j = 0; j < J; ++j)
+    for (int y = 0; y < Np; ++y)
+      for (int x = 0; x < Np; ++x) {
+        const size_t src = 2 * (((size_t)j * Np + y) * Np + x);
+        g[(((size_t)x * (Np / 16) + y / 16) * 16 + y % 16) * FK_JT + j] =
+            make_float2((float)(G[src] / gmax), (float)(G[src + 1] / gmax));
+      }
+  AOG_CUDA(cudaMemcpy(ts->gfib, g.data(), g.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  ts->have_gfib = true;
+  return AOG_OK;
+}
+}  // namespace
+
 int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
   TensorState* ts = TS(env);
   const aog_config& c = env->cfg;
   const int Np = TC_NP, Nf = TC_NF;
+  if (ts->fused && (which == AOG_TABLE_MFT_FIB_1 || which == AOG_TABLE_MFT_FIB_2 || which == AOG_TABLE_LP_MODES_W)) {
+    const double* m = static_cast<const double*>(host);
+    if (which == AOG_TABLE_MFT_FIB_1) { ts->h_m1.assign(m, m + (size_t)2 * Nf * Np); ts->have_m1 = true; }
+    if (which == AOG_TABLE_MFT_FIB_2) { ts->h_m2.assign(m, m + (size_t)2 * Np * Nf); ts->have_m2 = true; }
+    if (which == AOG_TABLE_LP_MODES_W) { ts->h_lp.assign(m, m + (size_t)c.num_lp_modes * env->NF2); ts->have_lp = true; }
+    if (ts->have_m1 && ts->have_m2 && ts->have_lp) return build_backprojected_modes(env, ts);
+    return AOG_OK;
+  }
   if (which == AOG_TABLE_MFT_FIB_1) {
     // M1 [Nf][Np] complex, every entry of modulus w (the pupil grid weight): factor it out.
     const double* m = static_cast<const double*>(host);
@@ -1516,7 +1652,7 @@ int aog_tensor_column_updated(aog_env* env, int phys_col, cudaStream_t st) {
 //   which = AOG_FIELD_TC_STAGE1: stage-1 product [v][x] complex (unit-modulus twiddles)
 int aog_tensor_get_field(aog_env* env, int which, int env_in_chunk, double* host_out, size_t count) {
   TensorState* ts = TS(env);
-  if (!ts) AOG_FAIL(AOG_ERR_STATE, "handle has no tensor path");
+  if (!ts || ts->fused) AOG_FAIL(AOG_ERR_STATE, "handle has no matrix-Fourier-transform GEMM stages");
   if (env_in_chunk < 0 || env_in_chunk >= env->chunk) AOG_FAIL(AOG_ERR_INVALID, "env index outside the chunk");
   if (which == AOG_FIELD_TC_PUPIL) {          // phi [y / 16][x][16] radians -> out [y][x] = aperture exp(i phi)
     if (count != (size_t)2 * TC_NP * TC_NP) AOG_FAIL(AOG_ERR_INVALID, "count");
@@ -1557,30 +1693,31 @@ int aog_tensor_check(aog_env* env) {
 }
 
 namespace {
-template <bool STREHL, int NOBS>
+template <bool STREHL, int NOBS, bool FUSED>
 int launch_phase(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
-  const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES + 1024 + FK_AUX_BAR + FK_PARTS * 128 * (int)sizeof(double2) +
+  const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES + 1024 + FK_AUX_BAR +
+                   (FUSED ? 1 + FK_JT : 1) * FK_PARTS * 128 * (int)sizeof(double2) +
                    NOBS * TC_NP * (int)sizeof(float2) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
   static bool configured = false;
   if (!configured) {
-    AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_dm_phase_tc<STREHL, NOBS><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
+  k_dm_phase_tc<STREHL, NOBS, FUSED><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
   AOG_LAUNCH_CHECK();
   return AOG_OK;
 }
-template <bool STREHL>
+template <bool STREHL, bool FUSED>
 int launch_phase_n(aog_env* env, TensorState* ts, const FieldParams& p, int n, int grid, cudaStream_t st) {
   switch (n) {
-    case 1: return launch_phase<STREHL, 1>(env, ts, p, grid, st);
-    case 2: return launch_phase<STREHL, 2>(env, ts, p, grid, st);
-    case 3: return launch_phase<STREHL, 3>(env, ts, p, grid, st);
-    case 4: return launch_phase<STREHL, 4>(env, ts, p, grid, st);
-    case 5: return launch_phase<STREHL, 5>(env, ts, p, grid, st);
-    case 6: return launch_phase<STREHL, 6>(env, ts, p, grid, st);
-    case 7: return launch_phase<STREHL, 7>(env, ts, p, grid, st);
-    case 8: return launch_phase<STREHL, 8>(env, ts, p, grid, st);
+    case 1: return launch_phase<STREHL, 1, FUSED>(env, ts, p, grid, st);
+    case 2: return launch_phase<STREHL, 2, FUSED>(env, ts, p, grid, st);
+    case 3: return launch_phase<STREHL, 3, FUSED>(env, ts, p, grid, st);
+    case 4: return launch_phase<STREHL, 4, FUSED>(env, ts, p, grid, st);
+    case 5: return launch_phase<STREHL, 5, FUSED>(env, ts, p, grid, st);
+    case 6: return launch_phase<STREHL, 6, FUSED>(env, ts, p, grid, st);
+    case 7: return launch_phase<STREHL, 7, FUSED>(env, ts, p, grid, st);
+    case 8: return launch_phase<STREHL, 8, FUSED>(env, ts, p, grid, st);
   }
   AOG_FAIL(AOG_ERR_UNSUPPORTED, "obs_dim");
 }
@@ -1589,8 +1726,10 @@ int launch_phase_n(aog_env* env, TensorState* ts, const FieldParams& p, int n, i
 int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_outputs& out, cudaStream_t st) {
   TensorState* ts = TS(env);
   const aog_config& c = env->cfg;
-  if (!(ts->have_m1 && ts->have_m2 && ts->have_lp && ts->have_modes && ts->have_ap && ts->have_m2o && ts->have_m1o))
+  if (!(ts->have_m1 && ts->have_m2 && ts->have_lp && ts->have_modes && ts->have_ap && ts->have_m2o && ts->have_m1o) ||
+      (ts->fused && !ts->have_gfib))
     AOG_FAIL(AOG_ERR_STATE, "tensor path tables incomplete");
+  const bool fused = ts->fused;
   (void)flat_dm;
   const int Np = TC_NP, n = c.obs_dim, K = c.num_modes, J = c.num_lp_modes, B = c.num_envs;
   const bool strehl = with_reward && c.rew_type == AOG_REW_STREHL_RATIO;
@@ -1615,22 +1754,21 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       fp.sci_ratio_q32 = (uint32_t)std::llround(c.wavelength_wfs / c.wavelength_sci * 4294967296.0);
       fp.hwt = ts->hwt; fp.apmask = ts->apmask; fp.m1o32 = ts->m1o32; fp.phi = ts->phi; fp.R4 = ts->R4;
       fp.strehl_part = env->strehl_part;
+      fp.gfib = ts->gfib; fp.fib_part = ts->fib_part;
       fp.err_flag = ts->err_flag;
       const int grid = cdiv(fp.num_items, fp.items_per_cta);
       int rc;
-      if (strehl) {
-        AOG_CUDA(cudaMemsetAsync(env->strehl_part, 0, (size_t)nB * FK_SLOTS * sizeof(double2), st));
-        rc = launch_phase_n<true>(env, ts, fp, n, grid, st);
-      } else {
-        rc = launch_phase_n<false>(env, ts, fp, n, grid, st);
-      }
+      if (strehl) AOG_CUDA(cudaMemsetAsync(env->strehl_part, 0, (size_t)nB * FK_SLOTS * sizeof(double2), st));
+      if (fused) AOG_CUDA(cudaMemsetAsync(ts->fib_part, 0, (size_t)nB * FK_SLOTS * FK_JT * sizeof(double2), st));
+      if (fused) rc = strehl ? launch_phase_n<true, true>(env, ts, fp, n, grid, st) : launch_phase_n<false, true>(env, ts, fp, n, grid, st);
+      else       rc = strehl ? launch_phase_n<true, false>(env, ts, fp, n, grid, st) : launch_phase_n<false, false>(env, ts, fp, n, grid, st);
       if (rc) return rc;
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev0, st)); }
     const int max_clusters = ts->num_sms / 2;
     int tc_dbg = 0;
     { const char* d = getenv("AOG_TC_DEBUG"); tc_dbg = d ? atoi(d) : 0; }
-    {
+    if (!fused) {
       F1Params f1{};
       f1.num_items = nB;
       f1.apmask = ts->apmask;
@@ -1645,7 +1783,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       AOG_LAUNCH_CHECK();
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->evm, st)); }
-    if (with_reward) {
+    if (with_reward && !fused) {
       TcParams p{};
       p.num_envs = nB;
       p.err_flag = ts->err_flag;
@@ -1666,9 +1804,10 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     a.R = nullptr; a.R4 = ts->R4; a.r4_parts = FK_PARTS; a.m1o = ts->m2oT;
     {
       // coef holds the raw projection sums (re, im): scale = norm * amp * pupil weight * table scale
-      const double sc = c.amp_fiber * ts->pupil_weight * ts->lpw_scale;
+      const double sc = fused ? c.amp_fiber * ts->gfib_scale : c.amp_fiber * ts->pupil_weight * ts->lpw_scale;
       a.coef_scale = make_double2(c.mft_norm_re * sc, c.mft_norm_im * sc);
-      a.coef_is_raw = 2;
+      a.coef_is_raw = fused ? 3 : 2;
+      a.fib_part = ts->fib_part; a.fib_slots = FK_SLOTS; a.fib_stride = FK_JT;
     } a.coef = nullptr; a.coef4 = ts->coef4; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
     a.strehl_part = env->strehl_part; a.strehl_blocks = FK_SLOTS;
     a.Np = Np; a.n = n; a.J = J; a.rew_type = c.rew_type; a.has_thr = c.has_rew_threshold;

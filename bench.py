@@ -168,9 +168,10 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='environments per GPU')
     ap.add_argument('--workload', default='quasi_static_64act', choices=list(WORKLOADS))
-    ap.add_argument('--precision', default=os.environ.get('AOG_PRECISION', 'auto'), choices=['auto', 'f64', 'tensor'])
+    ap.add_argument('--precision', default=os.environ.get('AOG_PRECISION', 'auto'), choices=['auto', 'f64', 'tensor', 'fused'])
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-mft-arm', action='store_true', help='skip the secondary timing of the tensor-core MFT path')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -193,18 +194,8 @@ def main():
 
     w = WORKLOADS[args.workload]
     B, K, n2, T = args.envs, w['act_dim'], w['obs_dim'] ** 2, w['timesteps_per_episode']
-    precision = args.precision
-    env = None
-    if precision in ('auto', 'tensor'):
-        try:
-            env = AOVecEnv(B, **w, device=local, seed=1234, precision='tensor', env_id_base=rank * B)
-            precision = 'tensor'
-        except AogError as e:
-            if precision == 'tensor' or 'not built' not in str(e):
-                raise
-    if env is None:
-        env = AOVecEnv(B, **w, device=local, seed=1234, precision='f64', env_id_base=rank * B)
-        precision = 'f64'
+    precision = 'fused' if args.precision == 'auto' else args.precision
+    env = AOVecEnv(B, **w, device=local, seed=1234, precision=precision, env_id_base=rank * B)
     Np, Nf = env.num_pupil_pixels, env.num_focal_pixels_fiber
 
     # action pool: device-resident for `value`, pinned host for `e2e`
@@ -275,56 +266,95 @@ def main():
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     clocks = sampler.summary() if sampler else None      # sampled over both timed regions
 
-    # roofline of the dominant kernel sequence: MFT GEMMs, CUDA events inside the library
-    env._h.set_timing(True)
-    mft_ms = []
-    kms = []
-    state['t'] = 1          # no reset inside this loop
-    for i in range(6):
-        step_device(i)
-        torch.cuda.synchronize()
-        mft_ms.append(env._h.last_mft_ms())
-        if precision == 'tensor':
-            kms.append(env._h.last_kernel_ms())
-    env._h.set_timing(False)
-    mft_ms = sorted(mft_ms[1:])
-    mft = mft_ms[len(mft_ms) // 2]
-    chunk = min(env._h.chunk_size(), B)
-    last_chunk = B - (B - 1) // chunk * chunk
-    flop = MFT_FLOP_PER_ENV(Np, Nf) * last_chunk
-    achieved = flop / (mft * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
-    if precision == 'tensor':
-        peak = peaks.get('bf16_tflops_sustained', 1400.0)
-        peak_note = ('measured cuBLAS bf16 sustained (MEASURED_PEAKS.json)' if peaks else
-                     'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)')
-        issued = 3.0
+
+    def kernel_times(e, prec):
+        """median per-kernel milliseconds of one step (CUDA events on the launch stream inside the library)"""
+        e._h.set_timing(True)
+        mft_ms, kms = [], []
+        for i in range(6):      # no reset inside this loop
+            e.step(e.SH_step()[0] if sh_loop else act_dev[i % pool])
+            torch.cuda.synchronize()
+            mft_ms.append(e._h.last_mft_ms())
+            if prec != 'f64':
+                kms.append(e._h.last_kernel_ms())
+        e._h.set_timing(False)
+        mft_ms = sorted(mft_ms[1:])
+        km = {k: sorted(d[k] for d in kms[1:])[len(kms[1:]) // 2] for k in kms[0]} if kms else None
+        return mft_ms[len(mft_ms) // 2], km
+
+    def traffic_from_profiles(name, last_chunk):
+        # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture (profiles/),
+        # valid for the chunk size it was taken at
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', name)))
+            if tj.get('envs_per_launch') == last_chunk:
+                return tj['bytes_per_launch']
+        except Exception:
+            pass
+        return None
+
+    def mft_roofline(e, prec):
+        """the matrix-Fourier-transform GEMMs against the tensor (or FP64) pipe"""
+        mft, km = kernel_times(e, prec)
+        chunk = min(e._h.chunk_size(), B)
+        last_chunk = B - (B - 1) // chunk * chunk
+        achieved = MFT_FLOP_PER_ENV(Np, Nf) * last_chunk / (mft * 1e-3) / 1e12
+        if prec == 'tensor':
+            peak = peaks.get('bf16_tflops_sustained', 1400.0)
+            peak_note = ('measured cuBLAS bf16 sustained (MEASURED_PEAKS.json)' if peaks else
+                         'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)')
+            issued = 3.0
+        else:
+            peak = 37.0
+            peak_note = 'nominal B200 FP64 37 TFLOP/s (no measured FP64 peak in MEASURED_PEAKS.json)'
+            issued = 1.0
+        r = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+             'traffic': traffic_from_profiles('mft_dram_traffic.json', last_chunk) if prec == 'tensor' else None,
+             'kernel': ('matrix Fourier transform: k_field_mft1 (field formation + stage-1 product) + k_mft2 (stage-2 '
+                        'product + fibre projection)') if prec == 'tensor' else 'MFT stage-1 + stage-2 complex GEMMs (FP64)',
+             'ms_per_launch': mft, 'envs_per_launch': last_chunk, 'algorithmic_flop_per_env': MFT_FLOP_PER_ENV(Np, Nf),
+             'issued_over_algorithmic': issued, 'peak_source': peak_note}
+        if km:
+            r['kernel_ms'] = km
+        return r
+
+    mft_arm = None
+    if precision == 'fused':
+        # dominant kernel: k_dm_phase_tc<fused> -- DM-surface GEMM (tcgen05) + phase + every reduction of the step.
+        # Algorithmic bytes (SURVEY 8d, fused design): one FP32-sized read of the screen per env-step, 4 P bytes.
+        _, km = kernel_times(env, precision)
+        chunk = min(env._h.chunk_size(), B)
+        last_chunk = B - (B - 1) // chunk * chunk
+        alg_bytes = 4.0 * Np * Np
+        ach = alg_bytes * last_chunk / (km['field'] * 1e-3) / 1e9
+        peak = peaks.get('hbm_gbs', 6500.0)
+        roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                    'traffic': traffic_from_profiles('fused_dram_traffic.json', last_chunk),
+                    'kernel': 'k_dm_phase_tc<fused>: tcgen05 DM-surface GEMM, wavefront phase, obs-arm / Strehl / '
+                              'back-projected fibre-mode reductions (the whole optics chain of a step)',
+                    'ms_per_launch': km['field'], 'envs_per_launch': last_chunk,
+                    'algorithmic_bytes_per_env': alg_bytes,
+                    'peak_source': 'measured copy bandwidth (MEASURED_PEAKS.json)' if peaks else
+                                   'fallback 6.5 TB/s (B200_PROFILING.md)',
+                    'note': 'the kernel is issue / SFU bound (4 MUFU per lit pixel), not HBM bound; see DESIGN.md 4.3'}
     else:
-        peak = 37.0
-        peak_note = 'nominal B200 FP64 37 TFLOP/s (no measured FP64 peak in MEASURED_PEAKS.json)'
-        issued = 1.0
-    # dram__bytes_read + dram__bytes_write of the two MFT kernels from the committed ncu --set full capture
-    # (profiles/), valid for the chunk size it was taken at
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'mft_dram_traffic.json')))
-        if precision == 'tensor' and tj.get('envs_per_launch') == last_chunk:
-            traffic = tj['bytes_per_launch']
-    except Exception:
-        pass
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'traffic': traffic,
-                'kernel': ('matrix Fourier transform: k_field_mft1 (field formation + stage-1 product) + k_mft2 (stage-2 '
-                           'product + fibre projection)') if precision == 'tensor' else 'MFT stage-1 + stage-2 complex GEMMs (FP64)',
-                'ms_per_launch': mft,
-                'envs_per_launch': last_chunk, 'algorithmic_flop_per_env': MFT_FLOP_PER_ENV(Np, Nf),
-                'issued_over_algorithmic': issued, 'peak_source': peak_note}
-    if kms:
-        roofline['kernel_ms'] = {k: sorted(d[k] for d in kms[1:])[len(kms[1:]) // 2] for k in kms[0]}
+        roofline = mft_roofline(env, precision)
+    if precision == 'fused' and not args.no_mft_arm and args.workload != 'dynamic_v20_sh':
+        # BASELINE.json's metric also asks for the MFT tensor-pipe utilisation: time the path that runs the
+        # fibre-arm matrix Fourier transform as tcgen05 GEMMs (precision='tensor') on the same workload
+        env_t = AOVecEnv(B, **w, device=local, seed=1234, precision='tensor', env_id_base=rank * B)
+        main_env, env = env, env_t
+        ms_t, _ = timed(step_device, max(10, args.steps // 10), 3)
+        n_t = max(10, args.steps // 10)
+        mft_arm = {'precision': 'tensor', 'value': world * B * n_t / (ms_t * 1e-3), 'unit': 'env-steps/s',
+                   'ms_per_step': ms_t / n_t, 'steps': n_t, 'roofline': mft_roofline(env_t, 'tensor')}
+        env = main_env
+        env_t.close()
 
     if rank != 0:
         if world > 1:
@@ -342,12 +372,15 @@ def main():
     line = {
         'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f64' if precision == 'f64' else 'f16x3(tcgen05)+f32/f64',
+        'vs_baseline': None,
+        'dtype': {'f64': 'f64', 'tensor': 'f16x3(tcgen05)+f32/f64', 'fused': 'f16x3(tcgen05 DM GEMM)+f32/f64'}[precision],
         'data': 'synthetic',
         'config': {'workload': describe(args.workload, B, world), 'precision': precision, 'envs_per_gpu': B,
                    'l2_policy': (f'inputs larger than L2: {B * Np * Np * 4 / 1e6:.0f} MB of phase-screen tiles read per step, '
                                  f'plus {B * Np * Np * 4 / 1e6:.0f} MB of phase and {B * 128 * 480 * 4 / 1e6:.0f} MB of stage-1 product '
                                  'written and re-read (126 MB L2)') if precision == 'tensor' else
+                                (f'inputs larger than L2: {B * Np * Np * 4 / 1e6:.0f} MB of phase-screen tiles read per step '
+                                 '(126 MB L2)') if precision == 'fused' else
                                 f'inputs larger than L2: {B * Np * Np * 8 / 1e6:.0f} MB of screens read per step',
                    'timing': 'CUDA events on the launch stream, max over ranks'},
         'e2e': {'value': e2e, 'unit': 'env-steps/s', 'h2d_bytes_per_step': world * B * K * 4,
@@ -357,6 +390,8 @@ def main():
         'cpu_baseline': cpu,
         'clocks': clocks,
     }
+    if mft_arm:
+        line['mft_gemm_path'] = mft_arm
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

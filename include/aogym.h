@@ -56,8 +56,13 @@ typedef enum aog_status {
 enum { AOG_ATM_QUASI_STATIC = 0, AOG_ATM_SEMI_DYNAMIC = 1, AOG_ATM_DYNAMIC = 2 };
 enum { AOG_REW_STREHL_RATIO = 0, AOG_REW_SMF_SSIM = 1 };
 enum { AOG_DTYPE_F32 = 0, AOG_DTYPE_F64 = 1 };
-/* arithmetic of the step path: FP64 everywhere, or split-fp16 tcgen05 MFT + FP32 field math */
-enum { AOG_PRECISION_F64 = 0, AOG_PRECISION_TENSOR = 1 };
+/* arithmetic of the step path:
+ *   F64    FP64 everywhere (guaranteed parity)
+ *   TENSOR tcgen05 DM GEMM + FP32 phase math + the fibre-arm matrix Fourier transform as split-fp16 tcgen05 GEMMs
+ *   FUSED  tcgen05 DM GEMM + ONE fused kernel: the fibre coupling coefficients are inner products of the pupil
+ *          field with the fibre modes propagated back to the pupil (G_j = M1^T (mode_j w) M2^T, FP64 on the host),
+ *          so the screen is read once per step and neither the field nor the focal plane exists in HBM */
+enum { AOG_PRECISION_F64 = 0, AOG_PRECISION_TENSOR = 1, AOG_PRECISION_FUSED = 2 };
 
 /* Tables (host FP64 unless noted), sizes with Np pupil px/side, P = Np*Np, K modes, Nf focal
  * px/side, n obs px/side, J fibre modes, Ns stencil points. */

@@ -44,7 +44,7 @@ def test_oracle_reproduces_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('precision', ['f64', 'tensor'])
+@pytest.mark.parametrize('precision', ['f64', 'tensor', 'fused'])
 @pytest.mark.parametrize('name', NAMES)
 def test_cuda_path_matches_golden(name, precision):
     import sys
@@ -64,7 +64,7 @@ def test_cuda_path_matches_golden(name, precision):
             tabs.update(sh_recon=ref.reconstruction_matrix,
                         sh_offset=np.array((sh.mla_x[idx], sh.mla_y[idx])) + ref.slopes_ref)
     env = AOEnv(**kw, initial_screen=z['screen'], precision=precision, tables=tabs)
-    rtol = {'f64': 1e-7, 'tensor': 1e-5}[precision]
+    rtol = {'f64': 1e-7, 'tensor': 1e-5, 'fused': 1e-5}[precision]
     T = kw['timesteps_per_episode']
     noise, pos, i = z['noise'], 0, 0
     for ep in range(case['episodes']):

@@ -6,8 +6,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-PRECISIONS = ['f64', 'tensor']
-RTOL = {'f64': 1e-9, 'tensor': 1e-5}
+PRECISIONS = ['f64', 'tensor', 'fused']
+RTOL = {'f64': 1e-9, 'tensor': 1e-5, 'fused': 1e-5}
 
 
 def _mk(precision, **kw):
