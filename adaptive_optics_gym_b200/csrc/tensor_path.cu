@@ -67,14 +67,20 @@ struct TensorState {
   int act_rows = 128;
   double2* m2oT = nullptr;                            // [n][Np] transposed obs table
   int* err_flag = nullptr;                            // device flag set by a timed-out barrier wait
-  // AOG_PRECISION_FUSED: fibre modes propagated back to the pupil, G_j = M1^T (mode_j w) M2^T / max|G| (FP32),
-  // [Np x][Np / 16][16 y][J]: the 16-pixel chunk of a column is one contiguous 128 J-byte run for the bulk prefetch
+  // AOG_PRECISION_FUSED: per-pixel records [Np x][Np / 16][16 y][FK_NT(n)] float2 = [obs-arm twiddles m1o[v][y] |
+  // fibre modes propagated back to the pupil, G_j = M1^T (mode_j w) M2^T / max|G| | (aperture, 0)], all times the
+  // aperture: the 16 records of a column chunk are one contiguous run for the bulk prefetch
   bool fused = false;
   float2* gfib = nullptr;
   double gfib_scale = 0.0;
-  double2* fib_part = nullptr;                        // [chunk][FK_SLOTS][J] partial projection sums
-  bool have_gfib = false;
-  std::vector<double> h_m1, h_m2, h_lp;               // host copies of the tables G is built from
+  double2* fib_part = nullptr;                        // [chunk][FK_SLOTS][FK_JT] partial projection sums
+  bool have_gfib = false, have_G = false;
+  std::vector<double> h_m1, h_m2, h_lp, h_G, h_m1o, h_ap;   // host copies of the tables the records are built from
+  // symmetric tables (kernel MODE 2, see FK_NF): G_j = e^{i theta_j} R_j; lpphase_f[j] = e^{i beta_j L} e^{i theta_j}
+  bool sym = false, g_real = false, have_lpphase = false;
+  double theta[AOG_MAX_LP] = {0};
+  std::vector<double> h_lpphase;
+  double2* lpphase_f = nullptr;
   CUtensorMap tmA1_hi, tmA1_lo, tmB2_hi, tmB2_lo;
   CUtensorMap tmT128_hi, tmT128_lo;
   CUtensorMap tmTout_hi, tmTout_lo;                   // stage-1 epilogue stores: 128 rows x 16 columns, SWIZZLE_32B                   // stage-1 product, one env (128 rows) per box
@@ -517,17 +523,40 @@ constexpr int FK_STAGES = 1;                            // the double-buffered T
 constexpr int FK_A_TILE = 128 * 64 * 2;                 // 16 KB: 128 env rows x 128 B
 constexpr int FK_B_TILE = 256 * 64 * 2;                 // 32 KB slot (240 rows used)
 constexpr int FK_STAGE_BYTES = 2 * FK_A_TILE + 2 * FK_B_TILE;   // 96 KB
-constexpr int FK_EPI_WARPS = 12;                        // 3 per TMEM lane group: 5 of the 15 column chunks each
+#ifndef AOG_FK_EPI_WARPS      // tuning builds: 12 or 16
+#define AOG_FK_EPI_WARPS 12
+#endif
+constexpr int FK_EPI_WARPS = AOG_FK_EPI_WARPS;          // 3 per TMEM lane group: 5 of the 15 column chunks each
 constexpr int FK_PARTS = FK_EPI_WARPS / 4;
+// Work item -> pupil column: a CTA's contiguous item range strides through the pupil (53 is coprime with 240), so
+// every CTA sees the same mix of short (edge) and long (centre) aperture chords.
+constexpr int FK_COL_STRIDE = 53;
+__device__ __forceinline__ int fk_column(int item_in_block) { return (item_in_block * FK_COL_STRIDE) % TC_NP; }
 constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
 constexpr int FK_SLOTS = 16;                            // Strehl partial slots per env (>= CTAs touching an env block)
 constexpr int FK_MIN_ITEMS = 16;                        // items per CTA at least (bounds the slots)
 constexpr int FK_PF_TILE = 32 * 16 * 4;                 // 2 KB: 32 envs x 16 pixels of phase (one bulk copy)
 constexpr int FK_JT = 3;                                // fibre modes of the fused kernel (LP01 + 2 x LP11, AO_env.py:393)
-constexpr int FK_G_TILE = 16 * FK_JT * 8;               // 384 B: back-projected fibre modes of 16 pixels
-constexpr int FK_PF_SLOT = FK_PF_TILE + 512;            // phase tile + fibre-mode chunk (fused kernel)
-constexpr int FK_PF_BYTES = FK_EPI_WARPS * 2 * FK_PF_SLOT;   // per warp: 2 buffers
-constexpr int FK_AUX_BAR = 256;
+// Fused kernel: per pixel one record of FK_NT(n) float2 = [n obs-arm twiddles | FK_JT back-projected fibre modes |
+// (aperture, 0)], every entry already multiplied by the aperture, so the arithmetic needs no mask; the 16 records
+// of a (column, 16-pixel chunk) are one contiguous run fetched with the phase tile.
+__host__ __device__ constexpr int FK_NT(int nobs) { return (nobs + FK_JT + 1 + 1) & ~1; }
+// Symmetric fused kernel (kernel MODE 2).  hcipy's pupil and focal grids are symmetric about the axis, so
+//   * the obs-arm twiddle rows come in conjugate pairs, m1o[n-1-v][y] = conj(m1o[v][y]) (the centre row of an odd n
+//     is real): with m = a + ib and E = c + is the four products ac, bs, as, bc serve both rows of a pair;
+//   * every back-projected fibre mode is a real function times one unit phasor, G_j = e^{i theta_j} R_j (the Fourier
+//     transform of a real mode that is even or odd along each axis): the projection is two real sums and the phasor
+//     joins the mode's propagation phase in k_finalize.
+// Record = FK_NF(n) floats: [a, b per pair | centre a | R_0..R_2 | aperture], padded to a multiple of 4.
+// The tables are checked for both properties when they are uploaded; tables without them run kernel MODE 1.
+__host__ __device__ constexpr int FK_NF(int nobs) { return (2 * (nobs / 2) + (nobs & 1) + FK_JT + 1 + 3) & ~3; }
+// kernel MODE: 0 = tensor path (stores the phase for the MFT stages), 1 = fused, 2 = fused + symmetric tables
+__host__ __device__ constexpr int FK_TAB_TILE(int nobs, int mode) {
+  return mode == 1 ? 16 * FK_NT(nobs) * 8 : (mode == 2 ? 16 * FK_NF(nobs) * 4 : 0);
+}
+__host__ __device__ constexpr int FK_PF_SLOT(int nobs, int mode) { return FK_PF_TILE + FK_TAB_TILE(nobs, mode); }
+__host__ __device__ constexpr int FK_PF_BYTES(int nobs, int mode) { return FK_EPI_WARPS * 2 * FK_PF_SLOT(nobs, mode); }
+constexpr int FK_AUX_BAR = 512;
 
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -547,6 +576,27 @@ __device__ __forceinline__ float small_int_to_float(int32_t v) {
 }
 __device__ __forceinline__ void sincos_fixed(int32_t t, float* s, float* c) {
   const float x = small_int_to_float((t << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(x));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(x));
+}
+
+// sin / cos of a fixed-point phase given as tb = t + 2^22 (half a turn of bias): the low 23 bits of tb are the
+// phase mod one turn, offset so that [0, 2^23) maps to [-pi, pi); OR-ing them under the exponent of 2^23 makes
+// the float 2^23 + (tb mod 2^23) without a conversion.
+__device__ __forceinline__ void sincos_biased(int32_t tb, float* s, float* c) {
+  const float f = __int_as_float((tb & 0x7FFFFF) | 0x4B000000);
+  const float x = (f - 12582912.f) * (3.14159265358979323846f / PHI_ONE);      // 12582912 = 2^23 + 2^22
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(x));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(x));
+}
+
+// the same in three instructions before the SFU: one LOP3 ((tb & kmask) | kexp, the constants in registers) and one
+// FMA (the rounded constant -3 pi shifts every pixel by the same 1e-7 rad, which no |.|^2 output sees)
+__device__ __forceinline__ void sincos_biased_fma(int32_t tb, int32_t kmask, int32_t kexp, float* s, float* c) {
+  int32_t u;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(u) : "r"(tb), "r"(kmask), "r"(kexp));
+  constexpr float sc = 3.14159265358979323846f / PHI_ONE;
+  const float x = fmaf(__int_as_float(u), sc, -12582912.f * sc);
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(x));
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(x));
 }
@@ -574,12 +624,12 @@ struct FieldParams {
   float* phi;            // [env][Np / 16][Np x][16 y] total phase out, radians in [-pi, pi)
   float2* R4;            // [env][Np x][FK_PARTS][n] obs-arm column partial sums out
   double2* strehl_part;  // [env][FK_SLOTS]
-  const float2* gfib;    // fused kernel: [Np x][Np / 16][16 y][FK_JT] back-projected fibre modes
+  const void* gfib;      // fused kernel: [Np x][Np / 16][16 y] per-pixel records (FK_NT float2 or FK_NF floats each)
   double2* fib_part;     // fused kernel: [env][FK_SLOTS][FK_JT] partial projection sums out
   int* err_flag;
 };
 
-template <bool STREHL, int NOBS, bool FUSED>
+template <bool STREHL, int NOBS, int MODE>
 __global__ void __launch_bounds__(FK_THREADS, 1)
 k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constant__ CUtensorMap tmAct_lo,
               const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
@@ -590,7 +640,10 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint8_t* pf = base + FK_STAGES * FK_STAGE_BYTES;                       // phase prefetch ring of the epilogue warps
-  uint8_t* aux = pf + FK_PF_BYTES;
+  constexpr bool FUSED = MODE != 0, SYM = MODE == 2;
+  constexpr int PF_SLOT = FK_PF_SLOT(NOBS, MODE);
+  constexpr int NT = FK_NT(NOBS);
+  uint8_t* aux = pf + FK_PF_BYTES(NOBS, MODE);
   uint64_t* full = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty = full + FK_STAGES;
   uint64_t* tmem_full = empty + FK_STAGES;       // [2]
@@ -599,15 +652,16 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pfbar + 2 * FK_EPI_WARPS);
   constexpr int NRED = FUSED ? 1 + FK_JT : 1;                            // Strehl sum + fibre projections
   double2* sred = reinterpret_cast<double2*>(aux + FK_AUX_BAR);          // [NRED][FK_PARTS][128 envs]
-  float2* m1o_s = reinterpret_cast<float2*>(sred + NRED * FK_PARTS * 128);   // [n][Np]
-  uint16_t* apmask_s = reinterpret_cast<uint16_t*>(m1o_s + NOBS * Np);  // [Np][Np / 16]
+  float2* m1o_s = reinterpret_cast<float2*>(sred + NRED * FK_PARTS * 128);   // [n][Np] (not used by the fused kernel)
+  uint16_t* apmask_s = reinterpret_cast<uint16_t*>(m1o_s + (FUSED ? 0 : NOBS * Np));  // [Np][Np / 16]
   uint8_t* run_s = reinterpret_cast<uint8_t*>(apmask_s + Np * (Np / 16));   // [Np][2]: first lit chunk, lit count
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item_lo = blockIdx.x * p.items_per_cta;
   const int item_hi = min(p.num_items, item_lo + p.items_per_cta);
 
-  for (int i = threadIdx.x; i < NOBS * Np; i += blockDim.x) m1o_s[i] = p.m1o32[i];
+  if (!FUSED)
+    for (int i = threadIdx.x; i < NOBS * Np; i += blockDim.x) m1o_s[i] = p.m1o32[i];
   for (int i = threadIdx.x; i < Np * (Np / 16); i += blockDim.x) apmask_s[i] = p.apmask[i];
   for (int xx = threadIdx.x; xx < Np; xx += blockDim.x) {
     int first = 0, cnt = 0;
@@ -642,7 +696,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int item = item_lo; item < item_hi; ++item) {
-        const int eb = item / Np, x = item - eb * Np;
+        const int eb = item / Np, x = fk_column(item - eb * Np);
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait<200>(&empty[stage], phase ^ 1, p.err_flag, 11);
           mbar_expect_tx(&full[stage], TX_BYTES);
@@ -702,6 +756,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
     const int row = lg * 32 + lane;           // env within the block
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     double st_re = 0.0, st_im = 0.0;
+    int m_base = 0;                                    // lit chunks of the CTA's earlier items (mod FK_PARTS)
     double fb_re[FK_JT], fb_im[FK_JT];                 // fused kernel: fibre projection sums of my env
 #pragma unroll
     for (int j = 0; j < FK_JT; ++j) fb_re[j] = fb_im[j] = 0.0;
@@ -710,37 +765,43 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
 
     // Phase prefetch: the warp's 32 envs x 16 pixels of atmospheric phase are one contiguous, pre-swizzled
     // 2 KB tile: a single cp.async.bulk one chunk ahead of the arithmetic.
-    const uint32_t pf_warp = smem_u32(pf + ew * (2 * FK_PF_SLOT));
-    const uint8_t* pf_warp_ptr = pf + ew * (2 * FK_PF_SLOT);
+    const uint32_t pf_warp = smem_u32(pf + ew * (2 * PF_SLOT));
+    const uint8_t* pf_warp_ptr = pf + ew * (2 * PF_SLOT);
     uint64_t* pbar = pfbar + 2 * ew;
     uint32_t pphase0 = 0, pphase1 = 0;
     int buf = 0;
+    // The lit chunks of all of the CTA's items form ONE stream dealt round-robin to the FK_PARTS warps of a lane
+    // group (chunk g of the stream -> warp g % FK_PARTS), so the warps stay within one chunk of each other over
+    // the whole kernel instead of per item; the double-buffered accumulator absorbs the per-item difference.
     int n_item = item_lo - 1, n_ci = 0, n_end = 0;       // prefetch cursor: chunk n_ci of item n_item
+    int n_x = 0, n_base = 0, n_cnt = 0;                  // its column, lit chunks before the item (mod FK_PARTS), its lit count
     auto next_lit = [&]() -> bool {
       n_ci += FK_PARTS;
       while (n_ci >= n_end) {
+        n_base = (n_base + n_cnt) % FK_PARTS;
         if (++n_item >= item_hi) return false;
-        const int xx = n_item - (n_item / Np) * Np;
-        n_ci = run_s[2 * xx] + q;
-        n_end = run_s[2 * xx] + run_s[2 * xx + 1];
+        n_x = fk_column(n_item - (n_item / Np) * Np);
+        n_cnt = run_s[2 * n_x + 1];
+        n_ci = run_s[2 * n_x] + (q + FK_PARTS - n_base) % FK_PARTS;
+        n_end = run_s[2 * n_x] + n_cnt;
       }
       return true;
     };
     auto issue_prefetch = [&](int b) {
       if (lane == 0) {
-        const int eb2 = n_item / Np, x2 = n_item - eb2 * Np;
+        const int eb2 = n_item / Np, x2 = n_x;
         int xp2 = x2 + p.col_origin;
         if (xp2 >= Np) xp2 -= Np;
         const size_t eb32 = (size_t)(p.env0 + eb2 * 128 + lg * 32) >> 5;
         const int32_t* src = p.hwt + ((eb32 * Np + xp2) * (Np / 16) + n_ci) * (32 * 16);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&pbar[b], FUSED ? FK_PF_TILE + FK_G_TILE : FK_PF_TILE);
+        mbar_expect_tx(&pbar[b], PF_SLOT);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(pf_warp + b * FK_PF_SLOT), "l"(src), "r"((uint32_t)FK_PF_TILE), "r"(smem_u32(&pbar[b])) : "memory");
+                     ::"r"(pf_warp + b * PF_SLOT), "l"(src), "r"((uint32_t)FK_PF_TILE), "r"(smem_u32(&pbar[b])) : "memory");
         if (FUSED) {
-          const float2* gsrc = p.gfib + ((size_t)x2 * (Np / 16) + n_ci) * (16 * FK_JT);
+          const uint8_t* gsrc = static_cast<const uint8_t*>(p.gfib) + ((size_t)x2 * (Np / 16) + n_ci) * FK_TAB_TILE(NOBS, MODE);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(pf_warp + b * FK_PF_SLOT + FK_PF_TILE), "l"(gsrc), "r"((uint32_t)FK_G_TILE), "r"(smem_u32(&pbar[b])) : "memory");
+                       ::"r"(pf_warp + b * PF_SLOT + FK_PF_TILE), "l"(gsrc), "r"((uint32_t)FK_TAB_TILE(NOBS, MODE)), "r"(smem_u32(&pbar[b])) : "memory");
         }
       }
     };
@@ -784,7 +845,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
     };
 
     for (int item = item_lo; item < item_hi; ++item, ++it) {
-      const int eb = item / Np, x = item - eb * Np;
+      const int eb = item / Np, x = fk_column(item - eb * Np);
       if ((STREHL || FUSED) && eb != cur_eb) {
         if (cur_eb >= 0) flush_strehl(cur_eb);
         cur_eb = eb;
@@ -794,13 +855,17 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       mbar_wait(&tmem_full[as], (it >> 1) & 1, p.err_flag, 14);
       tc_fence_after();
       const bool valid = env < p.num_envs;
+      // obs-arm column sums of this item: (re, im) per row; MODE 2: (ac, bs, as, bc) per conjugate pair, (ac, as) centre
       double obs_re[NOBS], obs_im[NOBS];
 #pragma unroll
       for (int v = 0; v < NOBS; ++v) obs_re[v] = obs_im[v] = 0.0;
+      constexpr int kmask = 0x7FFFFF, kexp = 0x4B000000;
       float sre = 0.f, sim = 0.f;
       const int run_first = run_s[2 * x], run_end = run_first + run_s[2 * x + 1];
+      const int my_first = run_first + (q + FK_PARTS - m_base) % FK_PARTS;   // my chunks of the stream in this item
+      m_base = (m_base + run_s[2 * x + 1]) % FK_PARTS;
 #pragma unroll 1
-      for (int ci = run_first + q; ci < run_end; ci += FK_PARTS) {       // warp-uniform: only lit chunks
+      for (int ci = my_first; ci < run_end; ci += FK_PARTS) {            // warp-uniform: only lit chunks
         const uint32_t mask = apmask_s[x * (Np / 16) + ci];
         const int y0 = ci * 16;
         float d[16];
@@ -816,8 +881,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
           else         { mbar_wait(&pbar[1], pphase1, p.err_flag, 16); pphase1 ^= 1; }
         }
         buf ^= 1;
-        const uint8_t* tile = pf_warp_ptr + cb * FK_PF_SLOT + lane * 64;
-        const float2* gt = reinterpret_cast<const float2*>(pf_warp_ptr + cb * FK_PF_SLOT + FK_PF_TILE);   // [16 y][FK_JT]
+        const uint8_t* tile = pf_warp_ptr + cb * PF_SLOT + lane * 64;
         const int sw = (lane >> 1) & 3;                                   // pieces were stored at j ^ ((env >> 1) & 3)
         int32_t t[16];
 #pragma unroll
@@ -826,79 +890,169 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
           t[4 * j] = h.x; t[4 * j + 1] = h.y; t[4 * j + 2] = h.z; t[4 * j + 3] = h.w;
         }
         tc_wait_ld();
-        float ph[16];                                                     // total phase at lambda_wfs, [-pi, pi)
+        if constexpr (SYM) {
+          // ---- fused kernel, symmetric tables: 12 FMAs per pixel for the obs pair, the three fibre modes and Strehl
+          constexpr int NP2 = NOBS / 2, NC = NOBS & 1, NF = FK_NF(NOBS);
+          const float4* tab = reinterpret_cast<const float4*>(pf_warp_ptr + cb * PF_SLOT + FK_PF_TILE);   // [16 y][NF / 4]
+          const int32_t q31 = (int32_t)(p.sci_ratio_q32 >> 1);
+          const int32_t sci_bias = (1 << 22) - 2 * (int32_t)(((long long)(1 << 22) * (long long)q31) >> 32);
+          float pp[4 * NP2 + 2 * NC + 1], fre[FK_JT], fim[FK_JT];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          t[j] += __float2int_rn(d[j] * PHI_ONE);                         // atmosphere + DM, fixed point, unreduced
-          ph[j] = small_int_to_float((t[j] << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
-        }
-        if (!FUSED && !(p.dbg & 1)) {
-          // Full-sector stores: a lane's 16 pixels are 64 contiguous bytes, but a thread stores at most 16 per
-          // instruction.  Lane pairs swap halves so that each store instruction writes whole 32-byte sectors
-          // (lanes 2i, 2i+1 -> the two halves of a sector of env 2i, then of env 2i+1).
-          const bool odd = lane & 1;
-          const bool valid_even = (env & ~1) < p.num_envs, valid_odd = (env | 1) < p.num_envs;
-          float* row_even = p.phi + (((size_t)(env & ~1) * (Np / 16) + ci) * Np + x) * 16 + (odd ? 4 : 0);
-          float* row_odd = row_even + (size_t)Np * Np;
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {              // pixels [8 h8, 8 h8 + 8) = one sector per env
-            const float* a = ph + 8 * h8;
-            float r[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) r[k] = __shfl_xor_sync(0xffffffffu, odd ? a[k] : a[4 + k], 1);
-            // even lane: own[0..3] -> env 2i first half;  received = env 2i+1's first half
-            // odd lane : received = env 2i's second half;  own[4..7] -> env 2i+1 second half
-            if (valid_even)
-              *reinterpret_cast<float4*>(row_even + 8 * h8) = odd ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(a[0], a[1], a[2], a[3]);
-            if (valid_odd)
-              *reinterpret_cast<float4*>(row_odd + 8 * h8) = odd ? make_float4(a[4], a[5], a[6], a[7]) : make_float4(r[0], r[1], r[2], r[3]);
-          }
-        }
-        {
-          // obs arm: 16-pixel partial sums in FP32, folded into FP64 per chunk
-          float ore[NOBS], oim[NOBS];
-#pragma unroll
-          for (int v = 0; v < NOBS; ++v) ore[v] = oim[v] = 0.f;
-          float fre[FK_JT], fim[FK_JT];               // fused kernel: fibre projections, same 16-pixel FP32 partials
+          for (int v = 0; v < 4 * NP2 + 2 * NC + 1; ++v) pp[v] = 0.f;
 #pragma unroll
           for (int k = 0; k < FK_JT; ++k) fre[k] = fim[k] = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
+            const int32_t tb = t[j] + __float2int_rn(d[j] * PHI_ONE) + (1 << 22);
             float c0, s0;
-            asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(ph[j]));
-            asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(ph[j]));
-            if (mask != 0xFFFFu && !((mask >> j) & 1u)) { c0 = 0.f; s0 = 0.f; }
+            sincos_biased_fma(tb, kmask, kexp, &s0, &c0);
+            float4 rec[NF / 4];
+#pragma unroll
+            for (int r = 0; r < NF / 4; ++r) rec[r] = tab[j * (NF / 4) + r];
+            const float* m = reinterpret_cast<const float*>(rec);
+#pragma unroll
+            for (int v = 0; v < NP2; ++v) {
+              pp[4 * v + 0] = fmaf(m[2 * v], c0, pp[4 * v + 0]);
+              pp[4 * v + 1] = fmaf(m[2 * v + 1], s0, pp[4 * v + 1]);
+              pp[4 * v + 2] = fmaf(m[2 * v], s0, pp[4 * v + 2]);
+              pp[4 * v + 3] = fmaf(m[2 * v + 1], c0, pp[4 * v + 3]);
+            }
+            if (NC) {
+              pp[4 * NP2] = fmaf(m[2 * NP2], c0, pp[4 * NP2]);
+              pp[4 * NP2 + 1] = fmaf(m[2 * NP2], s0, pp[4 * NP2 + 1]);
+            }
+#pragma unroll
+            for (int k = 0; k < FK_JT; ++k) {
+              fre[k] = fmaf(m[2 * NP2 + NC + k], c0, fre[k]);
+              fim[k] = fmaf(m[2 * NP2 + NC + k], s0, fim[k]);
+            }
+            if (STREHL) {
+              const int32_t ts = 2 * __mulhi(tb, q31) + sci_bias;
+              float cs, ss;
+              sincos_biased_fma(ts, kmask, kexp, &ss, &cs);
+              sre = fmaf(m[2 * NP2 + NC + FK_JT], cs, sre);
+              sim = fmaf(m[2 * NP2 + NC + FK_JT], ss, sim);
+            }
+          }
+          // pair v: row v = (ac - bs, as + bc), row n-1-v = (ac + bs, as - bc)
+#pragma unroll
+          for (int v = 0; v < NP2; ++v) {
+            obs_re[v] += (double)pp[4 * v + 0] - (double)pp[4 * v + 1];
+            obs_im[v] += (double)pp[4 * v + 2] + (double)pp[4 * v + 3];
+            obs_re[NOBS - 1 - v] += (double)pp[4 * v + 0] + (double)pp[4 * v + 1];
+            obs_im[NOBS - 1 - v] += (double)pp[4 * v + 2] - (double)pp[4 * v + 3];
+          }
+          if (NC) { obs_re[NP2] += (double)pp[4 * NP2]; obs_im[NP2] += (double)pp[4 * NP2 + 1]; }
+#pragma unroll
+          for (int k = 0; k < FK_JT; ++k) { fb_re[k] += (double)fre[k]; fb_im[k] += (double)fim[k]; }
+        } else if constexpr (FUSED) {
+          // ---- fused kernel: the whole optics chain of these 16 pixels, nothing leaves the SM
+          const float4* tab = reinterpret_cast<const float4*>(pf_warp_ptr + cb * PF_SLOT + FK_PF_TILE);   // [16 y][NT / 2]
+          const int32_t q31 = (int32_t)(p.sci_ratio_q32 >> 1);
+          // 2 mulhi(tb, q31) + sci_bias = (t lambda_wfs / lambda_sci) + 2^22, with tb = t + 2^22
+          const int32_t sci_bias = (1 << 22) - 2 * (int32_t)(((long long)(1 << 22) * (long long)q31) >> 32);
+          float ore[NOBS], oim[NOBS], fre[FK_JT], fim[FK_JT];
+#pragma unroll
+          for (int v = 0; v < NOBS; ++v) ore[v] = oim[v] = 0.f;
+#pragma unroll
+          for (int k = 0; k < FK_JT; ++k) fre[k] = fim[k] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // atmosphere + DM in fixed point (2^22 per half-turn, unreduced), biased by half a turn
+            const int32_t tb = t[j] + __float2int_rn(d[j] * PHI_ONE) + (1 << 22);
+            float c0, s0;
+            sincos_biased(tb, &s0, &c0);
+            float4 rec[NT / 2];
+#pragma unroll
+            for (int r = 0; r < NT / 2; ++r) rec[r] = tab[j * (NT / 2) + r];
+            const float2* m = reinterpret_cast<const float2*>(rec);   // [obs rows | fibre modes | (aperture, 0)]
 #pragma unroll
             for (int v = 0; v < NOBS; ++v) {
-              const float2 m = m1o_s[v * Np + y0 + j];
-              ore[v] = fmaf(m.x, c0, fmaf(-m.y, s0, ore[v]));
-              oim[v] = fmaf(m.x, s0, fmaf(m.y, c0, oim[v]));
+              ore[v] = fmaf(m[v].x, c0, fmaf(-m[v].y, s0, ore[v]));
+              oim[v] = fmaf(m[v].x, s0, fmaf(m[v].y, c0, oim[v]));
             }
-            if (FUSED) {
-              // c_j = sum_pixels E . G_j (AO_env.py:471 through the back-projected mode)
+            // c_j = sum_pixels E . G_j (AO_env.py:471 through the back-projected mode)
 #pragma unroll
-              for (int k = 0; k < FK_JT; ++k) {
-                const float2 g = gt[j * FK_JT + k];
-                fre[k] = fmaf(g.x, c0, fmaf(-g.y, s0, fre[k]));
-                fim[k] = fmaf(g.x, s0, fmaf(g.y, c0, fim[k]));
-              }
+            for (int k = 0; k < FK_JT; ++k) {
+              fre[k] = fmaf(m[NOBS + k].x, c0, fmaf(-m[NOBS + k].y, s0, fre[k]));
+              fim[k] = fmaf(m[NOBS + k].x, s0, fmaf(m[NOBS + k].y, c0, fim[k]));
+            }
+            if (STREHL) {
+              // phase at lambda_sci = phase at lambda_wfs x (lambda_wfs / lambda_sci), to two fixed-point units
+              const int32_t ts = 2 * __mulhi(tb, q31) + sci_bias;
+              float cs, ss;
+#ifdef AOG_FK_NO_STREHL_MUFU       // tuning build: how much of the kernel is the SFU pipe
+              cs = __int_as_float((ts & 0x7FFFFF) | 0x3F000000); ss = cs;
+#else
+              sincos_biased(ts, &ss, &cs);
+#endif
+              sre = fmaf(m[NOBS + FK_JT].x, cs, sre);
+              sim = fmaf(m[NOBS + FK_JT].x, ss, sim);
             }
           }
 #pragma unroll
           for (int v = 0; v < NOBS; ++v) { obs_re[v] += (double)ore[v]; obs_im[v] += (double)oim[v]; }
-          if (FUSED) {
 #pragma unroll
-            for (int k = 0; k < FK_JT; ++k) { fb_re[k] += (double)fre[k]; fb_im[k] += (double)fim[k]; }
-          }
-        }
-        if (STREHL) {
+          for (int k = 0; k < FK_JT; ++k) { fb_re[k] += (double)fre[k]; fb_im[k] += (double)fim[k]; }
+        } else {
+          float ph[16];                                                     // total phase at lambda_wfs, [-pi, pi)
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            // phase at lambda_sci = phase at lambda_wfs x (lambda_wfs / lambda_sci), exact to one fixed-point unit
-            const int32_t ts = (int32_t)(((long long)t[j] * (long long)p.sci_ratio_q32) >> 32);
-            float c0, s0;
-            sincos_fixed(ts, &s0, &c0);
-            if (mask == 0xFFFFu || ((mask >> j) & 1u)) { sre += c0; sim += s0; }
+            t[j] += __float2int_rn(d[j] * PHI_ONE);                         // atmosphere + DM, fixed point, unreduced
+            ph[j] = small_int_to_float((t[j] << 9) >> 9) * (3.14159265358979323846f / PHI_ONE);
+          }
+          if (!(p.dbg & 1)) {
+            // Full-sector stores: a lane's 16 pixels are 64 contiguous bytes, but a thread stores at most 16 per
+            // instruction.  Lane pairs swap halves so that each store instruction writes whole 32-byte sectors
+            // (lanes 2i, 2i+1 -> the two halves of a sector of env 2i, then of env 2i+1).
+            const bool odd = lane & 1;
+            const bool valid_even = (env & ~1) < p.num_envs, valid_odd = (env | 1) < p.num_envs;
+            float* row_even = p.phi + (((size_t)(env & ~1) * (Np / 16) + ci) * Np + x) * 16 + (odd ? 4 : 0);
+            float* row_odd = row_even + (size_t)Np * Np;
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {              // pixels [8 h8, 8 h8 + 8) = one sector per env
+              const float* a = ph + 8 * h8;
+              float r[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) r[k] = __shfl_xor_sync(0xffffffffu, odd ? a[k] : a[4 + k], 1);
+              // even lane: own[0..3] -> env 2i first half;  received = env 2i+1's first half
+              // odd lane : received = env 2i's second half;  own[4..7] -> env 2i+1 second half
+              if (valid_even)
+                *reinterpret_cast<float4*>(row_even + 8 * h8) = odd ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(a[0], a[1], a[2], a[3]);
+              if (valid_odd)
+                *reinterpret_cast<float4*>(row_odd + 8 * h8) = odd ? make_float4(a[4], a[5], a[6], a[7]) : make_float4(r[0], r[1], r[2], r[3]);
+            }
+          }
+          {
+            // obs arm: 16-pixel partial sums in FP32, folded into FP64 per chunk
+            float ore[NOBS], oim[NOBS];
+#pragma unroll
+            for (int v = 0; v < NOBS; ++v) ore[v] = oim[v] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float c0, s0;
+              asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(ph[j]));
+              asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(ph[j]));
+              if (mask != 0xFFFFu && !((mask >> j) & 1u)) { c0 = 0.f; s0 = 0.f; }
+#pragma unroll
+              for (int v = 0; v < NOBS; ++v) {
+                const float2 m = m1o_s[v * Np + y0 + j];
+                ore[v] = fmaf(m.x, c0, fmaf(-m.y, s0, ore[v]));
+                oim[v] = fmaf(m.x, s0, fmaf(m.y, c0, oim[v]));
+              }
+            }
+#pragma unroll
+            for (int v = 0; v < NOBS; ++v) { obs_re[v] += (double)ore[v]; obs_im[v] += (double)oim[v]; }
+          }
+          if (STREHL) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              // phase at lambda_sci = phase at lambda_wfs x (lambda_wfs / lambda_sci), exact to one fixed-point unit
+              const int32_t ts = (int32_t)(((long long)t[j] * (long long)p.sci_ratio_q32) >> 32);
+              float c0, s0;
+              sincos_fixed(ts, &s0, &c0);
+              if (mask == 0xFFFFu || ((mask >> j) & 1u)) { sre += c0; sim += s0; }
+            }
           }
         }
       }
@@ -1406,9 +1560,10 @@ int aog_tensor_create(aog_env* env) {
     A(talloc(env, &ts->lpwr, (size_t)c.num_lp_modes * env->NF2));
     A(talloc(env, &ts->coef4, ch * (size_t)c.num_lp_modes * 4));
   } else {
-    A(talloc(env, &ts->gfib, (size_t)P * FK_JT));
-    AOG_CUDA(cudaMemset(ts->gfib, 0, (size_t)P * FK_JT * sizeof(float2)));
+    A(talloc(env, &ts->gfib, (size_t)P * FK_NT(c.obs_dim)));
+    AOG_CUDA(cudaMemset(ts->gfib, 0, (size_t)P * FK_NT(c.obs_dim) * sizeof(float2)));
     A(talloc(env, &ts->fib_part, ch * (size_t)FK_SLOTS * FK_JT));
+    A(talloc(env, &ts->lpphase_f, (size_t)AOG_MAX_LP));
   }
   if (c.obs_dim > 8) AOG_FAIL(AOG_ERR_UNSUPPORTED, "tensor precision path supports obs_dim <= 8");
   ts->kpad = ((c.num_modes + 63) / 64) * 64;
@@ -1454,7 +1609,7 @@ void aog_tensor_destroy(aog_env* env) {
   if (!ts) return;
   void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->phi, ts->T_hi, ts->T_lo, ts->lpw, ts->lpwr, ts->coef4,
                   ts->hwt, ts->modesK_hi, ts->modesK_lo, ts->act_hi, ts->act_lo, ts->apmask, ts->m1o32, ts->R4,
-                  ts->m2oT, ts->err_flag, ts->gfib, ts->fib_part};
+                  ts->m2oT, ts->err_flag, ts->gfib, ts->fib_part, ts->lpphase_f};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ts;
@@ -1497,14 +1652,92 @@ int build_backprojected_modes(aog_env* env, TensorState* ts) {
   }
   if (gmax == 0.0) gmax = 1.0;
   ts->gfib_scale = gmax;
-  std::vector<float2> g((size_t)Np * Np * FK_JT, make_float2(0.f, 0.f));
-  for (int j = 0; j < J; ++j)
+  // is every G_j one unit phasor times a real function?  (true on hcipy's symmetric grids)
+  ts->g_real = true;
+  for (int j = 0; j < J; ++j) {
+    const double* g = &G[(size_t)2 * j * Np * Np];
+    size_t imax = 0;
+    double amax = 0.0;
+    for (size_t i = 0; i < (size_t)Np * Np; ++i) {
+      const double a = g[2 * i] * g[2 * i] + g[2 * i + 1] * g[2 * i + 1];
+      if (a > amax) { amax = a; imax = i; }
+    }
+    const double th = std::atan2(g[2 * imax + 1], g[2 * imax]);
+    ts->theta[j] = th;
+    const double cr = std::cos(th), sr = std::sin(th);
+    double res = 0.0;
+    for (size_t i = 0; i < (size_t)Np * Np; ++i) res = std::max(res, std::fabs(g[2 * i + 1] * cr - g[2 * i] * sr));
+    if (res > 1e-10 * std::sqrt(amax)) ts->g_real = false;
+  }
+  ts->h_G.swap(G);
+  ts->have_G = true;
+  return AOG_OK;
+}
+
+// per-pixel records of the fused kernel (TensorState::gfib), once G, the obs-arm table and the aperture are known
+int build_fused_records(aog_env* env, TensorState* ts) {
+  if (!(ts->have_G && ts->have_m1o && ts->have_ap && ts->have_lpphase)) return AOG_OK;
+  const int Np = TC_NP, J = env->cfg.num_lp_modes, n = env->cfg.obs_dim, NT = FK_NT(n);
+  // do the obs-arm rows come in conjugate pairs (real centre row)?
+  bool obs_sym = true;
+  {
+    double mx = 0.0, res = 0.0;
+    for (size_t i = 0; i < (size_t)2 * n * Np; ++i) mx = std::max(mx, std::fabs(ts->h_m1o[i]));
+    for (int v = 0; v < (n + 1) / 2; ++v)
+      for (int y = 0; y < Np; ++y) {
+        const double* a = &ts->h_m1o[2 * ((size_t)v * Np + y)];
+        const double* b = &ts->h_m1o[2 * ((size_t)(n - 1 - v) * Np + y)];
+        res = std::max(res, std::max(std::fabs(a[0] - b[0]), std::fabs(a[1] + b[1])));
+      }
+    obs_sym = res <= 1e-12 * mx;
+  }
+  ts->sym = obs_sym && ts->g_real && getenv("AOG_FUSED_GENERIC") == nullptr;
+  {
+    std::vector<double> ph((size_t)2 * AOG_MAX_LP, 0.0);
+    for (int j = 0; j < J; ++j) {
+      const double th = ts->sym ? ts->theta[j] : 0.0;
+      const double pr = ts->h_lpphase[2 * j], pi = ts->h_lpphase[2 * j + 1];
+      ph[2 * j] = pr * std::cos(th) - pi * std::sin(th);
+      ph[2 * j + 1] = pr * std::sin(th) + pi * std::cos(th);
+    }
+    AOG_CUDA(cudaMemcpy(ts->lpphase_f, ph.data(), ph.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (ts->sym) {
+    const int NF = FK_NF(n), np2 = n / 2, nc = n & 1;
+    std::vector<float> g((size_t)Np * Np * NF, 0.f);
     for (int y = 0; y < Np; ++y)
       for (int x = 0; x < Np; ++x) {
-        const size_t src = 2 * (((size_t)j * Np + y) * Np + x);
-        g[(((size_t)x * (Np / 16) + y / 16) * 16 + y % 16) * FK_JT + j] =
-            make_float2((float)(G[src] / gmax), (float)(G[src + 1] / gmax));
+        const double a = ts->h_ap[(size_t)y * Np + x] != 0.0 ? 1.0 : 0.0;
+        float* rec = &g[(((size_t)x * (Np / 16) + y / 16) * 16 + y % 16) * NF];
+        for (int v = 0; v < np2; ++v) {
+          rec[2 * v] = (float)(a * ts->h_m1o[2 * ((size_t)v * Np + y)]);
+          rec[2 * v + 1] = (float)(a * ts->h_m1o[2 * ((size_t)v * Np + y) + 1]);
+        }
+        if (nc) rec[2 * np2] = (float)(a * ts->h_m1o[2 * ((size_t)np2 * Np + y)]);
+        for (int j = 0; j < J; ++j) {
+          const size_t src = 2 * (((size_t)j * Np + y) * Np + x);
+          const double re = ts->h_G[src] * std::cos(ts->theta[j]) + ts->h_G[src + 1] * std::sin(ts->theta[j]);
+          rec[2 * np2 + nc + j] = (float)(a * re / ts->gfib_scale);
+        }
+        rec[2 * np2 + nc + FK_JT] = (float)a;
       }
+    AOG_CUDA(cudaMemcpy(ts->gfib, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ts->have_gfib = true;
+    return AOG_OK;
+  }
+  std::vector<float2> g((size_t)Np * Np * NT, make_float2(0.f, 0.f));
+  for (int y = 0; y < Np; ++y)
+    for (int x = 0; x < Np; ++x) {
+      const double a = ts->h_ap[(size_t)y * Np + x] != 0.0 ? 1.0 : 0.0;
+      float2* rec = &g[(((size_t)x * (Np / 16) + y / 16) * 16 + y % 16) * NT];
+      for (int v = 0; v < n; ++v)
+        rec[v] = make_float2((float)(a * ts->h_m1o[2 * ((size_t)v * Np + y)]), (float)(a * ts->h_m1o[2 * ((size_t)v * Np + y) + 1]));
+      for (int j = 0; j < J; ++j) {
+        const size_t src = 2 * (((size_t)j * Np + y) * Np + x);
+        rec[n + j] = make_float2((float)(a * ts->h_G[src] / ts->gfib_scale), (float)(a * ts->h_G[src + 1] / ts->gfib_scale));
+      }
+      rec[n + FK_JT] = make_float2((float)a, 0.f);
+    }
   AOG_CUDA(cudaMemcpy(ts->gfib, g.data(), g.size() * sizeof(float2), cudaMemcpyHostToDevice));
   ts->have_gfib = true;
   return AOG_OK;
@@ -1515,12 +1748,22 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
   TensorState* ts = TS(env);
   const aog_config& c = env->cfg;
   const int Np = TC_NP, Nf = TC_NF;
+  if (ts->fused && which == AOG_TABLE_LP_PHASE) {
+    const double* m = static_cast<const double*>(host);
+    ts->h_lpphase.assign(m, m + (size_t)2 * c.num_lp_modes);
+    ts->have_lpphase = true;
+    return build_fused_records(env, ts);
+  }
   if (ts->fused && (which == AOG_TABLE_MFT_FIB_1 || which == AOG_TABLE_MFT_FIB_2 || which == AOG_TABLE_LP_MODES_W)) {
     const double* m = static_cast<const double*>(host);
     if (which == AOG_TABLE_MFT_FIB_1) { ts->h_m1.assign(m, m + (size_t)2 * Nf * Np); ts->have_m1 = true; }
     if (which == AOG_TABLE_MFT_FIB_2) { ts->h_m2.assign(m, m + (size_t)2 * Np * Nf); ts->have_m2 = true; }
     if (which == AOG_TABLE_LP_MODES_W) { ts->h_lp.assign(m, m + (size_t)c.num_lp_modes * env->NF2); ts->have_lp = true; }
-    if (ts->have_m1 && ts->have_m2 && ts->have_lp) return build_backprojected_modes(env, ts);
+    if (ts->have_m1 && ts->have_m2 && ts->have_lp) {
+      int rc = build_backprojected_modes(env, ts);
+      if (rc) return rc;
+      return build_fused_records(env, ts);
+    }
     return AOG_OK;
   }
   if (which == AOG_TABLE_MFT_FIB_1) {
@@ -1603,12 +1846,14 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
         if (m[(size_t)y * Np + x] != 0.0) bits[(size_t)x * (Np / 16) + y / 16] |= (uint16_t)(1u << (y % 16));
     AOG_CUDA(cudaMemcpy(ts->apmask, bits.data(), bits.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     ts->have_ap = true;
+    if (ts->fused) { ts->h_ap.assign(m, m + (size_t)Np * Np); return build_fused_records(env, ts); }
   } else if (which == AOG_TABLE_MFT_OBS_1) {
     const double* m = static_cast<const double*>(host);   // [n][Np] complex
     std::vector<float2> f((size_t)c.obs_dim * Np);
     for (size_t i = 0; i < f.size(); ++i) f[i] = make_float2((float)m[2 * i], (float)m[2 * i + 1]);
     AOG_CUDA(cudaMemcpy(ts->m1o32, f.data(), f.size() * sizeof(float2), cudaMemcpyHostToDevice));
     ts->have_m1o = true;
+    if (ts->fused) { ts->h_m1o.assign(m, m + (size_t)2 * c.obs_dim * Np); return build_fused_records(env, ts); }
   } else if (which == AOG_TABLE_MFT_OBS_2) {
     const double* m = static_cast<const double*>(host);   // [Np][n] complex -> [n][Np]
     const int n = c.obs_dim;
@@ -1693,31 +1938,32 @@ int aog_tensor_check(aog_env* env) {
 }
 
 namespace {
-template <bool STREHL, int NOBS, bool FUSED>
+template <bool STREHL, int NOBS, int MODE>
 int launch_phase(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
-  const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES + 1024 + FK_AUX_BAR +
+  constexpr bool FUSED = MODE != 0;
+  const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES(NOBS, MODE) + 1024 + FK_AUX_BAR +
                    (FUSED ? 1 + FK_JT : 1) * FK_PARTS * 128 * (int)sizeof(double2) +
-                   NOBS * TC_NP * (int)sizeof(float2) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
+                   (FUSED ? 0 : NOBS * TC_NP * (int)sizeof(float2)) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
   static bool configured = false;
   if (!configured) {
-    AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  k_dm_phase_tc<STREHL, NOBS, FUSED><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
+  k_dm_phase_tc<STREHL, NOBS, MODE><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
   AOG_LAUNCH_CHECK();
   return AOG_OK;
 }
-template <bool STREHL, bool FUSED>
+template <bool STREHL, int MODE>
 int launch_phase_n(aog_env* env, TensorState* ts, const FieldParams& p, int n, int grid, cudaStream_t st) {
   switch (n) {
-    case 1: return launch_phase<STREHL, 1, FUSED>(env, ts, p, grid, st);
-    case 2: return launch_phase<STREHL, 2, FUSED>(env, ts, p, grid, st);
-    case 3: return launch_phase<STREHL, 3, FUSED>(env, ts, p, grid, st);
-    case 4: return launch_phase<STREHL, 4, FUSED>(env, ts, p, grid, st);
-    case 5: return launch_phase<STREHL, 5, FUSED>(env, ts, p, grid, st);
-    case 6: return launch_phase<STREHL, 6, FUSED>(env, ts, p, grid, st);
-    case 7: return launch_phase<STREHL, 7, FUSED>(env, ts, p, grid, st);
-    case 8: return launch_phase<STREHL, 8, FUSED>(env, ts, p, grid, st);
+    case 1: return launch_phase<STREHL, 1, MODE>(env, ts, p, grid, st);
+    case 2: return launch_phase<STREHL, 2, MODE>(env, ts, p, grid, st);
+    case 3: return launch_phase<STREHL, 3, MODE>(env, ts, p, grid, st);
+    case 4: return launch_phase<STREHL, 4, MODE>(env, ts, p, grid, st);
+    case 5: return launch_phase<STREHL, 5, MODE>(env, ts, p, grid, st);
+    case 6: return launch_phase<STREHL, 6, MODE>(env, ts, p, grid, st);
+    case 7: return launch_phase<STREHL, 7, MODE>(env, ts, p, grid, st);
+    case 8: return launch_phase<STREHL, 8, MODE>(env, ts, p, grid, st);
   }
   AOG_FAIL(AOG_ERR_UNSUPPORTED, "obs_dim");
 }
@@ -1760,8 +2006,9 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       int rc;
       if (strehl) AOG_CUDA(cudaMemsetAsync(env->strehl_part, 0, (size_t)nB * FK_SLOTS * sizeof(double2), st));
       if (fused) AOG_CUDA(cudaMemsetAsync(ts->fib_part, 0, (size_t)nB * FK_SLOTS * FK_JT * sizeof(double2), st));
-      if (fused) rc = strehl ? launch_phase_n<true, true>(env, ts, fp, n, grid, st) : launch_phase_n<false, true>(env, ts, fp, n, grid, st);
-      else       rc = strehl ? launch_phase_n<true, false>(env, ts, fp, n, grid, st) : launch_phase_n<false, false>(env, ts, fp, n, grid, st);
+      if (fused && ts->sym) rc = strehl ? launch_phase_n<true, 2>(env, ts, fp, n, grid, st) : launch_phase_n<false, 2>(env, ts, fp, n, grid, st);
+      else if (fused)       rc = strehl ? launch_phase_n<true, 1>(env, ts, fp, n, grid, st) : launch_phase_n<false, 1>(env, ts, fp, n, grid, st);
+      else                  rc = strehl ? launch_phase_n<true, 0>(env, ts, fp, n, grid, st) : launch_phase_n<false, 0>(env, ts, fp, n, grid, st);
       if (rc) return rc;
     }
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->ev0, st)); }
@@ -1808,7 +2055,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       a.coef_scale = make_double2(c.mft_norm_re * sc, c.mft_norm_im * sc);
       a.coef_is_raw = fused ? 3 : 2;
       a.fib_part = ts->fib_part; a.fib_slots = FK_SLOTS; a.fib_stride = FK_JT;
-    } a.coef = nullptr; a.coef4 = ts->coef4; a.lpphase = env->t_lpphase; a.lpgram = env->t_lpgram;
+    } a.coef = nullptr; a.coef4 = ts->coef4; a.lpphase = fused ? ts->lpphase_f : env->t_lpphase; a.lpgram = env->t_lpgram;
     a.strehl_part = env->strehl_part; a.strehl_blocks = FK_SLOTS;
     a.Np = Np; a.n = n; a.J = J; a.rew_type = c.rew_type; a.has_thr = c.has_rew_threshold;
     a.compute_reward = with_reward ? 1 : 0;
