@@ -556,13 +556,19 @@ int aog_step(aog_env* env, const void* actions_dev, int act_dtype, const double*
   // AO_env.py:115-120
   const size_t shm = (size_t)(K + 32) * sizeof(double);
   const double target = 0.1 * c.wavelength_sci;
-  if (act_dtype == AOG_DTYPE_F32)
-    k_actuators<float><<<B, 128, shm, st>>>((const float*)actions_dev, env->t_gram, env->act, K, c.sh_operation, target);
-  else if (act_dtype == AOG_DTYPE_F64)
-    k_actuators<double><<<B, 128, shm, st>>>((const double*)actions_dev, env->t_gram, env->act, K, c.sh_operation, target);
-  else
-    AOG_FAIL(AOG_ERR_INVALID, "act_dtype");
-  AOG_LAUNCH_CHECK();
+  if (act_dtype != AOG_DTYPE_F32 && act_dtype != AOG_DTYPE_F64) AOG_FAIL(AOG_ERR_INVALID, "act_dtype");
+  int arc = AOG_ERR_UNSUPPORTED;
+  if (c.precision != AOG_PRECISION_F64) {
+    arc = aog_tensor_actuators(env, actions_dev, act_dtype, st);
+    if (arc != AOG_OK && arc != AOG_ERR_UNSUPPORTED) return arc;
+  }
+  if (arc != AOG_OK) {
+    if (act_dtype == AOG_DTYPE_F32)
+      k_actuators<float><<<B, 128, shm, st>>>((const float*)actions_dev, env->t_gram, env->act, K, c.sh_operation, target);
+    else
+      k_actuators<double><<<B, 128, shm, st>>>((const double*)actions_dev, env->t_gram, env->act, K, c.sh_operation, target);
+    AOG_LAUNCH_CHECK();
+  }
   // AO_env.py:123-125
   const int64_t old_t = env->cnt.timestep;
   env->cnt.timestep += 1;

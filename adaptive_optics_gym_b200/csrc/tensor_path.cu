@@ -71,6 +71,7 @@ struct TensorState {
   // fibre modes propagated back to the pupil, G_j = M1^T (mode_j w) M2^T / max|G| | (aperture, 0)], all times the
   // aperture: the 16 records of a column chunk are one contiguous run for the bulk prefetch
   bool fused = false;
+  bool packed_valid = false;                          // act_hi / act_lo already hold this step's actuators (k_actuators_pack)
   float2* gfib = nullptr;
   double gfib_scale = 0.0;
   double2* fib_part = nullptr;                        // [chunk][FK_SLOTS][FK_JT] partial projection sums
@@ -1407,6 +1408,49 @@ k_field_mft1(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   }
 }
 
+// Action -> actuators (AO_env.py:115-120) with the GEMM A operand written in the same pass: one warp per env, the
+// Gram matrix of the modes (var(M a) = a^T G a, np.std over the whole grid) staged once per block in shared memory
+// and read transposed (G is symmetric) so that lanes hit consecutive banks.  a_hi / a_lo rows >= B and columns
+// >= K stay zero from allocation.
+template <typename ActT>
+__global__ void __launch_bounds__(256)
+k_actuators_pack(const ActT* __restrict__ actions, const double* __restrict__ gram, double* __restrict__ act,
+                 __half* __restrict__ a_hi, __half* __restrict__ a_lo, int B, int K, int kpad, int sh_operation,
+                 double target_rms, double pack_scale) {
+  extern __shared__ double sh_g[];                     // [K][K] Gram + [8 warps][K] actions
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* A = sh_g + (size_t)K * K + warp * K;
+  if (!sh_operation)
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) sh_g[i] = gram[i];
+  __syncthreads();
+  for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
+    for (int k = lane; k < K; k += 32) {
+      const double a = (double)actions[(size_t)b * K + k];
+      A[k] = sh_operation ? a : a / (double)(k + 10);
+    }
+    __syncwarp();
+    double scale = 1.0;
+    if (!sh_operation) {
+      double part = 0.0;
+      for (int i = lane; i < K; i += 32) {
+        double r = 0.0;
+        for (int j = 0; j < K; ++j) r += sh_g[(size_t)j * K + i] * A[j];
+        part += A[i] * r;
+      }
+      scale = target_rms / sqrt(warp_sum(part));       // var == 0 -> inf -> 0 * inf = NaN (reference semantics)
+    }
+    for (int k = lane; k < K; k += 32) {
+      const double v = A[k] * scale;
+      act[(size_t)b * K + k] = v;
+      const double w = v * pack_scale;
+      const __half h = __float2half_rn((float)w);
+      a_hi[(size_t)b * kpad + k] = h;
+      a_lo[(size_t)b * kpad + k] = __float2half_rn((float)(w - (double)__half2float(h)));
+    }
+    __syncwarp();
+  }
+}
+
 // actuators (FP64, after normalisation) -> GEMM A operand: half-turn scale, split fp16, zero padded
 __global__ void k_act_pack(const double* __restrict__ act, __half* __restrict__ a_hi, __half* __restrict__ a_lo,
                            int K, int kpad, int env0, int nB, int rows, double scale) {
@@ -1577,6 +1621,8 @@ int aog_tensor_create(aog_env* env) {
   A(talloc(env, &ts->modesK_lo, P * ts->kpad));
   A(talloc(env, &ts->act_hi, (size_t)ts->act_rows * ts->kpad));
   A(talloc(env, &ts->act_lo, (size_t)ts->act_rows * ts->kpad));
+  AOG_CUDA(cudaMemset(ts->act_hi, 0, (size_t)ts->act_rows * ts->kpad * sizeof(__half)));
+  AOG_CUDA(cudaMemset(ts->act_lo, 0, (size_t)ts->act_rows * ts->kpad * sizeof(__half)));
   A(talloc(env, &ts->apmask, (size_t)TC_NP * (TC_NP / 16)));
   A(talloc(env, &ts->m1o32, (size_t)c.obs_dim * TC_NP));
   A(talloc(env, &ts->R4, ch * TC_NP * FK_PARTS * c.obs_dim));
@@ -1928,6 +1974,27 @@ int aog_tensor_get_field(aog_env* env, int which, int env_in_chunk, double* host
   return AOG_OK;
 }
 
+// AO_env.py:115-120 for every env, with the DM-GEMM operand packed in the same kernel.  Returns AOG_ERR_UNSUPPORTED
+// (and launches nothing) when the handle runs more than one chunk or the Gram matrix does not fit shared memory.
+int aog_tensor_actuators(aog_env* env, const void* actions_dev, int act_dtype, cudaStream_t st) {
+  TensorState* ts = TS(env);
+  const aog_config& c = env->cfg;
+  const int B = c.num_envs, K = c.num_modes;
+  const size_t shm = ((size_t)K * K + 8 * (size_t)K) * sizeof(double);
+  if (!ts || B > env->chunk || shm > 48 * 1024) return AOG_ERR_UNSUPPORTED;
+  const int grid = std::min(cdiv(B, 8), 4 * ts->num_sms);
+  const double target = 0.1 * c.wavelength_sci, pscale = 4.0 / c.wavelength_wfs;
+  if (act_dtype == AOG_DTYPE_F32)
+    k_actuators_pack<float><<<grid, 256, shm, st>>>((const float*)actions_dev, env->t_gram, env->act, ts->act_hi, ts->act_lo,
+                                                    B, K, ts->kpad, c.sh_operation, target, pscale);
+  else
+    k_actuators_pack<double><<<grid, 256, shm, st>>>((const double*)actions_dev, env->t_gram, env->act, ts->act_hi,
+                                                     ts->act_lo, B, K, ts->kpad, c.sh_operation, target, pscale);
+  AOG_LAUNCH_CHECK();
+  ts->packed_valid = true;
+  return AOG_OK;
+}
+
 int aog_tensor_check(aog_env* env) {
   TensorState* ts = TS(env);
   if (!ts) return AOG_OK;
@@ -1986,9 +2053,12 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     {
       // actuators -> half-turns of DM phase per unit mode (2 k s / pi = 4 s / lambda), split fp16
       const int rows = cdiv(nB, 128) * 128;
-      k_act_pack<<<cdiv(rows * ts->kpad, 256), 256, 0, st>>>(env->act, ts->act_hi, ts->act_lo, K, ts->kpad, e0, nB,
-                                                             rows, 4.0 / c.wavelength_wfs);
-      AOG_LAUNCH_CHECK();
+      if (!ts->packed_valid) {
+        k_act_pack<<<cdiv(rows * ts->kpad, 256), 256, 0, st>>>(env->act, ts->act_hi, ts->act_lo, K, ts->kpad, e0, nB,
+                                                               rows, 4.0 / c.wavelength_wfs);
+        AOG_LAUNCH_CHECK();
+      }
+      ts->packed_valid = false;                      // good for the one optics pass that follows k_actuators_pack
       FieldParams fp{};
       fp.num_envs = nB;
       fp.num_items = cdiv(nB, 128) * Np;
@@ -2069,7 +2139,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     a.power = out.power ? out.power + e0 : nullptr;
     a.strehl = out.strehl ? out.strehl + e0 : nullptr;
     a.ssim = out.ssim ? out.ssim + e0 : nullptr;
-    k_finalize<<<nB, 128, 0, st>>>(a);
+    k_finalize_tc<<<nB, 128, (size_t)Np * n * sizeof(double2), st>>>(a);
     AOG_LAUNCH_CHECK();
   }
   return AOG_OK;

@@ -124,7 +124,12 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    # K "steps", each a bounded sample of the workload: one full episode of the single CPU env
+    # K "steps", each a bounded sample of the workload: one full episode of the single CPU env.
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is to use every host thread it can
+    # (rank 0 alone runs), so the BLAS pool is sized before NumPy loads.
+    threads = os.environ.get('AOG_REF_THREADS', str(os.cpu_count()))
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[k] = threads
     import numpy as np
     from oracle.ao_oracle import OracleAOEnv
     w = WORKLOADS[args.workload]
@@ -144,7 +149,7 @@ def run_reference(args):
         episode()
     dt = time.perf_counter() - t0
     v = args.steps * T / dt
-    cores = os.cpu_count()
+    cores = int(threads)
     line = {
         'impl': 'reference', 'metric': 'env-steps/sec', 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
@@ -153,7 +158,7 @@ def run_reference(args):
                    'note': 'reference arm = single CPU env (the reference has no batching); one bench step = one '
                            f'{T}-step episode incl. reset'},
         'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{args.steps} episodes x {T} steps of one env, NumPy/OpenBLAS default threads '
+                         'sample': f'{args.steps} episodes x {T} steps of one env, NumPy/OpenBLAS with {cores} threads '
                                    '(hcipy==0.5.1 is not installable here: oracle port, unabridged op sequence)'},
         'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }

@@ -82,3 +82,56 @@ def test_gather_episode_stats_single_process():
     from adaptive_optics_gym_b200.sharding import gather_episode_stats
     st = gather_episode_stats(torch.tensor([1.0, 2.0, 3.0]))
     assert st == dict(count=3, mean=2.0, std=pytest.approx((2 / 3) ** 0.5), min=1.0, max=3.0)
+
+
+class _FakeVecEnv:
+    """CPU stand-in with AOVecEnv's interface: obs = [env id, step counter], reward = -(step + env / 100)."""
+
+    def __init__(self, B=3, T=4, K=2):
+        import torch
+        from adaptive_optics_gym_b200._gym_compat import spaces
+        self.num_envs, self.max_steps, self.device, self.SH_operation = B, T, torch.device('cpu'), False
+        self.single_observation_space = spaces.Box(low=-1, high=1, shape=(2,), dtype=np.float16)
+        self.single_action_space = spaces.Box(low=-1, high=1, shape=(K,), dtype=np.float16)
+        self.t = 0
+
+    def _obs(self):
+        import torch
+        return torch.stack([torch.arange(self.num_envs, dtype=torch.float16),
+                            torch.full((self.num_envs,), float(self.t), dtype=torch.float16)], dim=1)
+
+    def reset(self):
+        self.t = 0
+        return self._obs(), {}
+
+    def step(self, actions):
+        import torch
+        assert actions.shape == (self.num_envs, self.single_action_space.shape[0])
+        rew = -(self.t + torch.arange(self.num_envs, dtype=torch.float64) / 100)
+        self.t += 1
+        done = torch.full((self.num_envs,), self.t == self.max_steps)
+        return self._obs(), rew, done, torch.zeros(self.num_envs, dtype=torch.bool), {'power': rew}
+
+
+def test_vec_rollout_collector_layout_matches_reference_rollout():
+    """the seven fields of algorithm.py:216-296, each env's episode a contiguous run of T rows"""
+    import torch
+    from adaptive_optics_gym_b200.rollout import VecRolloutCollector
+    env = _FakeVecEnv(B=3, T=4, K=2)
+    policy = lambda o: (o[:, :1].repeat(1, 2) * 0.5, -o[:, 1])        # action from the env id, log-prob from the step
+    col = VecRolloutCollector(env, policy)
+    obs, act, logp, rew, nxt, done, lens = col.rollout(episodes_per_iteration=2)
+    N = 2 * 3 * 4
+    assert obs.shape == (N, 2) and act.shape == (N, 2) and logp.shape == (N,) and rew.shape == (N,)
+    assert nxt.shape == (N, 2) and done.shape == (N,) and lens.shape == (6,) and torch.all(lens == 4)
+    rows = obs.reshape(2, 3, 4, 2)
+    for e in range(2):
+        for b in range(3):
+            assert torch.all(rows[e, b, :, 0] == b) and rows[e, b, :, 1].tolist() == [0, 1, 2, 3]
+    assert torch.all(nxt.reshape(2, 3, 4, 2)[..., 1] == torch.tensor([1., 2., 3., 4.]))
+    assert torch.all(done.reshape(2, 3, 4)[..., :3] == 0) and torch.all(done.reshape(2, 3, 4)[..., 3] == 1)
+    assert torch.allclose(act.reshape(2, 3, 4, 2)[0, 2], torch.full((4, 2), 1.0))
+    assert torch.allclose(col.episode_returns(), torch.tensor([-6.0, -6.04, -6.08] * 2))
+    assert col.num_episodes == 6
+    with pytest.raises(ValueError):
+        VecRolloutCollector(env, None)

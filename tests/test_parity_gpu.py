@@ -346,3 +346,31 @@ def test_vec_env_shack_hartmann_matches_single():
             break                             # only env 0 shares env_id_base with its single twin
     for e in [vec] + singles:
         e.close()
+
+
+def test_vec_rollout_collector_on_device_matches_stepwise_fused_and_f64():
+    """VecRolloutCollector on AOVecEnv: the batch is what stepping the env by hand gives, rows ordered
+    (episode, env, step); the fused path's rewards agree with the FP64 path's within 1e-5."""
+    import torch
+    from adaptive_optics_gym_b200 import AOVecEnv
+    from adaptive_optics_gym_b200.rollout import VecRolloutCollector
+    B, T = 5, 3
+    kw = dict(atm_fried=0.20, act_dim=64, obs_dim=2, rew_type='strehl_ratio', timesteps_per_episode=T)
+    scr = np.stack([_screen(40 + i, r0=0.20) for i in range(B)])
+    g = torch.Generator(device='cpu').manual_seed(0)
+    W = torch.randn(4, 64, generator=g).cuda()
+    policy = lambda o: (torch.tanh(o @ W), -(o ** 2).sum(dim=1))
+    out = {}
+    for precision in ('f64', 'fused'):
+        env = AOVecEnv(B, **kw, initial_screens=scr, precision=precision)
+        col = VecRolloutCollector(env, policy)
+        out[precision] = [x.clone() for x in col.rollout(episodes_per_iteration=2)]
+        assert col.num_episodes == 2 * B and col.batch_ep_rew.shape == (2 * B, T)
+        env.close()
+    obs, act, logp, rew, nxt, done, lens = out['f64']
+    N = 2 * B * T
+    assert obs.shape == (N, 4) and act.shape == (N, 64) and rew.shape == (N,) and lens.tolist() == [T] * (2 * B)
+    assert obs.is_cuda and torch.equal(done.reshape(2, B, T)[..., -1], torch.ones(2, B, device='cuda'))
+    # next_obs of step t is obs of step t + 1 within an episode
+    assert torch.equal(nxt.reshape(2, B, T, 4)[:, :, :-1], obs.reshape(2, B, T, 4)[:, :, 1:])
+    _close(out['fused'][3].cpu().numpy(), rew.cpu().numpy(), 1e-5, 'fused rollout rewards vs f64')
