@@ -531,8 +531,13 @@ constexpr int FK_EPI_WARPS = AOG_FK_EPI_WARPS;          // 3 per TMEM lane group
 constexpr int FK_PARTS = FK_EPI_WARPS / 4;
 // Work item -> pupil column: a CTA's contiguous item range strides through the pupil (53 is coprime with 240), so
 // every CTA sees the same mix of short (edge) and long (centre) aperture chords.
+// (The tensor path's phase kernel keeps the natural order: its phase stores of neighbouring columns are neighbours
+// in HBM, and striding them costs more DRAM page misses than the imbalance does.)
 constexpr int FK_COL_STRIDE = 53;
-__device__ __forceinline__ int fk_column(int item_in_block) { return (item_in_block * FK_COL_STRIDE) % TC_NP; }
+template <int MODE>
+__device__ __forceinline__ int fk_column(int item_in_block) {
+  return MODE == 0 ? item_in_block : (item_in_block * FK_COL_STRIDE) % TC_NP;
+}
 constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
 constexpr int FK_SLOTS = 16;                            // Strehl partial slots per env (>= CTAs touching an env block)
 constexpr int FK_MIN_ITEMS = 16;                        // items per CTA at least (bounds the slots)
@@ -697,7 +702,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int item = item_lo; item < item_hi; ++item) {
-        const int eb = item / Np, x = fk_column(item - eb * Np);
+        const int eb = item / Np, x = fk_column<MODE>(item - eb * Np);
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait<200>(&empty[stage], phase ^ 1, p.err_flag, 11);
           mbar_expect_tx(&full[stage], TX_BYTES);
@@ -781,7 +786,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       while (n_ci >= n_end) {
         n_base = (n_base + n_cnt) % FK_PARTS;
         if (++n_item >= item_hi) return false;
-        n_x = fk_column(n_item - (n_item / Np) * Np);
+        n_x = fk_column<MODE>(n_item - (n_item / Np) * Np);
         n_cnt = run_s[2 * n_x + 1];
         n_ci = run_s[2 * n_x] + (q + FK_PARTS - n_base) % FK_PARTS;
         n_end = run_s[2 * n_x] + n_cnt;
@@ -846,7 +851,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
     };
 
     for (int item = item_lo; item < item_hi; ++item, ++it) {
-      const int eb = item / Np, x = fk_column(item - eb * Np);
+      const int eb = item / Np, x = fk_column<MODE>(item - eb * Np);
       if ((STREHL || FUSED) && eb != cur_eb) {
         if (cur_eb >= 0) flush_strehl(cur_eb);
         cur_eb = eb;
