@@ -63,14 +63,23 @@ int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long
                                     flipped, c.sqrt_cn2, noise_stride, c.seed, (unsigned long long)c.env_id_base,
                                     (unsigned long long)env->cnt.extrusions);
     AOG_LAUNCH_CHECK();
-    dim3 g2(cdiv(Np, 64), cdiv(nB, 64));
-    k_dgemm<<<g2, 256, 0, st>>>(env->arZ, env->t_arW, env->arNew, nB, Np, Ns + Np, Ns + Np, Np, Np);
-    AOG_LAUNCH_CHECK();
-    dim3 g3(cdiv(Np, 128), nB);
-    k_ar_scatter<<<g3, 128, 0, st>>>(env->screens, env->arNew, env->P, Np, e0, phys, flipped);
+    static const bool split = getenv("AOG_AR_SPLIT") != nullptr;     // tuning: the three-kernel form
+    if (split) {
+      dim3 g2(cdiv(Np, 64), cdiv(nB, 64));
+      k_dgemm<<<g2, 256, 0, st>>>(env->arZ, env->t_arW, env->arNew, nB, Np, Ns + Np, Ns + Np, Np, Np);
+      AOG_LAUNCH_CHECK();
+      dim3 g3(cdiv(Np, 128), nB);
+      k_ar_scatter<<<g3, 128, 0, st>>>(env->screens, env->arNew, env->P, Np, e0, phys, flipped);
+      AOG_LAUNCH_CHECK();
+      continue;
+    }
+    // GEMM with the scatter into the ring slot (and the phase-tile refresh of the tensor / fused paths) in its epilogue
+    dim3 g2(cdiv(Np, 64), cdiv(nB, 128));
+    k_ar_step<<<g2, 256, 0, st>>>(env->arZ, env->t_arW, env->screens, env->phase_tiles, nB, Np, Ns + Np, env->P, e0, phys,
+                                  flipped, 1.0 / (c.wavelength_wfs * 3.14159265358979323846), env->phase_tiles_unit);
     AOG_LAUNCH_CHECK();
   }
-  if (c.precision != AOG_PRECISION_F64) {
+  if (getenv("AOG_AR_SPLIT") != nullptr && c.precision != AOG_PRECISION_F64) {
     int rc = aog_tensor_column_updated(env, phys, st);
     if (rc) return rc;
   }

@@ -84,6 +84,8 @@ struct aog_env {
   int64_t launches = 0;
   int64_t screen_draws = 0;        // von-Karman syntheses so far (Philox offset domain)
   void* tensor_state = nullptr;     // TensorState (tensor_path.cu) when precision == TENSOR
+  int32_t* phase_tiles = nullptr;   // TensorState::hwt (tiled fixed-point phase) for k_ar_step's epilogue, else null
+  double phase_tiles_unit = 0.0;    // fixed-point units per half-turn (PHI_ONE)
   cudaStream_t own_stream = nullptr;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evf = nullptr, evm = nullptr;   // evf: before the field kernel, evm: between the MFT stages

@@ -532,6 +532,101 @@ static __global__ void k_ar_gather(const double* __restrict__ screens, const int
   Z[(size_t)b * (Ns + Np) + j] = v;
 }
 
+// new column = Z . W (hcipy _extrude: A z + B xi for every env) on the FP64 tensor cores, with the scatter into the
+// ring-buffered screens -- and, for the tensor / fused paths, the refresh of that column's fixed-point phase tiles --
+// in the epilogue.  mma.sync.m8n8k4.f64 (DMMA) sustains 36 TFLOP/s on B200 with 4-8 warps per SM where scalar DFMA
+// needs 16+ warps of 32 independent chains for 31 (tools/micro/dmma_bench.cu), and it issues 8x fewer instructions,
+// which leaves the slots for the operand traffic.  Block tile 128 envs x 64 pixels, K step 8, 8 warps as 4 x 2, warp
+// tile 32 x 32 = 4 x 4 fragments; shared-memory rows padded by 4 doubles so that a fragment load (4 k rows x 8
+// consecutive m or n) touches every bank once; next tile prefetched in registers with volatile 16-byte loads.
+//   screens[(env0 + b) P + y Np + phys_col] = new[b][flipped ? Np - 1 - y : y]
+//   tiles (TensorState::hwt layout) [env / 32][phys_col][y / 16][env % 32][piece][y % 4] = fixed(new / (lambda_wfs pi))
+static __global__ void __launch_bounds__(256)
+k_ar_step(const double* __restrict__ Z, const double* __restrict__ W, double* __restrict__ screens,
+          int32_t* __restrict__ tiles, int nB, int Np, int Kd, int P, int env0, int phys_col, int flipped,
+          double inv_w, double phi_one) {
+  constexpr int TM = 128, TN = 64, TK = 8, LDA = TM + 4, LDB = TN + 4;
+  __shared__ __align__(16) double As[2][TK][LDA];
+  __shared__ __align__(16) double Bs[2][TK][LDB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;      // warp tile origin inside the block tile
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  // loader roles: A row m0 + t / 2, 4 k's;  B row k = t / 32, 2 n's
+  const int am = threadIdx.x >> 1, ak = (threadIdx.x & 1) * 4;
+  const int bk = threadIdx.x >> 5, bn = (threadIdx.x & 31) * 2;
+  const bool a_ok = m0 + am < nB, b_ok = n0 + bn < Np;
+  const double* a_src = Z + (size_t)(m0 + am) * Kd + ak;
+  const double* b_src = W + (size_t)bk * Np + n0 + bn;
+  // Operand prefetch as volatile 16-byte loads: issued a whole K step of MMAs ahead of their use (left to itself the
+  // compiler sinks them next to the shared-memory stores and the warp waits out the L2 round trip).  Kd and Np are
+  // even and every row starts 16-byte aligned, so a pair never straddles the edge.
+  double ra[4], rb[2];
+  auto ld2 = [](const double* p, bool ok, double& x, double& y) {
+    x = 0.0; y = 0.0;
+    if (ok) asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
+  };
+  auto load = [&](int k0) {
+    ld2(a_src + k0, a_ok && k0 + ak < Kd, ra[0], ra[1]);
+    ld2(a_src + k0 + 2, a_ok && k0 + ak + 2 < Kd, ra[2], ra[3]);
+    ld2(b_src + (size_t)k0 * Np, b_ok && k0 + bk < Kd, rb[0], rb[1]);
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[buf][ak + i][am] = ra[i];
+    *reinterpret_cast<double2*>(&Bs[buf][bk][bn]) = make_double2(rb[0], rb[1]);
+  };
+  double acc[4][4][2] = {};
+  load(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < Kd; k0 += TK) {
+    const bool more = k0 + TK < Kd;
+    if (more) load(k0 + TK);
+#pragma unroll
+    for (int k4 = 0; k4 < TK; k4 += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[buf][k4 + tig][wm + 8 * i + gid];     // A fragment: row gid, column (k) tig
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][k4 + tig][wn + 8 * j + gid];     // B fragment: row (k) tig, column gid
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // C fragment: row gid, columns 2 tig + {0, 1}
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = m0 + wm + 8 * i + gid;
+    if (b >= nB) continue;
+    const size_t env = (size_t)env0 + b;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const int n = n0 + wn + 8 * j + 2 * tig + e2;
+        if (n >= Np) continue;
+        const int y = flipped ? Np - 1 - n : n;
+        const double S = acc[i][j][e2];
+        screens[env * P + (size_t)y * Np + phys_col] = S;
+        if (tiles) {
+          double f = S * inv_w * phi_one;
+          f = fmin(fmax(f, -2147483000.0), 2147483000.0);
+          const int l = (int)(env & 31), ci = y >> 4, piece = ((y >> 2) & 3) ^ ((l >> 1) & 3), e = y & 3;
+          const size_t tile = (((env >> 5) * Np + phys_col) * (size_t)(Np / 16) + ci) * 512;
+          tiles[tile + (size_t)l * 16 + piece * 4 + e] = (int32_t)__double2ll_rn(f);
+        }
+      }
+  }
+}
+
 static __global__ void k_ar_scatter(double* __restrict__ screens, const double* __restrict__ newcol, int P, int Np,
                              int env0, int phys_col, int flipped) {
   const int b = blockIdx.y;

@@ -1621,6 +1621,8 @@ int aog_tensor_create(aog_env* env) {
     const size_t tiles = ((B + 127) / 128) * 4 * TC_NP * (TC_NP / 16);   // whole 128-env blocks: the prefetch reads them all
     A(talloc(env, &ts->hwt, tiles * 512));
     AOG_CUDA(cudaMemset(ts->hwt, 0, tiles * 512 * sizeof(int32_t)));
+    env->phase_tiles = ts->hwt;
+    env->phase_tiles_unit = (double)PHI_ONE;
   }
   A(talloc(env, &ts->modesK_hi, P * ts->kpad));
   A(talloc(env, &ts->modesK_lo, P * ts->kpad));
