@@ -374,3 +374,51 @@ def test_vec_rollout_collector_on_device_matches_stepwise_fused_and_f64():
     # next_obs of step t is obs of step t + 1 within an episode
     assert torch.equal(nxt.reshape(2, B, T, 4)[:, :, :-1], obs.reshape(2, B, T, 4)[:, :, 1:])
     _close(out['fused'][3].cpu().numpy(), rew.cpu().numpy(), 1e-5, 'fused rollout rewards vs f64')
+
+
+@pytest.mark.parametrize('precision', ['fused', 'tensor'])
+def test_full_size_batch_properties(precision):
+    """BASELINE.json's full batch (4096 envs on one B200) through size-independent properties:
+    * replication: env i carries screen i % 8 and action i % 8, so all 512 copies of a case must return the SAME
+      observation / reward / power, and the 8 distinct cases must agree with an 8-env run of the FP64 path (1e-5);
+    * a flat wavefront with a flat mirror (case 0 at reset) gives four equal detector pixels, identical over copies;
+    * only the direction of an action matters (AO_env.py:119-120): scaling a row by a positive constant is a no-op."""
+    import torch
+    from adaptive_optics_gym_b200 import AOVecEnv
+    B, R = 4096, 8
+    kw = dict(atm_fried=0.20, act_dim=64, obs_dim=2, rew_type='strehl_ratio', timesteps_per_episode=4)
+    scr = np.stack([_screen(60 + i, r0=0.20) for i in range(R)])
+    scr[0] = 0.0                                                   # case 0: flat wavefront
+    rng = np.random.default_rng(9)
+    acts = rng.uniform(-1, 1, (3, R, 64)).astype(np.float32)
+    big = AOVecEnv(B, **kw, initial_screens=np.tile(scr, (B // R, 1)), precision=precision)
+    ref = AOVecEnv(R, **kw, initial_screens=scr, precision='f64')
+    big.reset()
+    ref.reset()
+    scale = torch.linspace(0.5, 3.0, B // R, device='cuda').repeat_interleave(R).unsqueeze(1)   # per-copy action scale
+    for t in range(3):
+        a = torch.from_numpy(np.tile(acts[t], (B // R, 1))).cuda()
+        if t == 2:
+            a = a * scale                                           # direction only: a different scale per copy
+        obs, rew, done, _, info = big.step(a)
+        o_r, r_r, _, _, i_r = ref.step(torch.from_numpy(acts[t]).cuda())
+        torch.cuda.synchronize()
+        # copies agree to FP64 summation order (per-CTA partial slots differ between env blocks) / to the fp16 split
+        # of differently rounded actuators on the scaled step
+        tol = 1e-12 if t < 2 else 1e-5
+        o64 = big.obs_f64.reshape(B // R, R, 4)
+        for x in (o64, rew.reshape(-1, R), info['power'].reshape(-1, R)):
+            x0 = x[:1].expand_as(x)
+            assert torch.all((x - x0).abs() <= tol * x0.abs()), f'copies of one case differ (step {t})'
+        _close(o64[0].cpu().numpy(), ref.obs_f64.cpu().numpy(), 1e-5, f'obs step {t}')
+        _close(info['power'][:R].cpu().numpy(), i_r['power'].cpu().numpy(), 1e-5, f'power step {t}')
+        _close(big.strehl[:R].cpu().numpy(), ref.strehl.cpu().numpy(), 1e-5, f'strehl step {t}')
+    # flat wavefront and flat mirror (reset): every copy identical, and the four detector pixels equal by symmetry
+    big.reset()
+    torch.cuda.synchronize()
+    flat_obs = big.obs_f64.reshape(B // R, R, 4)[:, 0]
+    assert torch.equal(flat_obs, flat_obs[:1].expand_as(flat_obs))
+    got = flat_obs[0].cpu().numpy()
+    assert np.allclose(got, got[0], rtol=1e-6) and got[0] > 0
+    big.close()
+    ref.close()
