@@ -338,7 +338,8 @@ void aog_destroy(aog_env* env) {
                   env->strehl_part, env->arZ, env->arNew, env->act_in, env->noise_in, env->o_obs16, env->o_obs64,
                   env->o_reward, env->o_power, env->o_strehl, env->o_ssim, env->t_sh_mla, env->t_sh_C, env->t_sh_CT,
                   env->t_sh_off, env->t_sh_pix, env->t_sh_px, env->t_sh_py, env->t_sh_offset, env->t_sh_recon,
-                  env->t_sh_act0, env->act_sh, env->o_action, env->sh_noisy_in};
+                  env->t_sh_act0, env->act_sh, env->o_action, env->sh_noisy_in, env->t_sh_Cf[0], env->t_sh_Cf[1],
+                  env->t_sh_Cf[2], env->t_sh_Cf[3]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (env->h_pinned) cudaFreeHost(env->h_pinned);
@@ -405,6 +406,38 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
   if (which == AOG_TABLE_SH_FRESNEL) {
     k_transpose_z<<<cdiv((int)P, 256), 256>>>(env->t_sh_C, env->t_sh_CT, (int)Np, (int)Np);
     AOG_LAUNCH_CHECK();
+    // centrosymmetric operator -> parity-folded tables (common.cuh: t_sh_Cf)
+    const double* m = static_cast<const double*>(host);
+    const size_t N = Np, Nh = Np / 2;
+    double mx = 0.0, res = 0.0;
+    for (size_t i = 0; i < N; ++i)
+      for (size_t j = 0; j < N; ++j) {
+        const double* a = &m[2 * (i * N + j)];
+        const double* b = &m[2 * ((N - 1 - i) * N + (N - 1 - j))];
+        mx = std::max(mx, std::max(std::fabs(a[0]), std::fabs(a[1])));
+        res = std::max(res, std::max(std::fabs(a[0] - b[0]), std::fabs(a[1] - b[1])));
+      }
+    env->sh_fold = (N % 2 == 0) && res <= 1e-13 * mx && getenv("AOG_SH_NO_FOLD") == nullptr;
+    if (env->sh_fold) {
+      std::vector<double> t(4 * 2 * Nh * Nh);
+      for (size_t i = 0; i < Nh; ++i)
+        for (size_t j = 0; j < Nh; ++j) {
+          const double* a = &m[2 * (i * N + j)];
+          const double* b = &m[2 * (i * N + (N - 1 - j))];
+          for (int c = 0; c < 2; ++c) {
+            const double ce = 0.5 * (a[c] + b[c]), co = 0.5 * (a[c] - b[c]);
+            t[0 * 2 * Nh * Nh + 2 * (i * Nh + j) + c] = ce;
+            t[1 * 2 * Nh * Nh + 2 * (i * Nh + j) + c] = co;
+            t[2 * 2 * Nh * Nh + 2 * (j * Nh + i) + c] = ce;
+            t[3 * 2 * Nh * Nh + 2 * (j * Nh + i) + c] = co;
+          }
+        }
+      for (int k = 0; k < 4; ++k) {
+        int rc = dev_alloc(env, &env->t_sh_Cf[k], Nh * Nh);
+        if (rc) return rc;
+        AOG_CUDA(cudaMemcpy(env->t_sh_Cf[k], &t[(size_t)k * 2 * Nh * Nh], Nh * Nh * sizeof(double2), cudaMemcpyHostToDevice));
+      }
+    }
   }
   if (which == AOG_TABLE_SH_ACT0) {   // every env's SH mirror starts from the same actuators (AO_env.py:431-447)
     k_broadcast_rows<<<cdiv((int)K * c.num_envs, 256), 256>>>(env->t_sh_act0, env->act_sh, (int)K, c.num_envs);
@@ -677,7 +710,32 @@ int aog_sh_step(aog_env* env, int noise_mode, const double* noisy_image_dev, dou
   constexpr int ET = 4;
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     const int nB = std::min(env->chunk, B - e0);
-    if (noise_mode != AOG_SH_NOISE_INJECTED) {
+    const double2* F = env->bufC;
+    long long strideF = sC;
+    if (noise_mode != AOG_SH_NOISE_INJECTED && env->sh_fold) {
+      // parity-folded Fresnel step: four (Np/2)^3 products per stage instead of one Np^3 (common.cuh: t_sh_Cf)
+      const int Nh = Np / 2, Q = Nh * Nh;
+      const long long blk = (long long)env->chunk * Q;
+      k_sh_field_fold<ET><<<dim3(cdiv(Q, 128), cdiv(nB, ET)), 128, ET * K * sizeof(double), st>>>(
+          env->screens, env->act_sh, env->t_modes, env->t_aperture, env->t_sh_mla, env->bufA, blk, P, Np, K, e0, nB,
+          (int)env->cnt.column_origin, c.wavelength_wfs, env->sh_amplitude);
+      AOG_LAUNCH_CHECK();
+      const dim3 g(cdiv(Nh, 64), cdiv(Nh, 64), nB);
+      for (int b = 0; b < 4; ++b) {          // Y_pq = C_p E_pq
+        k_zgemm<<<g, 256, 0, st>>>(env->t_sh_Cf[b >> 1], env->bufA + b * blk, env->bufB + b * blk, Nh, Nh, Nh, Nh, Nh, Nh,
+                                   0, (long long)Q, (long long)Q);
+        AOG_LAUNCH_CHECK();
+      }
+      for (int b = 0; b < 4; ++b) {          // G_pq = Y_pq C_q^T
+        k_zgemm<<<g, 256, 0, st>>>(env->bufB + b * blk, env->t_sh_Cf[2 + (b & 1)], env->bufC + b * blk, Nh, Nh, Nh, Nh, Nh,
+                                   Nh, (long long)Q, 0, (long long)Q);
+        AOG_LAUNCH_CHECK();
+      }
+      k_sh_unfold<<<dim3(cdiv(Q, 128), nB), 128, 0, st>>>(env->bufC, blk, env->bufA, Np, nB);
+      AOG_LAUNCH_CHECK();
+      F = env->bufA;
+      strideF = P;
+    } else if (noise_mode != AOG_SH_NOISE_INJECTED) {
       k_sh_field_f64<ET><<<dim3(cdiv(P, 128), cdiv(nB, ET)), 128, ET * K * sizeof(double), st>>>(
           env->screens, env->act_sh, env->t_modes, env->t_aperture, env->t_sh_mla, env->bufA, P, Np, K, e0, nB,
           (int)env->cnt.column_origin, c.wavelength_wfs, env->sh_amplitude);
@@ -690,7 +748,7 @@ int aog_sh_step(aog_env* env, int noise_mode, const double* noisy_image_dev, dou
       AOG_LAUNCH_CHECK();
     }
     k_sh_centroid_update<<<nB, 256, 2 * Nsub * sizeof(double), st>>>(
-        env->bufC, sC, env->t_sh_off, env->t_sh_pix, env->t_sh_px, env->t_sh_py, env->t_sh_offset, env->t_sh_recon,
+        F, strideF, env->t_sh_off, env->t_sh_pix, env->t_sh_px, env->t_sh_py, env->t_sh_offset, env->t_sh_recon,
         env->act_sh, action_out_dev, noisy_image_dev, P, K, Nsub, e0, env->sh_weight_dt, noise_mode,
         c.seed ^ 0xD1B54A32D192ED03ull, (unsigned long long)c.env_id_base, (unsigned long long)env->sh_draws);
     AOG_LAUNCH_CHECK();

@@ -43,6 +43,11 @@ struct aog_env {
   double* t_sh_mla = nullptr;      // [P]
   double2* t_sh_C = nullptr;       // [Np][Np]
   double2* t_sh_CT = nullptr;      // transpose
+  // Centrosymmetric Fresnel operator (C[N-1-i][N-1-j] = C[i][j], checked at upload): C acts separately on the even
+  // and odd parts of a vector, so E_out = C E C^T splits into four (N/2)^3 products, half the work.
+  // t_sh_Cf = {Ce, Co, Ce^T, Co^T}, each [N/2][N/2], Ce/o[i][j] = (C[i][j] +- C[i][N-1-j]) / 2
+  bool sh_fold = false;
+  double2* t_sh_Cf[4] = {nullptr, nullptr, nullptr, nullptr};
   int* t_sh_off = nullptr;         // [Nsub+1]
   int* t_sh_pix = nullptr;         // [npix]
   double* t_sh_px = nullptr;       // [npix]

@@ -705,6 +705,84 @@ static __global__ void k_sh_field_f64(const double* __restrict__ screens, const 
     }
 }
 
+// The same field, folded by parity for a centrosymmetric Fresnel operator.  Thread = one pixel (i, x) of the
+// top-left quadrant for ET envs; it forms the field at the four mirror-image pixels and writes
+//   E_pq[i][x] = E[i][x] + p E[N-1-i][x] + q E[i][N-1-x] + p q E[N-1-i][N-1-x],   p, q = +-1
+// as four [N/2][N/2] blocks: Efold[(p < 0) * 2 + (q < 0)][env][i * N/2 + x] (block stride = blk_stride elements).
+template <int ET>
+static __global__ void k_sh_field_fold(const double* __restrict__ screens, const double* __restrict__ act,
+                                       const double* __restrict__ modes, const double* __restrict__ aperture,
+                                       const double* __restrict__ mla_phase, double2* __restrict__ Efold,
+                                       long long blk_stride, int P, int Np, int K, int env0, int nB, int col_origin,
+                                       double l_wfs, double amp) {
+  extern __shared__ double sh_act[];   // [ET][K]
+  const int e0 = blockIdx.y * ET;
+  for (int i = threadIdx.x; i < ET * K; i += blockDim.x) {
+    int e = i / K, k = i - e * K;
+    sh_act[i] = (e0 + e < nB) ? act[(size_t)(env0 + e0 + e) * K + k] : 0.0;
+  }
+  __syncthreads();
+  const int Nh = Np / 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Nh * Nh) return;
+  const int i = q / Nh, x = q - i * Nh;
+  const int pix[4] = {i * Np + x, (Np - 1 - i) * Np + x, i * Np + (Np - 1 - x), (Np - 1 - i) * Np + (Np - 1 - x)};
+  double s[4][ET];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int e = 0; e < ET; ++e) s[c][e] = 0.0;
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double m = modes[(size_t)k * P + pix[c]];
+#pragma unroll
+      for (int e = 0; e < ET; ++e) s[c][e] = fma(m, sh_act[e * K + k], s[c][e]);
+    }
+  }
+  const double kw = 6.283185307179586476925286766559 / l_wfs;
+#pragma unroll
+  for (int e = 0; e < ET; ++e)
+    if (e0 + e < nB) {
+      double2 E[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int y = pix[c] / Np;
+        int xp = pix[c] - y * Np + col_origin;
+        if (xp >= Np) xp -= Np;
+        const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)y * Np + xp];
+        const double ap = aperture[pix[c]];
+        double sn, cs;
+        sincos(S / l_wfs + 2.0 * s[c][e] * kw + mla_phase[pix[c]], &sn, &cs);
+        E[c] = make_double2(amp * ap * cs, amp * ap * sn);
+      }
+      // c: 0 = (i, x), 1 = row-mirrored, 2 = column-mirrored, 3 = both
+      const size_t o = (size_t)(e0 + e) * Nh * Nh + q;
+      Efold[o] = make_double2(E[0].x + E[1].x + E[2].x + E[3].x, E[0].y + E[1].y + E[2].y + E[3].y);                       // p+ q+
+      Efold[o + blk_stride] = make_double2(E[0].x + E[1].x - E[2].x - E[3].x, E[0].y + E[1].y - E[2].y - E[3].y);          // p+ q-
+      Efold[o + 2 * blk_stride] = make_double2(E[0].x - E[1].x + E[2].x - E[3].x, E[0].y - E[1].y + E[2].y - E[3].y);      // p- q+
+      Efold[o + 3 * blk_stride] = make_double2(E[0].x - E[1].x - E[2].x + E[3].x, E[0].y - E[1].y - E[2].y + E[3].y);      // p- q-
+    }
+}
+
+// G_pq = C_p E_pq C_q^T (four [N/2][N/2] blocks per env) -> the full field: F at the four mirror images of (i, u) is
+// the sum of the blocks weighted by 1, p, q, p q.
+static __global__ void k_sh_unfold(const double2* __restrict__ G, long long blk_stride, double2* __restrict__ F, int Np,
+                                   int nB) {
+  const int Nh = Np / 2;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y;
+  if (q >= Nh * Nh || e >= nB) return;
+  const int i = q / Nh, u = q - i * Nh;
+  const size_t o = (size_t)e * Nh * Nh + q;
+  const double2 a = G[o], b = G[o + blk_stride], c = G[o + 2 * blk_stride], d = G[o + 3 * blk_stride];
+  double2* f = F + (size_t)e * Np * Np;
+  f[(size_t)i * Np + u] = make_double2(a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y);
+  f[(size_t)(Np - 1 - i) * Np + u] = make_double2(a.x + b.x - c.x - d.x, a.y + b.y - c.y - d.y);               // x p
+  f[(size_t)i * Np + (Np - 1 - u)] = make_double2(a.x - b.x + c.x - d.x, a.y - b.y + c.y - d.y);               // x q
+  f[(size_t)(Np - 1 - i) * Np + (Np - 1 - u)] = make_double2(a.x - b.x - c.x + d.x, a.y - b.y - c.y + d.y);    // x p q
+}
+
 // camera image (power x dt), photon noise, flux-weighted centroids per selected lenslet (one warp each,
 // deterministic), slopes, leaky integrator a <- 0.99 a - 0.3 R slopes.  Block per env.
 static __global__ void k_sh_centroid_update(const double2* __restrict__ F, long long strideF,
