@@ -783,6 +783,44 @@ static __global__ void k_sh_unfold(const double2* __restrict__ G, long long blk_
   f[(size_t)(Np - 1 - i) * Np + (Np - 1 - u)] = make_double2(a.x - b.x - c.x + d.x, a.y - b.y - c.y + d.y);    // x p q
 }
 
+// Photon noise of the Shack-Hartmann camera (hcipy large_poisson -> np.random.poisson, AO_env.py:274): an exact
+// Poisson sampler on a Philox stream.  lambda < 10: Knuth's product of uniforms; lambda >= 10: Hoermann's transformed
+// rejection with squeeze (PTRS, the algorithm NumPy itself uses; 86 % of draws accepted on the first uniform pair
+// without a logarithm).  cuRAND's curand_poisson spends most of its time in the incomplete-gamma rejection of its
+// 64 <= lambda < 4000 branch, which is where the lenslet pixels off the focal spot sit.
+__device__ __forceinline__ double poisson_draw(curandStatePhilox4_32_10_t* st, double lam) {
+  if (lam < 10.0) {
+    if (lam <= 0.0) return 0.0;
+    const double enlam = exp(-lam);
+    double prod = 1.0;
+    int k = 0;
+    while (true) {
+      prod *= curand_uniform_double(st);
+      if (prod > enlam) ++k; else return (double)k;
+    }
+  }
+  const double slam = sqrt(lam), loglam = log(lam);
+  const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+  const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+  while (true) {
+    const double U = curand_uniform_double(st) - 0.5, V = curand_uniform_double(st);
+    const double us = 0.5 - fabs(U);
+    const double k = floor((2.0 * a / us + b) * U + lam + 0.43);
+    if (us >= 0.07 && V <= vr) return k;
+    if (k < 0.0 || (us < 0.013 && V > us)) continue;
+    if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
+  }
+}
+
+// test hook (aog_debug_poisson): n draws at one rate, one Philox subsequence per draw as the camera kernel uses them
+static __global__ void k_debug_poisson(double lam, int n, unsigned long long seed, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)i, 0ull, &st);
+  out[i] = (lam > 1e6) ? rint(lam + sqrt(lam) * curand_normal_double(&st)) : poisson_draw(&st, lam);
+}
+
 // camera image (power x dt), photon noise, flux-weighted centroids per selected lenslet (one warp each,
 // deterministic), slopes, leaky integrator a <- 0.99 a - 0.3 R slopes.  Block per env.
 static __global__ void k_sh_centroid_update(const double2* __restrict__ F, long long strideF,
@@ -811,7 +849,7 @@ static __global__ void k_sh_centroid_update(const double2* __restrict__ F, long 
           curandStatePhilox4_32_10_t st;
           // one Philox subsequence per (global env, pixel); successive SH_step draws are 256 outputs apart
           curand_init(seed, (env_id_base + env0 + b) * (unsigned long long)P + p, draw * 256ull, &st);
-          v = (v > 1e6) ? rint(v + sqrt(v) * curand_normal_double(&st)) : (double)curand_poisson(&st, v);
+          v = (v > 1e6) ? rint(v + sqrt(v) * curand_normal_double(&st)) : poisson_draw(&st, v);
         }
       }
       v += 1e-10;                                     // AO_env.py:277
@@ -824,13 +862,17 @@ static __global__ void k_sh_centroid_update(const double2* __restrict__ F, long 
     }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+  // a <- 0.99 a - 0.3 R slopes: one warp per reconstructor row, lanes along the row (coalesced), fixed-order tree sum
+  for (int k = warp; k < K; k += nw) {
     double r = 0.0;
-    for (int m = 0; m < 2 * Nsub; ++m) r += recon[(size_t)k * 2 * Nsub + m] * slopes[m];
-    const size_t i = (size_t)(env0 + b) * K + k;
-    const double a = (1.0 - 0.01) * act_sh[i] - 0.3 * r;
-    act_sh[i] = a;
-    if (action_out) action_out[i] = a;
+    for (int m = lane; m < 2 * Nsub; m += 32) r += recon[(size_t)k * 2 * Nsub + m] * slopes[m];
+    r = warp_sum(r);
+    if (lane == 0) {
+      const size_t i = (size_t)(env0 + b) * K + k;
+      const double a = (1.0 - 0.01) * act_sh[i] - 0.3 * r;
+      act_sh[i] = a;
+      if (action_out) action_out[i] = a;
+    }
   }
 }
 

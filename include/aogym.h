@@ -209,6 +209,10 @@ AOG_API int aog_set_actuators(aog_env* env, const double* host_in);
 
 AOG_API int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size_t count);
 
+/* test hook: n draws of the Shack-Hartmann camera's photon-noise sampler at rate lambda (Poisson below 1e6, rounded
+ * normal above -- hcipy large_poisson, AO_env.py:274), Philox subsequence i for draw i; host_out [n] */
+AOG_API int aog_debug_poisson(int device, double lambda, int n, uint64_t seed, double* host_out);
+
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 AOG_API int64_t aog_launch_count(const aog_env* env);
 /* environments processed per kernel sequence (num_envs is walked in chunks of this size) */

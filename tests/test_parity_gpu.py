@@ -422,3 +422,26 @@ def test_full_size_batch_properties(precision):
     assert np.allclose(got, got[0], rtol=1e-6) and got[0] > 0
     big.close()
     ref.close()
+
+
+def test_device_poisson_sampler_statistics():
+    """The SH camera's photon-noise sampler (Knuth below 10, PTRS above, rounded normal above 1e6) is Poisson:
+    non-negative integers, mean and variance = lambda, P(0) = exp(-lambda), third central moment = lambda."""
+    import ctypes as C
+    from adaptive_optics_gym_b200 import _lib
+    lib = _lib.load()
+    n = 400000
+    out = np.empty(n)
+    for k, lam in enumerate((0.3, 4.0, 9.99, 10.0, 37.5, 640.0, 3999.0, 2.5e5, 5e6)):
+        rc = lib.aog_debug_poisson(0, float(lam), n, 1234 + k, out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        assert np.all(out >= 0) and np.all(out == np.rint(out))
+        m, v = out.mean(), out.var()
+        assert abs(m - lam) < 5 * np.sqrt(lam / n), (lam, m)
+        assert abs(v - lam) < 5 * lam * np.sqrt(2.0 / n + 1.0 / (lam * n)), (lam, v)
+        if lam < 5:
+            p0 = np.mean(out == 0)
+            assert abs(p0 - np.exp(-lam)) < 5 * np.sqrt(np.exp(-lam) / n)
+        if lam <= 1e6:
+            m3 = np.mean((out - m) ** 3)
+            assert abs(m3 - lam) < 6 * np.sqrt((lam + 9 * lam ** 2 + 15 * lam ** 3) / n) + 1e-9, (lam, m3)
