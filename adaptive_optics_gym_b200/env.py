@@ -288,10 +288,14 @@ class AOVecEnv(_AOCore):
         self.single_observation_space = spaces.Box(low=-1, high=1, shape=(n2,), dtype=np.float16)
         self.single_action_space = spaces.Box(low=-1, high=1, shape=(self.num_modes,), dtype=np.float16)
         kw = dict(device=self.device)
-        self.obs = torch.empty((B, n2), dtype=torch.float16, **kw)
+        # reward | power | obs share one allocation so that a caller on the host fetches a step's results with ONE
+        # device->host copy (``fetch``); the float64 arrays come first to keep them 8-byte aligned
+        self._packed = torch.empty(16 * B + 2 * B * n2, dtype=torch.uint8, **kw)
+        self.reward = self._packed[:8 * B].view(torch.float64)
+        self.power = self._packed[8 * B:16 * B].view(torch.float64)
+        self.obs = self._packed[16 * B:].view(torch.float16).view(B, n2)
+        self._packed_host = None
         self.obs_f64 = torch.empty((B, n2), dtype=torch.float64, **kw)
-        self.reward = torch.empty(B, dtype=torch.float64, **kw)
-        self.power = torch.empty(B, dtype=torch.float64, **kw)
         self.strehl = torch.zeros(B, dtype=torch.float64, **kw)
         self.ssim = torch.zeros(B, dtype=torch.float64, **kw)
         self._true = torch.ones(B, dtype=torch.bool, **kw)
@@ -337,6 +341,19 @@ class AOVecEnv(_AOCore):
         done = self._h.step_device(actions.data_ptr(), dt, self._out, nz_ptr, self._stream())
         self._sync_counters()
         return self.obs, self.reward, (self._true if done else self._false), self._false, {"power": self.power}
+
+    def fetch(self):
+        """The last step's (obs float16 [B, n^2], reward float64 [B], power float64 [B]) on the host: one
+        device->host copy of the packed output buffer into pinned memory, then a stream synchronise.  The returned
+        tensors are views of that pinned buffer (overwritten by the next ``fetch``)."""
+        torch = self._torch
+        B, n2 = self.num_envs, self.config.obs_dim ** 2
+        if self._packed_host is None:
+            self._packed_host = torch.empty(self._packed.numel(), dtype=torch.uint8).pin_memory()
+        h = self._packed_host
+        h.copy_(self._packed, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h[16 * B:].view(torch.float16).view(B, n2), h[:8 * B].view(torch.float64), h[8 * B:16 * B].view(torch.float64)
 
     def SH_step(self, noise='poisson', noisy_image=None):
         """Batched ``SH_step`` (AO_env.py:254-290): -> (actions [B, K] float64 cuda, ones [B] int64)."""

@@ -208,9 +208,6 @@ def main():
     pool = 8
     act_host = [torch.empty((B, K), dtype=torch.float32).uniform_(-1, 1, generator=g).pin_memory() for _ in range(pool)]
     act_dev = [a.to(dev) for a in act_host]
-    obs_h = torch.empty((B, n2), dtype=torch.float16).pin_memory()
-    rew_h = torch.empty(B, dtype=torch.float64).pin_memory()
-    pow_h = torch.empty(B, dtype=torch.float64).pin_memory()
 
     state = {'t': 0}
 
@@ -229,12 +226,9 @@ def main():
         a = act_host[i % pool].to(dev, non_blocking=True)
         if sh_loop:
             a = env.SH_step()[0]
-        obs, rew, done, _, info = env.step(a)
-        obs_h.copy_(obs, non_blocking=True)
-        rew_h.copy_(rew, non_blocking=True)
-        pow_h.copy_(info['power'], non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller needs the result before acting again
-        state['t'] += 1
+        env.step(a)
+        env.fetch()                     # obs, reward, power -> pinned host memory (one copy) + stream synchronise:
+        state['t'] += 1                 # the caller needs the result before acting again
 
     def barrier():
         if world > 1:

@@ -203,6 +203,9 @@ def test_vec_env_matches_single_env_and_shards():
         obs, rew, done, trunc, info = vec.step(torch.from_numpy(a).cuda())
         torch.cuda.synchronize()
         assert bool(done.all()) == (t == 2) and not bool(trunc.any())
+        ho, hr, hp = vec.fetch()                      # one packed device->host copy
+        assert not ho.is_cuda and torch.equal(ho, obs.cpu()) and torch.equal(hr, rew.cpu())
+        assert torch.equal(hp, info['power'].cpu())
         for i, s in enumerate(singles):
             o1, r1, d1, _, i1 = s.step(a[i])
             assert np.array_equal(obs[i].cpu().numpy().view(np.uint16), o1.view(np.uint16))
