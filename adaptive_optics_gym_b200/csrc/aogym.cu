@@ -339,7 +339,8 @@ void aog_destroy(aog_env* env) {
                   env->o_reward, env->o_power, env->o_strehl, env->o_ssim, env->t_sh_mla, env->t_sh_C, env->t_sh_CT,
                   env->t_sh_off, env->t_sh_pix, env->t_sh_px, env->t_sh_py, env->t_sh_offset, env->t_sh_recon,
                   env->t_sh_act0, env->act_sh, env->o_action, env->sh_noisy_in, env->t_sh_Cf[0], env->t_sh_Cf[1],
-                  env->t_sh_Cf[2], env->t_sh_Cf[3]};
+                  env->t_sh_Cf[2], env->t_sh_Cf[3], env->t_scrWst[0], env->t_scrWst[1], env->t_scrWrT[0], env->t_scrWrT[1],
+                  env->t_scrWiT[0], env->t_scrWiT[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (env->h_pinned) cudaFreeHost(env->h_pinned);
@@ -402,6 +403,39 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
   if (which == AOG_TABLE_SCR_W1) {
     k_transpose_z<<<cdiv((int)P, 256), 256>>>(env->t_scrW1, env->t_scrW1T, (int)Np, (int)Np);
     AOG_LAUNCH_CHECK();
+  }
+  if (which == AOG_TABLE_SCR_W1 || which == AOG_TABLE_SCR_W2) {
+    // conjugate-paired rows -> real-arithmetic synthesis tables (common.cuh: t_scrWst)
+    const int sidx = which == AOG_TABLE_SCR_W1 ? 0 : 1;
+    const size_t N = Np, Nh = Np / 2, Nk = sidx == 0 ? Np : N2;
+    const double* m = static_cast<const double*>(host);      // [N][Nk] complex
+    double mx = 0.0, res = 0.0;
+    for (size_t x = 0; x < N; ++x)
+      for (size_t k = 0; k < Nk; ++k) {
+        const double* a = &m[2 * (x * Nk + k)];
+        const double* b = &m[2 * ((N - 1 - x) * Nk + k)];
+        mx = std::max(mx, std::max(std::fabs(a[0]), std::fabs(a[1])));
+        res = std::max(res, std::max(std::fabs(a[0] - b[0]), std::fabs(a[1] + b[1])));
+      }
+    env->scr_sym[sidx] = N % 2 == 0 && Nk % 2 == 0 && res <= 1e-12 * mx && getenv("AOG_SCR_COMPLEX") == nullptr;
+    if (env->scr_sym[sidx]) {
+      std::vector<double> wst(N * Nk), wrT(Nk * Nh), wiT(Nk * Nh);
+      for (size_t x = 0; x < Nh; ++x)
+        for (size_t k = 0; k < Nk; ++k) {
+          const double re = m[2 * (x * Nk + k)], im = m[2 * (x * Nk + k) + 1];
+          wst[x * Nk + k] = re;
+          wst[(Nh + x) * Nk + k] = im;
+          wrT[k * Nh + x] = re;
+          wiT[k * Nh + x] = im;
+        }
+      int rc;
+      if ((rc = dev_alloc(env, &env->t_scrWst[sidx], N * Nk))) return rc;
+      if ((rc = dev_alloc(env, &env->t_scrWrT[sidx], Nk * Nh))) return rc;
+      if ((rc = dev_alloc(env, &env->t_scrWiT[sidx], Nk * Nh))) return rc;
+      AOG_CUDA(cudaMemcpy(env->t_scrWst[sidx], wst.data(), wst.size() * sizeof(double), cudaMemcpyHostToDevice));
+      AOG_CUDA(cudaMemcpy(env->t_scrWrT[sidx], wrT.data(), wrT.size() * sizeof(double), cudaMemcpyHostToDevice));
+      AOG_CUDA(cudaMemcpy(env->t_scrWiT[sidx], wiT.data(), wiT.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
   }
   if (which == AOG_TABLE_SH_FRESNEL) {
     k_transpose_z<<<cdiv((int)P, 256), 256>>>(env->t_sh_C, env->t_sh_CT, (int)Np, (int)Np);
@@ -518,8 +552,42 @@ int aog_generate_screens(aog_env* env, void* stream) {
   const unsigned long long base = (unsigned long long)(env->screen_draws++) * per;
   const long long sB = (long long)Np * std::max(c.num_focal_pixels, Np);
   const long long sC = (long long)std::max<size_t>(env->NF2, P);
+  // real-arithmetic form on the FP64 tensor cores (common.cuh: t_scrWst), one scale at a time:
+  //   out1 = [Re W_top ; Im W_top] . [Xr | Xi]   (N x 2 Nk)  ->  U = rows < N/2, V = rows >= N/2
+  //   P1 = Ur WrT, P2 = Vi WrT, P3 = Ui WiT, P4 = Vr WiT   (N/2 x N/2 each)  ->  k_scr_combine4
+  auto synth_real = [&](int sidx, int Nk, const double* Ctab, unsigned long long draw_base, int e0, int nB,
+                        int accumulate) -> int {
+    const int Nh = Np / 2, Q = Nh * Nh;
+    double* X = reinterpret_cast<double*>(env->bufA);
+    double* O = reinterpret_cast<double*>(env->bufB);
+    double* Pq = reinterpret_cast<double*>(env->bufC);
+    const long long sX = 2LL * P, sO = 2 * sB, sP = 2 * sC;
+    k_scr_noise_planes<<<dim3(cdiv(Nk * Nk, 256), nB), 256, 0, st>>>(Ctab, X, Nk, sX, e0, seed,
+                                                                      (unsigned long long)c.env_id_base, draw_base);
+    AOG_LAUNCH_CHECK();
+    k_dgemm_mma<<<dim3(cdiv(2 * Nk, 64), cdiv(Np, 128), nB), 256, 0, st>>>(env->t_scrWst[sidx], X, O, Np, 2 * Nk, Nk, Nk,
+                                                                           2 * Nk, 2 * Nk, 0, sX, sO);
+    AOG_LAUNCH_CHECK();
+    const double* Aop[4] = {O, O + (size_t)Nh * 2 * Nk + Nk, O + Nk, O + (size_t)Nh * 2 * Nk};      // Ur, Vi, Ui, Vr
+    const double* Bop[4] = {env->t_scrWrT[sidx], env->t_scrWrT[sidx], env->t_scrWiT[sidx], env->t_scrWiT[sidx]};
+    for (int q = 0; q < 4; ++q) {
+      k_dgemm_mma<<<dim3(cdiv(Nh, 64), cdiv(Nh, 128), nB), 256, 0, st>>>(Aop[q], Bop[q], Pq + (size_t)q * Q, Nh, Nh, Nk,
+                                                                         2 * Nk, Nh, Nh, sO, 0, sP);
+      AOG_LAUNCH_CHECK();
+    }
+    k_scr_combine4<<<dim3(cdiv(Q, 256), nB), 256, 0, st>>>(env->screens, Pq, Np, sP, e0, c.sqrt_cn2, accumulate);
+    AOG_LAUNCH_CHECK();
+    return AOG_OK;
+  };
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     const int nB = std::min(env->chunk, B - e0);
+    if (env->scr_sym[0] && env->scr_sym[1]) {
+      int rc = synth_real(0, Np, env->t_scrC1, base, e0, nB, 0);
+      if (rc) return rc;
+      rc = synth_real(1, N2, env->t_scrC2, base + P, e0, nB, 1);
+      if (rc) return rc;
+      continue;
+    }
     // scale 1: X1 [Np x Np] -> W1 X1 W1^T
     k_scr_noise<<<dim3(cdiv(P, 256), nB), 256, 0, st>>>(env->t_scrC1, env->bufA, P, (long long)P, e0, seed,
                                                         (unsigned long long)c.env_id_base, base);

@@ -541,25 +541,23 @@ static __global__ void k_ar_gather(const double* __restrict__ screens, const int
 // consecutive m or n) touches every bank once; next tile prefetched in registers with volatile 16-byte loads.
 //   screens[(env0 + b) P + y Np + phys_col] = new[b][flipped ? Np - 1 - y : y]
 //   tiles (TensorState::hwt layout) [env / 32][phys_col][y / 16][env % 32][piece][y % 4] = fixed(new / (lambda_wfs pi))
-static __global__ void __launch_bounds__(256)
-k_ar_step(const double* __restrict__ Z, const double* __restrict__ W, double* __restrict__ screens,
-          int32_t* __restrict__ tiles, int nB, int Np, int Kd, int P, int env0, int phys_col, int flipped,
-          double inv_w, double phi_one) {
+// Main loop shared by the FP64 tensor-core GEMMs: acc (warp tile 32 x 32 at (wm, wn) of the 128 x 64 block tile at
+// (m0, n0)) = A[M x Kd] (row stride lda) . B[Kd x N] (row stride ldb).  lda, ldb, Kd even, rows 16-byte aligned.
+__device__ __forceinline__ void dmma_mainloop(const double* __restrict__ A, int lda, int M, const double* __restrict__ B,
+                                              int ldb, int N, int Kd, int m0, int n0, double (&acc)[4][4][2]) {
   constexpr int TM = 128, TN = 64, TK = 8, LDA = TM + 4, LDB = TN + 4;
   __shared__ __align__(16) double As[2][TK][LDA];
   __shared__ __align__(16) double Bs[2][TK][LDB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;      // warp tile origin inside the block tile
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   // loader roles: A row m0 + t / 2, 4 k's;  B row k = t / 32, 2 n's
   const int am = threadIdx.x >> 1, ak = (threadIdx.x & 1) * 4;
   const int bk = threadIdx.x >> 5, bn = (threadIdx.x & 31) * 2;
-  const bool a_ok = m0 + am < nB, b_ok = n0 + bn < Np;
-  const double* a_src = Z + (size_t)(m0 + am) * Kd + ak;
-  const double* b_src = W + (size_t)bk * Np + n0 + bn;
+  const bool a_ok = m0 + am < M, b_ok = n0 + bn < N;
+  const double* a_src = A + (size_t)(m0 + am) * lda + ak;
+  const double* b_src = B + (size_t)bk * ldb + n0 + bn;
   // Operand prefetch as volatile 16-byte loads: issued a whole K step of MMAs ahead of their use (left to itself the
-  // compiler sinks them next to the shared-memory stores and the warp waits out the L2 round trip).  Kd and Np are
-  // even and every row starts 16-byte aligned, so a pair never straddles the edge.
+  // compiler sinks them next to the shared-memory stores and the warp waits out the L2 round trip).
   double ra[4], rb[2];
   auto ld2 = [](const double* p, bool ok, double& x, double& y) {
     x = 0.0; y = 0.0;
@@ -568,14 +566,17 @@ k_ar_step(const double* __restrict__ Z, const double* __restrict__ W, double* __
   auto load = [&](int k0) {
     ld2(a_src + k0, a_ok && k0 + ak < Kd, ra[0], ra[1]);
     ld2(a_src + k0 + 2, a_ok && k0 + ak + 2 < Kd, ra[2], ra[3]);
-    ld2(b_src + (size_t)k0 * Np, b_ok && k0 + bk < Kd, rb[0], rb[1]);
+    ld2(b_src + (size_t)k0 * ldb, b_ok && k0 + bk < Kd, rb[0], rb[1]);
   };
   auto stash = [&](int buf) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) As[buf][ak + i][am] = ra[i];
     *reinterpret_cast<double2*>(&Bs[buf][bk][bn]) = make_double2(rb[0], rb[1]);
   };
-  double acc[4][4][2] = {};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   load(0);
   stash(0);
   __syncthreads();
@@ -601,6 +602,41 @@ k_ar_step(const double* __restrict__ Z, const double* __restrict__ W, double* __
     __syncthreads();
     buf ^= 1;
   }
+}
+
+// Batched real FP64 GEMM on the tensor cores: C_z[M x N] = A_z[M x Kd] . B_z[Kd x N], z = blockIdx.z, operand z at
+// base + z * stride (stride 0 = shared table).  Grid (ceil(N / 64), ceil(M / 128), batch).
+static __global__ void __launch_bounds__(256)
+k_dgemm_mma(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int M, int N, int Kd,
+            int lda, int ldb, int ldc, long long sA, long long sB, long long sC) {
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 64;
+  double acc[4][4][2];
+  dmma_mainloop(A + (size_t)blockIdx.z * sA, lda, M, B + (size_t)blockIdx.z * sB, ldb, N, Kd, m0, n0, acc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  double* c = C + (size_t)blockIdx.z * sC;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + wm + 8 * i + gid;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + wn + 8 * j + 2 * tig;
+      if (n + 1 < N) *reinterpret_cast<double2*>(&c[(size_t)m * ldc + n]) = make_double2(acc[i][j][0], acc[i][j][1]);
+      else if (n < N) c[(size_t)m * ldc + n] = acc[i][j][0];
+    }
+  }
+}
+
+static __global__ void __launch_bounds__(256)
+k_ar_step(const double* __restrict__ Z, const double* __restrict__ W, double* __restrict__ screens,
+          int32_t* __restrict__ tiles, int nB, int Np, int Kd, int P, int env0, int phys_col, int flipped,
+          double inv_w, double phi_one) {
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 64;
+  double acc[4][4][2];
+  dmma_mainloop(Z, Kd, nB, W, Np, Np, Kd, m0, n0, acc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   // C fragment: row gid, columns 2 tig + {0, 1}
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -651,6 +687,43 @@ static __global__ void k_scr_noise(const double* __restrict__ C, double2* __rest
   const double2 z = curand_normal2_double(&st);
   const double c = C[i];
   X[(size_t)b * strideX + i] = make_double2(c * z.x, c * z.y);
+}
+
+// real-arithmetic synthesis (common.cuh: t_scrWst): the same draws as k_scr_noise, written as two real planes
+// X[b] = [Xr | Xi], Nk rows of 2 Nk doubles
+static __global__ void k_scr_noise_planes(const double* __restrict__ C, double* __restrict__ X, int Nk, long long strideX,
+                                          int env0, unsigned long long seed, unsigned long long env_id_base,
+                                          unsigned long long draw_base) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nk * Nk) return;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, env_id_base + env0 + b, (draw_base + (unsigned long long)i) * 4ull, &st);
+  const double2 z = curand_normal2_double(&st);
+  const double c = C[i];
+  const int k = i / Nk, l = i - k * Nk;
+  double* x = X + (size_t)b * strideX + (size_t)k * 2 * Nk + l;
+  x[0] = c * z.x;
+  x[Nk] = c * z.y;
+}
+
+// S at the four mirror images of (y, x), y, x < N/2, from P1 = Ur Wr^T, P2 = Vi Wr^T, P3 = Ui Wi^T, P4 = Vr Wi^T
+// (U = Re W_top X, V = Im W_top X): (P1 -+ P2) -+ (P3 +- P4)
+static __global__ void k_scr_combine4(double* __restrict__ screens, const double* __restrict__ Pq, int Np,
+                                      long long strideP, int env0, double scale, int accumulate) {
+  const int Nh = Np / 2, Q = Nh * Nh;
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int y = q / Nh, x = q - y * Nh;
+  const double* p = Pq + (size_t)b * strideP + q;
+  const double p1 = p[0], p2 = p[Q], p3 = p[2 * Q], p4 = p[3 * Q];
+  double* s = screens + (size_t)(env0 + b) * Np * Np;
+  const double v[4] = {(p1 - p2) - (p3 + p4), (p1 - p2) + (p3 + p4), (p1 + p2) - (p3 - p4), (p1 + p2) + (p3 - p4)};
+  const size_t idx[4] = {(size_t)y * Np + x, (size_t)y * Np + (Np - 1 - x), (size_t)(Np - 1 - y) * Np + x,
+                         (size_t)(Np - 1 - y) * Np + (Np - 1 - x)};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s[idx[c]] = accumulate ? (s[idx[c]] + scale * v[c]) : scale * v[c];
 }
 
 static __global__ void k_scr_combine(double* __restrict__ screens, const double2* __restrict__ Y, int P, long long strideY,

@@ -37,6 +37,15 @@ WORKLOADS = {
     'zernike6_smf_ssim': dict(atm_type='quasi_static', atm_vel=0, atm_fried=0.15, act_type='zernike', act_dim=6,
                               obs_dim=5, rew_type='smf_ssim', timesteps_per_episode=20,
                               flat_mirror_start_per_episode=True),
+    # BASELINE.json configs[2] as the reference runs it: semi_dynamic coerces the velocity to 0 (AO_env.py:200-203) and
+    # draws a fresh von-Karman screen at every reset (:76-77)
+    'semi_dynamic_64act': dict(atm_type='semi_dynamic', atm_vel=0, atm_fried=0.15, act_type='num_actuators', act_dim=64,
+                               obs_dim=5, rew_type='strehl_ratio', timesteps_per_episode=20,
+                               flat_mirror_start_per_episode=True),
+    # ... and with the phase-screen evolution that config names (dynamic, 5 m/s: 2.4 extrusions per step)
+    'dynamic_v5': dict(atm_type='dynamic', atm_vel=5, atm_fried=0.15, act_type='num_actuators', act_dim=64,
+                       obs_dim=5, rew_type='strehl_ratio', timesteps_per_episode=20,
+                       flat_mirror_start_per_episode=True),
     # BASELINE.json configs[3] physics without the SH loop
     'dynamic_v20': dict(atm_type='dynamic', atm_vel=20, atm_fried=0.10, act_type='num_actuators', act_dim=64,
                         obs_dim=2, rew_type='strehl_ratio', timesteps_per_episode=20,

@@ -448,3 +448,21 @@ def test_device_poisson_sampler_statistics():
         if lam <= 1e6:
             m3 = np.mean((out - m) ** 3)
             assert abs(m3 - lam) < 6 * np.sqrt((lam + 9 * lam ** 2 + 15 * lam ** 3) / n) + 1e-9, (lam, m3)
+
+
+def test_real_arithmetic_screen_synthesis_matches_complex_form(monkeypatch):
+    """von-Karman synthesis Re(W X W^T): the real-arithmetic tensor-core form (conjugate-paired rows of W) draws the
+    same Philox normals and must reproduce the two-complex-GEMM form to rounding."""
+    from adaptive_optics_gym_b200 import AOVecEnv
+    kw = dict(atm_type='semi_dynamic', atm_fried=0.15, seed=11)
+    env = AOVecEnv(7, **kw)
+    env.reset()
+    fast = env._h.get_screens()
+    env.close()
+    monkeypatch.setenv('AOG_SCR_COMPLEX', '1')
+    ref = AOVecEnv(7, **kw)
+    ref.reset()
+    slow = ref._h.get_screens()
+    ref.close()
+    assert np.abs(slow).max() > 0
+    assert np.abs(fast - slow).max() <= 1e-11 * np.abs(slow).max()
