@@ -282,6 +282,10 @@ struct FinalizeArgs {
   int coef_is_raw;     // 1: coef holds unscaled (re, im) projection sums; 2: coef4 holds [re|im][2 partials];
                        // 3: fib_part holds [fib_slots][fib_stride] partial sums per env;  all x coef_scale
   const double2* fib_part; int fib_slots, fib_stride;
+  // k_finalize_tc: the phase kernel's CTA c takes work items [c slot_ipc, (c + 1) slot_ipc) and the 128-env block eb
+  // owns items [eb slot_items, (eb + 1) slot_items), so only slots 0 .. last - first of an env are written (and
+  // summed): no clearing pass
+  int slot_ipc, slot_items;
   double2 coef_scale;
   int transpose_out;   // R / table hold the transposed contraction: result (a, b) is obs pixel (v = b, u = a)
   double thr, obs_weight, strehl_scale, ssim_peak;
@@ -437,6 +441,8 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
   }
   __syncthreads();
   if (warp != 0 || !a.compute_reward) return;
+  const int eb = b >> 7;
+  const int nslots = ((eb + 1) * a.slot_items - 1) / a.slot_ipc - (eb * a.slot_items) / a.slot_ipc + 1;
   // fibre: out = M (c e^{i beta L});  total power = c'^H G c'
   double2 c[AOG_MAX_LP];
   for (int j = 0; j < a.J; ++j) {
@@ -446,7 +452,7 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
       cj = make_double2(c4[0] + c4[1], c4[2] + c4[3]);
     } else {
       const double2* fp = a.fib_part + (size_t)b * a.fib_slots * a.fib_stride + j;
-      for (int i = lane; i < a.fib_slots; i += 32) { cj.x += fp[i * a.fib_stride].x; cj.y += fp[i * a.fib_stride].y; }
+      for (int i = lane; i < nslots; i += 32) { cj.x += fp[i * a.fib_stride].x; cj.y += fp[i * a.fib_stride].y; }
       cj.x = warp_sum(cj.x);
       cj.y = warp_sum(cj.y);
     }
@@ -462,7 +468,7 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
   if (a.rew_type == AOG_REW_STREHL_RATIO) {
     double sr = 0.0, si = 0.0;
     const double2* sp = a.strehl_part + (size_t)b * a.strehl_blocks;
-    for (int i = lane; i < a.strehl_blocks; i += 32) { sr += sp[i].x; si += sp[i].y; }
+    for (int i = lane; i < nslots; i += 32) { sr += sp[i].x; si += sp[i].y; }
     sr = warp_sum(sr);
     si = warp_sum(si);
     const double strehl = a.strehl_scale * (sr * sr + si * si);

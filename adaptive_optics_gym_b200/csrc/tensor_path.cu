@@ -2054,6 +2054,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
   const int Np = TC_NP, n = c.obs_dim, K = c.num_modes, J = c.num_lp_modes, B = c.num_envs;
   const bool strehl = with_reward && c.rew_type == AOG_REW_STREHL_RATIO;
   const double2 norm = make_double2(c.mft_norm_re * c.amp_fiber, c.mft_norm_im * c.amp_fiber);
+  int slot_ipc = 1;
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     const int nB = std::min(env->chunk, B - e0);
     if (env->timing) { AOG_CUDA(cudaEventRecord(env->evf, st)); }
@@ -2081,8 +2082,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       fp.err_flag = ts->err_flag;
       const int grid = cdiv(fp.num_items, fp.items_per_cta);
       int rc;
-      if (strehl) AOG_CUDA(cudaMemsetAsync(env->strehl_part, 0, (size_t)nB * FK_SLOTS * sizeof(double2), st));
-      if (fused) AOG_CUDA(cudaMemsetAsync(ts->fib_part, 0, (size_t)nB * FK_SLOTS * FK_JT * sizeof(double2), st));
+      slot_ipc = fp.items_per_cta;            // k_finalize_tc sums exactly the slots this launch writes
       if (fused && ts->sym) rc = strehl ? launch_phase_n<true, 2>(env, ts, fp, n, grid, st) : launch_phase_n<false, 2>(env, ts, fp, n, grid, st);
       else if (fused)       rc = strehl ? launch_phase_n<true, 1>(env, ts, fp, n, grid, st) : launch_phase_n<false, 1>(env, ts, fp, n, grid, st);
       else                  rc = strehl ? launch_phase_n<true, 0>(env, ts, fp, n, grid, st) : launch_phase_n<false, 0>(env, ts, fp, n, grid, st);
@@ -2134,6 +2134,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       a.fib_part = ts->fib_part; a.fib_slots = FK_SLOTS; a.fib_stride = FK_JT;
     } a.coef = nullptr; a.coef4 = ts->coef4; a.lpphase = fused ? ts->lpphase_f : env->t_lpphase; a.lpgram = env->t_lpgram;
     a.strehl_part = env->strehl_part; a.strehl_blocks = FK_SLOTS;
+    a.slot_ipc = slot_ipc; a.slot_items = Np;
     a.Np = Np; a.n = n; a.J = J; a.rew_type = c.rew_type; a.has_thr = c.has_rew_threshold;
     a.compute_reward = with_reward ? 1 : 0;
     a.transpose_out = 1;     // R is [x][v] and the table is M2o^T: results come out as (u, v)
