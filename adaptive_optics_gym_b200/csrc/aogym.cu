@@ -49,6 +49,16 @@ int64_t center_px(const aog_env* env, int64_t timestep) {
   return (int64_t)std::nearbyint(c / env->cfg.pupil_delta);
 }
 
+// the FP64 tensor-core GEMMs keep their cp.async ring in opt-in dynamic shared memory
+int dmma_configure(aog_env* env) {
+  static bool done = false;
+  if (done) return AOG_OK;
+  AOG_CUDA(cudaFuncSetAttribute(k_ar_step, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
+  AOG_CUDA(cudaFuncSetAttribute(k_dgemm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
+  done = true;
+  return AOG_OK;
+}
+
 // ---- one column extrusion for all envs -------------------------------------------------
 int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long noise_stride, cudaStream_t st) {
   const aog_config& c = env->cfg;
@@ -75,7 +85,8 @@ int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long
     }
     // GEMM with the scatter into the ring slot (and the phase-tile refresh of the tensor / fused paths) in its epilogue
     dim3 g2(cdiv(Np, 64), cdiv(nB, 128));
-    k_ar_step<<<g2, 256, 0, st>>>(env->arZ, env->t_arW, env->screens, env->phase_tiles, nB, Np, Ns + Np, env->P, e0, phys,
+    { int rc = dmma_configure(env); if (rc) return rc; }
+    k_ar_step<<<g2, DmmaCfg<1>::THREADS, DmmaCfg<1>::SMEM, st>>>(env->arZ, env->t_arW, env->screens, env->phase_tiles, nB, Np, Ns + Np, env->P, e0, phys,
                                   flipped, 1.0 / (c.wavelength_wfs * 3.14159265358979323846), env->phase_tiles_unit);
     AOG_LAUNCH_CHECK();
   }
@@ -565,13 +576,14 @@ int aog_generate_screens(aog_env* env, void* stream) {
     k_scr_noise_planes<<<dim3(cdiv(Nk * Nk, 256), nB), 256, 0, st>>>(Ctab, X, Nk, sX, e0, seed,
                                                                       (unsigned long long)c.env_id_base, draw_base);
     AOG_LAUNCH_CHECK();
-    k_dgemm_mma<<<dim3(cdiv(2 * Nk, 64), cdiv(Np, 128), nB), 256, 0, st>>>(env->t_scrWst[sidx], X, O, Np, 2 * Nk, Nk, Nk,
+    { int rc = dmma_configure(env); if (rc) return rc; }
+    k_dgemm_mma<<<dim3(cdiv(2 * Nk, 64), cdiv(Np, 128), nB), 256, DmmaCfg<1>::SMEM, st>>>(env->t_scrWst[sidx], X, O, Np, 2 * Nk, Nk, Nk,
                                                                            2 * Nk, 2 * Nk, 0, sX, sO);
     AOG_LAUNCH_CHECK();
     const double* Aop[4] = {O, O + (size_t)Nh * 2 * Nk + Nk, O + Nk, O + (size_t)Nh * 2 * Nk};      // Ur, Vi, Ui, Vr
     const double* Bop[4] = {env->t_scrWrT[sidx], env->t_scrWrT[sidx], env->t_scrWiT[sidx], env->t_scrWiT[sidx]};
     for (int q = 0; q < 4; ++q) {
-      k_dgemm_mma<<<dim3(cdiv(Nh, 64), cdiv(Nh, 128), nB), 256, 0, st>>>(Aop[q], Bop[q], Pq + (size_t)q * Q, Nh, Nh, Nk,
+      k_dgemm_mma<<<dim3(cdiv(Nh, 64), cdiv(Nh, 128), nB), 256, DmmaCfg<1>::SMEM, st>>>(Aop[q], Bop[q], Pq + (size_t)q * Q, Nh, Nh, Nk,
                                                                          2 * Nk, Nh, Nh, sO, 0, sP);
       AOG_LAUNCH_CHECK();
     }

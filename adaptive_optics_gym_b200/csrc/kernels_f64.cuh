@@ -542,61 +542,84 @@ static __global__ void k_ar_gather(const double* __restrict__ screens, const int
 // ring-buffered screens -- and, for the tensor / fused paths, the refresh of that column's fixed-point phase tiles --
 // in the epilogue.  mma.sync.m8n8k4.f64 (DMMA) sustains 36 TFLOP/s on B200 with 4-8 warps per SM where scalar DFMA
 // needs 16+ warps of 32 independent chains for 31 (tools/micro/dmma_bench.cu), and it issues 8x fewer instructions,
-// which leaves the slots for the operand traffic.  Block tile 128 envs x 64 pixels, K step 8, 8 warps as 4 x 2, warp
-// tile 32 x 32 = 4 x 4 fragments; shared-memory rows padded by 4 doubles so that a fragment load (4 k rows x 8
-// consecutive m or n) touches every bank once; next tile prefetched in registers with volatile 16-byte loads.
+// which leaves the slots for the operand traffic.  Block tile 128 envs x 64 pixels, warp tile 32 x 32 = 4 x 4
+// fragments.  ncu: DMMA pipe 50 % of the active cycles, 128 blocks on 148 SMs; splitting K over a second group of
+// 8 warps per tile (dmma_mainloop<2>) measured no gain (140 vs 135 us), so the plain form is used.
 //   screens[(env0 + b) P + y Np + phys_col] = new[b][flipped ? Np - 1 - y : y]
 //   tiles (TensorState::hwt layout) [env / 32][phys_col][y / 16][env % 32][piece][y % 4] = fixed(new / (lambda_wfs pi))
 // Main loop shared by the FP64 tensor-core GEMMs: acc (warp tile 32 x 32 at (wm, wn) of the 128 x 64 block tile at
-// (m0, n0)) = A[M x Kd] (row stride lda) . B[Kd x N] (row stride ldb).  lda, ldb, Kd even, rows 16-byte aligned.
-__device__ __forceinline__ void dmma_mainloop(const double* __restrict__ A, int lda, int M, const double* __restrict__ B,
+// (m0, n0)) = A[M x Kd] (row stride lda) . B[Kd x N] (row stride ldb).  lda, ldb, Kd, N even, rows 16-byte aligned.
+// Operands stream global -> shared with 16-byte cp.async through a DMMA_STAGES-deep ring of K steps of 8 * KSPLIT (no
+// register staging, no transposing stores): A keeps its row-major form, rows padded by 4 doubles so that a fragment
+// load (8 rows x 4 consecutive k) touches every bank once; B rows padded to 68.
+// KSPLIT = 2 (512 threads): two groups of 8 warps work on the SAME output tile, group g on the k range
+// [8 g, 8 g + 8) of every K step, and the second group's accumulators are added through shared memory at the end --
+// 16 warps per SM for a GEMM whose grid has fewer blocks than the GPU has SMs (the extrusion: 128 blocks).
+constexpr int DMMA_STAGES = 4, DMMA_LDB = 64 + 4;
+template <int KSPLIT> struct DmmaCfg {
+  static constexpr int TK = 8 * KSPLIT, LDA = TK + 4, A_STAGE = 128 * LDA, B_STAGE = TK * DMMA_LDB;   // doubles
+  static constexpr int RING = DMMA_STAGES * (A_STAGE + B_STAGE) * (int)sizeof(double);
+  static constexpr int SMEM = KSPLIT == 2 ? (RING > 65536 ? RING : 65536) : RING;       // ring, reused for the reduction
+  static constexpr int THREADS = 256 * KSPLIT;
+};
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = ok ? 16 : 0;                                   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+// returns true for the threads that hold the finished tile (group 0)
+template <int KSPLIT>
+__device__ __forceinline__ bool dmma_mainloop(const double* __restrict__ A, int lda, int M, const double* __restrict__ B,
                                               int ldb, int N, int Kd, int m0, int n0, double (&acc)[4][4][2]) {
-  constexpr int TM = 128, TN = 64, TK = 8, LDA = TM + 4, LDB = TN + 4;
-  __shared__ __align__(16) double As[2][TK][LDA];
-  __shared__ __align__(16) double Bs[2][TK][LDB];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  using Cfg = DmmaCfg<KSPLIT>;
+  constexpr int TK = Cfg::TK, LDA = Cfg::LDA;
+  extern __shared__ __align__(16) double dmma_smem[];
+  double* As = dmma_smem;                                      // [stage][128][LDA]
+  double* Bs = dmma_smem + DMMA_STAGES * Cfg::A_STAGE;         // [stage][TK][DMMA_LDB]
+  const int group = threadIdx.x >> 8, t = threadIdx.x & 255;
+  const int warp = t >> 5, lane = t & 31, gid = lane >> 2, tig = lane & 3;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;      // warp tile origin inside the block tile
-  // loader roles: A row m0 + t / 2, 4 k's;  B row k = t / 32, 2 n's
-  const int am = threadIdx.x >> 1, ak = (threadIdx.x & 1) * 4;
-  const int bk = threadIdx.x >> 5, bn = (threadIdx.x & 31) * 2;
-  const bool a_ok = m0 + am < M, b_ok = n0 + bn < N;
-  const double* a_src = A + (size_t)(m0 + am) * lda + ak;
-  const double* b_src = B + (size_t)bk * ldb + n0 + bn;
-  // Operand prefetch as volatile 16-byte loads: issued a whole K step of MMAs ahead of their use (left to itself the
-  // compiler sinks them next to the shared-memory stores and the warp waits out the L2 round trip).
-  double ra[4], rb[2];
-  auto ld2 = [](const double* p, bool ok, double& x, double& y) {
-    x = 0.0; y = 0.0;
-    if (ok) asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
-  };
-  auto load = [&](int k0) {
-    ld2(a_src + k0, a_ok && k0 + ak < Kd, ra[0], ra[1]);
-    ld2(a_src + k0 + 2, a_ok && k0 + ak + 2 < Kd, ra[2], ra[3]);
-    ld2(b_src + (size_t)k0 * ldb, b_ok && k0 + bk < Kd, rb[0], rb[1]);
-  };
-  auto stash = [&](int buf) {
+  // loader roles (group g loads the k range it will use): A row t / 2, k pairs 2 (t % 2) + {0, 1};  B row t / 32, n pair t % 32
+  const int am = t >> 1, ac = (t & 1) * 2, kg = group * 8;
+  const int bk = t >> 5, bc = t & 31;
+  const bool a_ok = m0 + am < M, b_ok = n0 + 2 * bc < N;
+  const double* a_src = A + (size_t)(a_ok ? m0 + am : 0) * lda;
+  const double* b_src = B + (b_ok ? n0 + 2 * bc : 0);
+  auto issue = [&](int ks) {                                   // K step ks -> ring slot ks % DMMA_STAGES
+    const int k0 = ks * TK + kg, st = ks % DMMA_STAGES;
+    double* as = As + st * Cfg::A_STAGE + am * LDA + kg;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) As[buf][ak + i][am] = ra[i];
-    *reinterpret_cast<double2*>(&Bs[buf][bk][bn]) = make_double2(rb[0], rb[1]);
+    for (int c = 0; c < 2; ++c) {
+      const int k = k0 + 2 * (ac + c);
+      cp_async16(as + 2 * (ac + c), a_src + (k < Kd ? k : 0), a_ok && k < Kd);
+    }
+    const int kb = k0 + bk;
+    cp_async16(Bs + st * Cfg::B_STAGE + (kg + bk) * DMMA_LDB + 2 * bc, b_src + (size_t)(kb < Kd ? kb : 0) * ldb, b_ok && kb < Kd);
   };
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  load(0);
-  stash(0);
-  __syncthreads();
-  int buf = 0;
-  for (int k0 = 0; k0 < Kd; k0 += TK) {
-    const bool more = k0 + TK < Kd;
-    if (more) load(k0 + TK);
+  const int nk = (Kd + TK - 1) / TK;
 #pragma unroll
-    for (int k4 = 0; k4 < TK; k4 += 4) {
+  for (int s0 = 0; s0 < DMMA_STAGES - 1; ++s0) {
+    if (s0 < nk) issue(s0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int ks = 0; ks < nk; ++ks) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(DMMA_STAGES - 2) : "memory");   // K step ks has landed
+    __syncthreads();                                            // ... for every thread; slot (ks - 1) % STAGES is free
+    if (ks + DMMA_STAGES - 1 < nk) issue(ks + DMMA_STAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* as = As + (ks % DMMA_STAGES) * Cfg::A_STAGE + kg;
+    const double* bs = Bs + (ks % DMMA_STAGES) * Cfg::B_STAGE + kg * DMMA_LDB;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; k4 += 4) {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[buf][k4 + tig][wm + 8 * i + gid];     // A fragment: row gid, column (k) tig
+      for (int i = 0; i < 4; ++i) a[i] = as[(wm + 8 * i + gid) * LDA + k4 + tig];          // A fragment: row gid, column (k) tig
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[buf][k4 + tig][wn + 8 * j + gid];     // B fragment: row (k) tig, column gid
+      for (int j = 0; j < 4; ++j) b[j] = bs[(k4 + tig) * DMMA_LDB + wn + 8 * j + gid];     // B fragment: row (k) tig, column gid
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -604,10 +627,31 @@ __device__ __forceinline__ void dmma_mainloop(const double* __restrict__ A, int 
           asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                        : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
     }
-    if (more) stash(buf ^ 1);
-    __syncthreads();
-    buf ^= 1;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (KSPLIT == 2) {
+    __syncthreads();                                            // the ring is dead: reuse it for the second group's tile
+    double* red = dmma_smem + (size_t)t * 32;
+    if (group == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<double2*>(red + (i * 4 + j) * 2) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+    __syncthreads();
+    if (group == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 v = *reinterpret_cast<const double2*>(red + (i * 4 + j) * 2);
+          acc[i][j][0] += v.x;
+          acc[i][j][1] += v.y;
+        }
+    }
+  }
+  return group == 0;
 }
 
 // Batched real FP64 GEMM on the tensor cores: C_z[M x N] = A_z[M x Kd] . B_z[Kd x N], z = blockIdx.z, operand z at
@@ -617,7 +661,7 @@ k_dgemm_mma(const double* __restrict__ A, const double* __restrict__ B, double* 
             int lda, int ldb, int ldc, long long sA, long long sB, long long sC) {
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 64;
   double acc[4][4][2];
-  dmma_mainloop(A + (size_t)blockIdx.z * sA, lda, M, B + (size_t)blockIdx.z * sB, ldb, N, Kd, m0, n0, acc);
+  dmma_mainloop<1>(A + (size_t)blockIdx.z * sA, lda, M, B + (size_t)blockIdx.z * sB, ldb, N, Kd, m0, n0, acc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   double* c = C + (size_t)blockIdx.z * sC;
@@ -640,7 +684,7 @@ k_ar_step(const double* __restrict__ Z, const double* __restrict__ W, double* __
           double inv_w, double phi_one) {
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 64;
   double acc[4][4][2];
-  dmma_mainloop(Z, Kd, nB, W, Np, Np, Kd, m0, n0, acc);
+  dmma_mainloop<1>(Z, Kd, nB, W, Np, Np, Kd, m0, n0, acc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
   // C fragment: row gid, columns 2 tig + {0, 1}
