@@ -102,3 +102,30 @@ def test_shack_hartmann_tables_match_oracle():
     for m in (0, sh['sh_num_sub'] // 2, sh['sh_num_sub'] - 1):
         np.testing.assert_array_equal(np.sort(pix[off[m]:off[m + 1]]),
                                       np.flatnonzero(o.mla_index == o.estimation_subapertures[m]))
+
+
+def test_tables_have_the_symmetries_the_fast_kernels_exploit():
+    """The library picks its fast forms from table symmetries it verifies at upload (and falls back otherwise):
+    conjugate-paired obs rows and real-times-phasor back-projected fibre modes (fused kernel MODE 2), conjugate-paired
+    rows of the screen-synthesis matrices (real-arithmetic synthesis), centrosymmetric Fresnel operator (parity-folded
+    SH step).  The reference geometry (hcipy's symmetric grids) must have all of them."""
+    from adaptive_optics_gym_b200.tables import build_sh_tables
+    for n in (2, 5):
+        cfg = AOConfig(act_type='zernike', num_modes=6, obs_dim=n)
+        tb = build_tables(cfg)
+        m1o = tb['mft_obs_1']                                    # [n][Np]
+        assert np.abs(m1o[::-1] - np.conj(m1o)).max() <= 1e-12 * np.abs(m1o).max()
+    M1, M2, lpw = tb['mft_fib_1'], tb['mft_fib_2'], tb['lp_modes_w']
+    for j in range(lpw.shape[0]):
+        G = M1.T @ lpw[j].reshape(M1.shape[0], -1) @ M2.T        # fibre mode propagated back to the pupil
+        k = np.argmax(np.abs(G))
+        ph = G.flat[k] / np.abs(G.flat[k])
+        assert np.abs((G / ph).imag).max() <= 1e-10 * np.abs(G).max()
+    for key in ('scr_W1', 'scr_W2'):
+        W = tb[key]
+        assert W.shape[0] % 2 == 0 and W.shape[1] % 2 == 0
+        assert np.abs(W[::-1] - np.conj(W)).max() <= 1e-12 * np.abs(W).max()
+    sh = build_sh_tables(AOConfig(act_type='num_actuators', num_modes=64, obs_dim=2), build_tables(
+        AOConfig(act_type='num_actuators', num_modes=64, obs_dim=2)))
+    C = sh['sh_fresnel']
+    assert np.abs(C[::-1, ::-1] - C).max() <= 1e-13 * np.abs(C).max()
