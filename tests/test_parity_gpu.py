@@ -466,3 +466,30 @@ def test_real_arithmetic_screen_synthesis_matches_complex_form(monkeypatch):
     ref.close()
     assert np.abs(slow).max() > 0
     assert np.abs(fast - slow).max() <= 1e-11 * np.abs(slow).max()
+
+
+@pytest.mark.parametrize('precision', ['fused', 'tensor'])
+def test_more_envs_than_one_chunk(precision):
+    """num_envs beyond the 4096-env chunk (BASELINE.json's sweep goes to 65 536): the second chunk (a ragged 200 envs)
+    must reproduce the first one's results for the same screens and actions, also across an extrusion."""
+    import torch
+    from adaptive_optics_gym_b200 import AOVecEnv
+    B, R = 4096 + 200, 8
+    tabs = None
+    kw = dict(atm_type='dynamic', atm_vel=20, atm_fried=0.12, act_dim=64, obs_dim=2, rew_type='strehl_ratio',
+              timesteps_per_episode=3)
+    scr = np.stack([_screen(80 + i, r0=0.12) for i in range(R)])
+    env = AOVecEnv(B, **kw, initial_screens=np.tile(scr, (B // R, 1)), precision=precision)
+    assert env._h.chunk_size() == 4096
+    env.reset()
+    rng = np.random.default_rng(3)
+    for t in range(3):
+        a = torch.from_numpy(np.tile(rng.uniform(-1, 1, (R, 64)).astype(np.float32), (B // R, 1))).cuda()
+        nz = np.tile(rng.standard_normal((1, env._h.next_extrusions(), 240)), (B, 1, 1))     # same noise for every env
+        obs, rew, done, _, info = env.step(a, extrusion_noise=nz)
+        torch.cuda.synchronize()
+        for x in (env.obs_f64, rew.unsqueeze(1), info['power'].unsqueeze(1), env.strehl.unsqueeze(1)):
+            first, second = x[:R], x[4096:4096 + R]              # 4096 % 8 == 0: same cases, other chunk
+            assert torch.all((first - second).abs() <= 1e-12 * first.abs()), f'chunks differ at step {t}'
+        assert bool(done.all()) == (t == 2)
+    env.close()
