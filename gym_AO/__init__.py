@@ -1,8 +1,8 @@
-"""Drop-in for the reference's ``gym_AO`` package: ``import gym_AO`` registers ``AO-v0``
-(reference ``gym_AO/__init__.py:6-11``) -- backed by the B200 CUDA step path."""
-from adaptive_optics_gym_b200._gym_compat import register
+"""Drop-in for the reference's ``gym_AO`` package: importing it makes ``gym.make('AO-v0', ...)`` resolve to the
+B200 CUDA step path (the reference registers the same id and entry point in ``gym_AO/__init__.py:6-11``)."""
+from adaptive_optics_gym_b200 import _gym_compat
 
-register(
-    id='AO-v0',
-    entry_point='gym_AO.envs:AOEnv',
-)
+ENV_ID = 'AO-v0'
+ENTRY_POINT = 'gym_AO.envs:AOEnv'
+
+_gym_compat.register(id=ENV_ID, entry_point=ENTRY_POINT)
