@@ -286,6 +286,10 @@ struct FinalizeArgs {
   // owns items [eb slot_items, (eb + 1) slot_items), so only slots 0 .. last - first of an env are written (and
   // summed): no clearing pass
   int slot_ipc, slot_items;
+  // k_finalize_tc: the env's normalised actuators [K].  An all-zero action makes them 0/0 = NaN (AO_env.py:119-120)
+  // and the reference then returns NaN observations, reward and power; the fixed-point phase arithmetic of the
+  // tensor / fused kernels would swallow the NaN, so it is re-applied here.
+  const double* act; int K;
   double2 coef_scale;
   int transpose_out;   // R / table hold the transposed contraction: result (a, b) is obs pixel (v = b, u = a)
   double thr, obs_weight, strehl_scale, ssim_peak;
@@ -408,6 +412,24 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
   __shared__ double obs[AOG_MAX_OBS * AOG_MAX_OBS];
   const int b = blockIdx.x, n = a.n, n2 = n * n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (a.act) {
+    int bad = 0;
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x) bad |= isfinite(a.act[(size_t)b * a.K + k]) ? 0 : 1;   // inf: exp(i inf) = NaN too
+    if (__syncthreads_or(bad)) {
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int t = threadIdx.x; t < n2; t += blockDim.x) {
+        if (a.obs64) a.obs64[(size_t)b * n2 + t] = qnan;
+        if (a.obs16) a.obs16[(size_t)b * n2 + t] = 0x7e00;
+      }
+      if (threadIdx.x == 0 && a.compute_reward) {
+        if (a.reward) a.reward[b] = qnan;
+        if (a.power) a.power[b] = qnan;
+        if (a.strehl) a.strehl[b] = qnan;
+        if (a.ssim) a.ssim[b] = qnan;
+      }
+      return;
+    }
+  }
   const float2* r4 = a.R4 + (size_t)b * a.Np * a.r4_parts * n;
   for (int i = threadIdx.x; i < a.Np * n; i += blockDim.x) {
     const int x = i / n, v = i - x * n;

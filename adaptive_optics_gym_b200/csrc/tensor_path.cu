@@ -2050,7 +2050,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       (ts->fused && !ts->have_gfib))
     AOG_FAIL(AOG_ERR_STATE, "tensor path tables incomplete");
   const bool fused = ts->fused;
-  (void)flat_dm;
+  (void)flat_dm;                         // the caller has already zeroed the actuators of a flattened mirror
   const int Np = TC_NP, n = c.obs_dim, K = c.num_modes, J = c.num_lp_modes, B = c.num_envs;
   const bool strehl = with_reward && c.rew_type == AOG_REW_STREHL_RATIO;
   const double2 norm = make_double2(c.mft_norm_re * c.amp_fiber, c.mft_norm_im * c.amp_fiber);
@@ -2135,6 +2135,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     } a.coef = nullptr; a.coef4 = ts->coef4; a.lpphase = fused ? ts->lpphase_f : env->t_lpphase; a.lpgram = env->t_lpgram;
     a.strehl_part = env->strehl_part; a.strehl_blocks = FK_SLOTS;
     a.slot_ipc = slot_ipc; a.slot_items = Np;
+    a.act = env->act + (size_t)e0 * K; a.K = K;      // (a flattened mirror has zero, not NaN, actuators)
     a.Np = Np; a.n = n; a.J = J; a.rew_type = c.rew_type; a.has_thr = c.has_rew_threshold;
     a.compute_reward = with_reward ? 1 : 0;
     a.transpose_out = 1;     // R is [x][v] and the table is M2o^T: results come out as (u, v)

@@ -114,12 +114,34 @@ def test_flat_wavefront_known_answers():
     env.close()
 
 
-def test_zero_action_is_nan_like_reference():
-    """All-zero action -> 0/0 in the normalisation (AO_env.py:119-120) -> NaN obs and reward."""
-    env = _mk('f64', initial_screen=_screen(5))
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_zero_action_is_nan_like_reference(precision):
+    """All-zero action -> 0/0 in the normalisation (AO_env.py:119-120) -> NaN obs and reward; the next step with a
+    proper action is finite again (the actuators are overwritten)."""
+    env = _mk(precision, initial_screen=_screen(5))
     env.reset()
     o, r, d, _, info = env.step(np.zeros(64, dtype=np.float32))
     assert np.all(np.isnan(o.astype(np.float64))) and np.isnan(r) and np.isnan(info['power'])
+    o, r, d, _, info = env.step(np.ones(64, dtype=np.float32))
+    assert np.all(np.isfinite(o.astype(np.float64))) and np.isfinite(r) and np.isfinite(info['power'])
+    env.close()
+
+
+def test_zero_action_poisons_only_its_own_env():
+    import torch
+    from adaptive_optics_gym_b200 import AOVecEnv
+    B = 130
+    scr = np.tile(_screen(5).reshape(1, -1), (B, 1))
+    env = AOVecEnv(B, initial_screens=scr, precision='fused', timesteps_per_episode=3)
+    env.reset()
+    a = torch.ones((B, 64), dtype=torch.float32, device='cuda')
+    a[[3, 129]] = 0.0
+    obs, rew, _, _, info = env.step(a)
+    torch.cuda.synchronize()
+    bad = torch.zeros(B, dtype=torch.bool, device='cuda')
+    bad[[3, 129]] = True
+    assert torch.equal(torch.isnan(rew), bad) and torch.equal(torch.isnan(info['power']), bad)
+    assert torch.equal(torch.isnan(obs.float()).all(dim=1), bad) and not torch.isnan(obs.float()[~bad]).any()
     env.close()
 
 
