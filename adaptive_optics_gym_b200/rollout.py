@@ -38,17 +38,18 @@ class VecRolloutCollector:
         n2, K = env.single_observation_space.shape[0], env.single_action_space.shape[0]
         E = int(episodes_per_iteration)
         kw = dict(dtype=torch.float32, device=env.device)
-        obs_b = torch.empty((E, B, T, n2), **kw)
-        act_b = torch.empty((E, B, T, K), **kw)
-        logp_b = torch.empty((E, B, T), **kw)
-        rew_b = torch.empty((E, B, T), **kw)
-        next_b = torch.empty((E, B, T, n2), **kw)
-        done_b = torch.zeros((E, B, T), **kw)
+        # collected time-major (every step writes one contiguous [B, ...] slab), transposed once at the end
+        obs_b = torch.empty((E, T, B, n2), **kw)
+        act_b = torch.empty((E, T, B, K), **kw)
+        logp_b = torch.empty((E, T, B), **kw)
+        rew_b = torch.empty((E, T, B), **kw)
+        next_b = torch.empty((E, T, B, n2), **kw)
+        done_b = torch.zeros((E, T, B), **kw)
         for e in range(E):
             obs, _ = env.reset()
             for t in range(T):
-                o32 = obs.to(torch.float32)
-                obs_b[e, :, t] = o32
+                o32 = obs_b[e, t]
+                o32.copy_(obs)                                  # float16 -> float32 straight into the batch
                 if self.policy is None:
                     action, logp = env.SH_step()
                     logp = logp.to(torch.float32)
@@ -58,17 +59,21 @@ class VecRolloutCollector:
                     if self.action_noise is not None:
                         action = action + self.action_noise(action)
                 obs, rew, done, _, _ = env.step(action)
-                act_b[e, :, t] = action.to(torch.float32)
-                logp_b[e, :, t] = logp
-                rew_b[e, :, t] = rew.to(torch.float32)
-                next_b[e, :, t] = obs.to(torch.float32)
-                done_b[e, :, t] = done.to(torch.float32)
+                act_b[e, t].copy_(action)
+                logp_b[e, t].copy_(logp)
+                rew_b[e, t].copy_(rew)
+                next_b[e, t].copy_(obs)
+                done_b[e, t].copy_(done)
             self.num_episodes += B
-        self.batch_ep_rew = rew_b.reshape(E * B, T)
-        lens = torch.full((E * B,), float(T), **kw)          # every env terminates on step T (AO_env.py:147)
         N = E * B * T
-        return (obs_b.reshape(N, n2), act_b.reshape(N, K), logp_b.reshape(N), rew_b.reshape(N),
-                next_b.reshape(N, n2), done_b.reshape(N), lens)
+
+        def rows(x):                                            # [E, T, B, ...] -> (episode, env, step) rows
+            return x.transpose(1, 2).reshape((N,) + tuple(x.shape[3:]))
+
+        rew_rows = rows(rew_b)
+        self.batch_ep_rew = rew_rows.reshape(E * B, T)
+        lens = torch.full((E * B,), float(T), **kw)          # every env terminates on step T (AO_env.py:147)
+        return rows(obs_b), rows(act_b), rows(logp_b), rew_rows, rows(next_b), rows(done_b), lens
 
     def episode_returns(self):
         """undiscounted return of every episode of the last ``rollout`` ([episodes] float32 cuda)"""
