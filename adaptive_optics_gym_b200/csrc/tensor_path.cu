@@ -1,6 +1,14 @@
-// Tensor-core arithmetic of the AO-v0 step path (AOG_PRECISION_TENSOR), sm_100a only.
+// Tensor-core arithmetic of the AO-v0 step path (AOG_PRECISION_FUSED and AOG_PRECISION_TENSOR), sm_100a only.
 //
-// Three kernels per chunk of environments:
+// AOG_PRECISION_FUSED -- one optics kernel per chunk of environments:
+//   k_actuators_pack  action -> normalised actuators -> split-fp16 GEMM operand
+//   k_dm_phase_tc<.., MODE 1 | 2>  DM surface as a tcgen05 GEMM over blocks of 128 envs; epilogue = total wavefront
+//                   phase (atmosphere + DM) and, from it, every output of the step as sums over the pupil: obs-arm
+//                   column sums, Strehl sum, fibre-coupling coefficients as inner products with the fibre modes
+//                   propagated back to the pupil (G_j = M1^T (mode_j w) M2^T).  Nothing but partial sums leaves the SM.
+//   k_finalize_tc   detector powers, fibre power, Strehl, SSIM, reward
+//
+// AOG_PRECISION_TENSOR -- the fibre arm through the matrix Fourier transform, three kernels per chunk:
 //   k_dm_phase_tc   DM surface as a tcgen05 GEMM over blocks of 128 envs; epilogue = total wavefront phase
 //                   (atmosphere + DM) -> HBM as FP32 radians, obs-arm column sums, Strehl sums
 //   k_field_mft1    field warps turn that phase into the pupil field ON CHIP (sincos, aperture, fp16 hi/lo) as the
