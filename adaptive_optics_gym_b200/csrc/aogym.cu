@@ -51,7 +51,8 @@ int64_t center_px(const aog_env* env, int64_t timestep) {
 
 // the FP64 tensor-core GEMMs keep their cp.async ring in opt-in dynamic shared memory
 int dmma_configure(aog_env* env) {
-  static bool done = false;
+  static bool done_on[64] = {};            // function attributes are per device: one flag per device ordinal
+  bool& done = done_on[env->cfg.device & 63];
   if (done) return AOG_OK;
   AOG_CUDA(cudaFuncSetAttribute(k_ar_step, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
   AOG_CUDA(cudaFuncSetAttribute(k_dgemm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));

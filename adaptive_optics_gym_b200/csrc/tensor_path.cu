@@ -2026,7 +2026,8 @@ int launch_phase(aog_env* env, TensorState* ts, const FieldParams& p, int grid, 
   const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES(NOBS, MODE) + 1024 + FK_AUX_BAR +
                    (FUSED ? 1 + FK_JT : 1) * FK_PARTS * 128 * (int)sizeof(double2) +
                    (FUSED ? 0 : NOBS * TC_NP * (int)sizeof(float2)) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
-  static bool configured = false;
+  static bool configured_on[64] = {};      // function attributes are per device: one flag per device ordinal
+  bool& configured = configured_on[env->cfg.device & 63];
   if (!configured) {
     AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -2105,7 +2106,8 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       f1.num_items = nB;
       f1.apmask = ts->apmask;
       f1.dbg = tc_dbg; f1.err_flag = ts->err_flag;
-      static bool configured = false;
+      static bool configured_on[64] = {};
+      bool& configured = configured_on[c.device & 63];
       if (!configured) {
         AOG_CUDA(cudaFuncSetAttribute(k_field_mft1, cudaFuncAttributeMaxDynamicSharedMemorySize, F1_SMEM_BYTES));
         configured = true;
