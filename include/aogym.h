@@ -221,7 +221,8 @@ AOG_API int aog_chunk_size(const aog_env* env);
  * CUDA events on the launch stream; negative if timing is disabled */
 AOG_API int aog_set_timing(aog_env* env, int enabled);
 AOG_API double aog_last_mft_ms(aog_env* env);
-/* tensor path only: the field kernel and the two MFT stages of the last timed chunk, milliseconds */
+/* tensor / fused paths: the phase kernel (fused path: the whole optics kernel) and the two MFT stages (0 on the fused
+ * path) of the last timed chunk, milliseconds */
 AOG_API int aog_last_kernel_ms(aog_env* env, double* field_ms, double* stage1_ms, double* stage2_ms);
 
 #ifdef __cplusplus
