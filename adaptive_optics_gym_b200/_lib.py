@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('AOG_LIB') or os.path.join(_HERE, 'libaogym.so')   # AOG_LIB: tuning builds only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ATM = {'quasi_static': 0, 'semi_dynamic': 1, 'dynamic': 2}
 REW = {'strehl_ratio': 0, 'smf_ssim': 1}
@@ -52,7 +52,7 @@ class AogOutputs(C.Structure):
 
 class AogCounters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ('timestep', 'timestep_render', 'episode_no', 'column_origin',
-                                         'extrusions')]
+                                         'extrusions', 'screen_draws', 'sh_draws')]
 
 
 class AogError(RuntimeError):
@@ -94,6 +94,10 @@ def load():
         'aog_set_counters': (C.c_int, [P, C.POINTER(AogCounters)]),
         'aog_get_actuators': (C.c_int, [P, P]),
         'aog_set_actuators': (C.c_int, [P, P]),
+        'aog_get_sh_actuators': (C.c_int, [P, P]),
+        'aog_set_sh_actuators': (C.c_int, [P, P]),
+        'aog_reseed': (C.c_int, [P, C.c_uint64]),
+        'aog_health': (C.c_int, [P]),
         'aog_get_field': (C.c_int, [P, C.c_int, C.c_int, P, C.c_size_t]),
         'aog_debug_poisson': (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_uint64, P]),
         'aog_launch_count': (C.c_int64, [P]),
@@ -203,6 +207,22 @@ class Handle:
     def set_actuators(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64).reshape(self.cfg.num_envs, self.cfg.num_modes)
         self.check(self.lib.aog_set_actuators(self._h, _ptr(a)), 'aog_set_actuators')
+
+    def get_sh_actuators(self):
+        out = np.empty((self.cfg.num_envs, self.cfg.num_modes))
+        self.check(self.lib.aog_get_sh_actuators(self._h, _ptr(out)), 'aog_get_sh_actuators')
+        return out
+
+    def set_sh_actuators(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(self.cfg.num_envs, self.cfg.num_modes)
+        self.check(self.lib.aog_set_sh_actuators(self._h, _ptr(a)), 'aog_set_sh_actuators')
+
+    def reseed(self, seed):
+        self.check(self.lib.aog_reseed(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1))), 'aog_reseed')
+        self.cfg.seed = int(seed) & (2 ** 64 - 1)
+
+    def health(self):
+        self.check(self.lib.aog_health(self._h), 'aog_health')
 
     def get_field(self, which, env_index=0):
         c = self.cfg

@@ -5,6 +5,7 @@
 #include "tensor_path.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -51,12 +52,12 @@ int64_t center_px(const aog_env* env, int64_t timestep) {
 
 // the FP64 tensor-core GEMMs keep their cp.async ring in opt-in dynamic shared memory
 int dmma_configure(aog_env* env) {
-  static bool done_on[64] = {};            // function attributes are per device: one flag per device ordinal
-  bool& done = done_on[env->cfg.device & 63];
-  if (done) return AOG_OK;
+  static std::atomic<bool> done_on[64];    // function attributes are per device: one flag per device ordinal
+  std::atomic<bool>& done = done_on[env->cfg.device & 63];
+  if (done.load(std::memory_order_acquire)) return AOG_OK;
   AOG_CUDA(cudaFuncSetAttribute(k_ar_step, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
   AOG_CUDA(cudaFuncSetAttribute(k_dgemm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
-  done = true;
+  done.store(true, std::memory_order_release);
   return AOG_OK;
 }
 
@@ -271,7 +272,7 @@ int aog_create(const aog_config* cfg, aog_env** out) {
   int ndev = 0;
   AOG_CUDA(cudaGetDeviceCount(&ndev));
   if (c.device < 0 || c.device >= ndev) AOG_FAIL(AOG_ERR_INVALID, "no such CUDA device");
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   cudaDeviceProp prop;
   AOG_CUDA(cudaGetDeviceProperties(&prop, c.device));
   if (prop.major != 10) AOG_FAIL(AOG_ERR_UNSUPPORTED, "libaogym is built for sm_100a (Blackwell B200) only");
@@ -340,7 +341,7 @@ int aog_create(const aog_config* cfg, aog_env** out) {
 
 void aog_destroy(aog_env* env) {
   if (!env) return;
-  cudaSetDevice(env->cfg.device);
+  DeviceGuard guard(env->cfg.device);
   cudaDeviceSynchronize();
   aog_tensor_destroy(env);
   void* ptrs[] = {env->t_aperture, env->t_modes, env->t_gram, env->t_m1f, env->t_m2f, env->t_m1o, env->t_m2o,
@@ -367,7 +368,7 @@ void aog_destroy(aog_env* env) {
 int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
   if (!env || !host) return AOG_ERR_INVALID;
   const aog_config& c = env->cfg;
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   const size_t Np = c.num_pupil_pixels, Nf = c.num_focal_pixels, K = c.num_modes, J = c.num_lp_modes, n = c.obs_dim;
   const size_t P = env->P, Ns = c.num_stencil, N2 = c.num_screen_fine;
   void* dst = nullptr;
@@ -505,7 +506,7 @@ int aog_set_screens(aog_env* env, const void* src, int dtype, int src_on_device,
   if (!env || !src) return AOG_ERR_INVALID;
   const aog_config& c = env->cfg;
   if (first_env < 0 || count < 1 || first_env + count > c.num_envs) AOG_FAIL(AOG_ERR_INVALID, "env range");
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   const size_t nel = (size_t)count * env->P;
   double* dst = env->screens + (size_t)first_env * env->P;
   if (env->cnt.column_origin != 0) AOG_FAIL(AOG_ERR_STATE, "set_screens after extrusions: reset counters first");
@@ -536,7 +537,7 @@ int aog_get_screens(aog_env* env, double* host_out, int first_env, int count) {
   if (!env || !host_out) return AOG_ERR_INVALID;
   const aog_config& c = env->cfg;
   if (first_env < 0 || count < 1 || first_env + count > c.num_envs) AOG_FAIL(AOG_ERR_INVALID, "env range");
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   AOG_CUDA(cudaDeviceSynchronize());
   const int Np = c.num_pupil_pixels, org = (int)env->cnt.column_origin;
   std::vector<double> tmp((size_t)count * env->P);
@@ -555,7 +556,7 @@ int aog_generate_screens(aog_env* env, void* stream) {
   if (c.num_screen_fine <= 0 || !env->have[AOG_TABLE_SCR_C1] || !env->have[AOG_TABLE_SCR_W1] ||
       !env->have[AOG_TABLE_SCR_C2] || !env->have[AOG_TABLE_SCR_W2])
     AOG_FAIL(AOG_ERR_STATE, "screen synthesis tables not set");
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   cudaStream_t st = (cudaStream_t)stream;
   const int Np = c.num_pupil_pixels, N2 = c.num_screen_fine, P = env->P, B = c.num_envs;
   // independent Philox domain from the extrusion noise: offset the seed
@@ -642,7 +643,7 @@ int aog_reset(aog_env* env, const aog_outputs* out_dev, void* stream) {
   if (!env) return AOG_ERR_INVALID;
   if (!tables_ready(env)) return AOG_ERR_STATE;
   const aog_config& c = env->cfg;
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   // AO_env.py:76-77 -- semi_dynamic draws a fresh screen per episode
@@ -673,7 +674,7 @@ int aog_step(aog_env* env, const void* actions_dev, int act_dtype, const double*
   if (!env || !actions_dev) return AOG_ERR_INVALID;
   if (!tables_ready(env)) return AOG_ERR_STATE;
   const aog_config& c = env->cfg;
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   cudaStream_t st = (cudaStream_t)stream;
   const int B = c.num_envs, K = c.num_modes;
   // AO_env.py:115-120
@@ -714,7 +715,7 @@ int aog_step_host(aog_env* env, const void* actions_host, int act_dtype, const d
                   const aog_outputs* out_host, int32_t* done_out) {
   if (!env || !actions_host) return AOG_ERR_INVALID;
   const aog_config& c = env->cfg;
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   cudaStream_t st = env->own_stream;
   const size_t esz = act_dtype == AOG_DTYPE_F32 ? sizeof(float) : sizeof(double);
   const size_t abytes = (size_t)c.num_envs * c.num_modes * esz;
@@ -743,7 +744,7 @@ int aog_sh_configure(aog_env* env, int num_sub, int num_pix, double amplitude, d
   if (!env) return AOG_ERR_INVALID;
   const aog_config& c = env->cfg;
   if (num_sub < 1 || num_pix < num_sub || num_pix > env->P) AOG_FAIL(AOG_ERR_INVALID, "Shack-Hartmann sizes");
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   const size_t P = env->P, K = c.num_modes, B = c.num_envs;
   env->sh_num_sub = num_sub;
   env->sh_num_pix = num_pix;
@@ -781,7 +782,7 @@ int aog_sh_step(aog_env* env, int noise_mode, const double* noisy_image_dev, dou
   if (!env->have[AOG_TABLE_APERTURE] || !env->have[AOG_TABLE_DM_MODES]) AOG_FAIL(AOG_ERR_STATE, "tables not set");
   if (noise_mode < AOG_SH_NOISE_NONE || noise_mode > AOG_SH_NOISE_INJECTED) AOG_FAIL(AOG_ERR_INVALID, "noise_mode");
   if (noise_mode == AOG_SH_NOISE_INJECTED && !noisy_image_dev) AOG_FAIL(AOG_ERR_INVALID, "noisy image missing");
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   int rc = ensure_f64_scratch(env);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -842,7 +843,7 @@ int aog_sh_step(aog_env* env, int noise_mode, const double* noisy_image_dev, dou
 int aog_sh_step_host(aog_env* env, int noise_mode, const double* noisy_image_host, double* action_out_host) {
   if (!env || !action_out_host) return AOG_ERR_INVALID;
   const aog_config& c = env->cfg;
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   cudaStream_t st = env->own_stream;
   const size_t B = c.num_envs, K = c.num_modes, P = env->P;
   if (!env->o_action) AOG_FAIL(AOG_ERR_STATE, "aog_sh_configure not called");
@@ -863,18 +864,56 @@ int aog_sh_step_host(aog_env* env, int noise_mode, const double* noisy_image_hos
 int aog_get_counters(const aog_env* env, aog_counters* out) {
   if (!env || !out) return AOG_ERR_INVALID;
   *out = env->cnt;
+  out->screen_draws = env->screen_draws;
+  out->sh_draws = env->sh_draws;
   return AOG_OK;
 }
 
 int aog_set_counters(aog_env* env, const aog_counters* in) {
   if (!env || !in) return AOG_ERR_INVALID;
   env->cnt = *in;
+  env->screen_draws = in->screen_draws;
+  env->sh_draws = in->sh_draws;
+  return AOG_OK;
+}
+
+int aog_reseed(aog_env* env, uint64_t seed) {
+  if (!env) return AOG_ERR_INVALID;
+  env->cfg.seed = seed;
+  env->cnt.extrusions = 0;      // the three Philox offset domains restart under the new key
+  env->screen_draws = 0;
+  env->sh_draws = 0;
+  return AOG_OK;
+}
+
+int aog_health(aog_env* env) {
+  if (!env) return AOG_ERR_INVALID;
+  return aog_tensor_check(env);
+}
+
+int aog_get_sh_actuators(aog_env* env, double* host_out) {
+  if (!env || !host_out) return AOG_ERR_INVALID;
+  if (!env->act_sh) AOG_FAIL(AOG_ERR_STATE, "aog_sh_configure not called");
+  AOG_DEVICE(env->cfg.device);
+  AOG_CUDA(cudaDeviceSynchronize());
+  AOG_CUDA(cudaMemcpy(host_out, env->act_sh, (size_t)env->cfg.num_envs * env->cfg.num_modes * sizeof(double),
+                      cudaMemcpyDeviceToHost));
+  return AOG_OK;
+}
+
+int aog_set_sh_actuators(aog_env* env, const double* host_in) {
+  if (!env || !host_in) return AOG_ERR_INVALID;
+  if (!env->act_sh) AOG_FAIL(AOG_ERR_STATE, "aog_sh_configure not called");
+  AOG_DEVICE(env->cfg.device);
+  AOG_CUDA(cudaDeviceSynchronize());
+  AOG_CUDA(cudaMemcpy(env->act_sh, host_in, (size_t)env->cfg.num_envs * env->cfg.num_modes * sizeof(double),
+                      cudaMemcpyHostToDevice));
   return AOG_OK;
 }
 
 int aog_get_actuators(aog_env* env, double* host_out) {
   if (!env || !host_out) return AOG_ERR_INVALID;
-  AOG_CUDA(cudaSetDevice(env->cfg.device));
+  AOG_DEVICE(env->cfg.device);
   AOG_CUDA(cudaDeviceSynchronize());
   AOG_CUDA(cudaMemcpy(host_out, env->act, (size_t)env->cfg.num_envs * env->cfg.num_modes * sizeof(double),
                       cudaMemcpyDeviceToHost));
@@ -883,7 +922,7 @@ int aog_get_actuators(aog_env* env, double* host_out) {
 
 int aog_set_actuators(aog_env* env, const double* host_in) {
   if (!env || !host_in) return AOG_ERR_INVALID;
-  AOG_CUDA(cudaSetDevice(env->cfg.device));
+  AOG_DEVICE(env->cfg.device);
   AOG_CUDA(cudaDeviceSynchronize());
   AOG_CUDA(cudaMemcpy(env->act, host_in, (size_t)env->cfg.num_envs * env->cfg.num_modes * sizeof(double),
                       cudaMemcpyHostToDevice));
@@ -895,7 +934,7 @@ int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size
   const aog_config& c = env->cfg;
   if (env_index < 0 || env_index >= c.num_envs) AOG_FAIL(AOG_ERR_INVALID, "env_index");
   if (!tables_ready(env)) return AOG_ERR_STATE;
-  AOG_CUDA(cudaSetDevice(c.device));
+  AOG_DEVICE(c.device);
   AOG_CUDA(cudaDeviceSynchronize());
   const size_t P = env->P;
   if (which == AOG_FIELD_SCREEN) {
@@ -987,7 +1026,8 @@ int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size
 
 int aog_debug_poisson(int device, double lambda, int n, uint64_t seed, double* host_out) {
   if (!host_out || n < 1 || !(lambda >= 0.0)) return AOG_ERR_INVALID;
-  if (cudaSetDevice(device) != cudaSuccess) return AOG_ERR_CUDA;
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return AOG_ERR_CUDA;
   double* d = nullptr;
   if (cudaMalloc((void**)&d, (size_t)n * sizeof(double)) != cudaSuccess) return AOG_ERR_CUDA;
   k_debug_poisson<<<cdiv(n, 256), 256>>>(lambda, n, (unsigned long long)seed, d);

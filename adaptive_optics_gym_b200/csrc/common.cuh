@@ -105,14 +105,43 @@ struct aog_env {
   bool ev_valid = false;
 };
 
+// tensor_path.cu: appends the code of a timed-out pipeline barrier (if one fired) to env->err -- a trap surfaces as a
+// generic sticky CUDA error on the next call, and this is what says which barrier it was
+void aog_tensor_annotate_error(aog_env* env);
+
 #define AOG_CUDA(call)                                                                  \
   do {                                                                                  \
     cudaError_t _e = (call);                                                            \
     if (_e != cudaSuccess) {                                                            \
       env->err = std::string(#call) + ": " + cudaGetErrorString(_e);                    \
+      aog_tensor_annotate_error(env);                                                   \
       return AOG_ERR_CUDA;                                                              \
     }                                                                                   \
   } while (0)
+
+// Every C-ABI entry point runs on the handle's device and restores the caller's current device on every return
+// path (torch reads the current device through cudaGetDevice: a handle on device 1 must not move the caller there).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define AOG_DEVICE(dev)                                                                  \
+  DeviceGuard _aog_guard(dev);                                                           \
+  if (_aog_guard.err != cudaSuccess) {                                                   \
+    env->err = std::string("cudaSetDevice: ") + cudaGetErrorString(_aog_guard.err);      \
+    return AOG_ERR_CUDA;                                                                 \
+  }
 
 #define AOG_FAIL(code, msg) \
   do { env->err = (msg); return (code); } while (0)

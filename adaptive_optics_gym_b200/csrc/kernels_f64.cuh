@@ -39,7 +39,9 @@ static __global__ void k_actuators(const ActT* __restrict__ actions, const doubl
     if (threadIdx.x == 0) red[0] = v;
   }
   __syncthreads();
-  const double scale = target_rms / sqrt(red[0]);   // var == 0 -> inf -> 0 * inf = NaN (reference semantics)
+  // var == 0 -> inf -> 0 * inf = NaN (reference semantics).  The Gram matrix is singular (duplicated disk-harmonic
+  // modes): for an action in its null space rounding can leave var slightly negative, where np.std is >= 0
+  const double scale = target_rms / sqrt(fmax(red[0], 0.0));
   for (int k = threadIdx.x; k < K; k += blockDim.x) act[(size_t)b * K + k] = sh_a[k] * scale;
 }
 

@@ -33,6 +33,7 @@
 
 #include <cuda.h>
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -74,7 +75,8 @@ struct TensorState {
   int kpad = 64;
   int act_rows = 128;
   double2* m2oT = nullptr;                            // [n][Np] transposed obs table
-  int* err_flag = nullptr;                            // device flag set by a timed-out barrier wait
+  int* err_flag = nullptr;                            // device alias of err_flag_host, set by a timed-out barrier wait
+  int* err_flag_host = nullptr;
   // AOG_PRECISION_FUSED: per-pixel records [Np x][Np / 16][16 y][FK_NT(n)] float2 = [obs-arm twiddles m1o[v][y] |
   // fibre modes propagated back to the pupil, G_j = M1^T (mode_j w) M2^T / max|G| | (aperture, 0)], all times the
   // aperture: the 16 records of a column chunk are one contiguous run for the bulk prefetch
@@ -133,7 +135,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   while (!mbar_try_wait(bar, parity)) {
     if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     if (++spins > (1u << 24)) {            // seconds: a protocol bug, not a slow producer
-      atomicExch(err_flag, code);
+      *(volatile int*)err_flag = code;          // mapped host memory: a plain store, then a system-scope fence
       __threadfence_system();
       asm volatile("trap;");
     }
@@ -1450,7 +1452,7 @@ k_actuators_pack(const ActT* __restrict__ actions, const double* __restrict__ gr
         for (int j = 0; j < K; ++j) r += sh_g[(size_t)j * K + i] * A[j];
         part += A[i] * r;
       }
-      scale = target_rms / sqrt(warp_sum(part));       // var == 0 -> inf -> 0 * inf = NaN (reference semantics)
+      scale = target_rms / sqrt(fmax(warp_sum(part), 0.0));   // var == 0 -> inf -> 0 * inf = NaN (reference semantics); never sqrt(-eps)
     }
     for (int k = lane; k < K; k += 32) {
       const double v = A[k] * scale;
@@ -1642,8 +1644,11 @@ int aog_tensor_create(aog_env* env) {
   A(talloc(env, &ts->m1o32, (size_t)c.obs_dim * TC_NP));
   A(talloc(env, &ts->R4, ch * TC_NP * FK_PARTS * c.obs_dim));
   A(talloc(env, &ts->m2oT, (size_t)c.obs_dim * TC_NP));
-  A(talloc(env, &ts->err_flag, 1));
-  AOG_CUDA(cudaMemset(ts->err_flag, 0, sizeof(int)));
+  // barrier-timeout code: mapped pinned HOST memory, so that the host can still read it after the trap that follows
+  // a timeout has poisoned the CUDA context (aog_health)
+  AOG_CUDA(cudaHostAlloc((void**)&ts->err_flag_host, sizeof(int), cudaHostAllocMapped));
+  *ts->err_flag_host = 0;
+  AOG_CUDA(cudaHostGetDevicePointer((void**)&ts->err_flag, ts->err_flag_host, 0));
   if (!ts->fused) {
     A(make_map(env, &ts->tmA1_hi, ts->A1_hi, 256, 128));
     A(make_map(env, &ts->tmA1_lo, ts->A1_lo, 256, 128));
@@ -1670,9 +1675,10 @@ void aog_tensor_destroy(aog_env* env) {
   if (!ts) return;
   void* ptrs[] = {ts->A1_hi, ts->A1_lo, ts->B2_hi, ts->B2_lo, ts->phi, ts->T_hi, ts->T_lo, ts->lpw, ts->lpwr, ts->coef4,
                   ts->hwt, ts->modesK_hi, ts->modesK_lo, ts->act_hi, ts->act_lo, ts->apmask, ts->m1o32, ts->R4,
-                  ts->m2oT, ts->err_flag, ts->gfib, ts->fib_part, ts->lpphase_f};
+                  ts->m2oT, ts->gfib, ts->fib_part, ts->lpphase_f};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (ts->err_flag_host) cudaFreeHost(ts->err_flag_host);
   delete ts;
   env->tensor_state = nullptr;
 }
@@ -2010,12 +2016,19 @@ int aog_tensor_actuators(aog_env* env, const void* actions_dev, int act_dtype, c
   return AOG_OK;
 }
 
+void aog_tensor_annotate_error(aog_env* env) {
+  TensorState* ts = env ? TS(env) : nullptr;
+  if (!ts || !ts->err_flag_host) return;
+  const int flag = *(volatile int*)ts->err_flag_host;
+  if (flag) env->err += " [tensor pipeline barrier timeout, code " + std::to_string(flag) + ": the kernel trapped, this process's CUDA context is no longer usable]";
+}
+
 int aog_tensor_check(aog_env* env) {
   TensorState* ts = TS(env);
   if (!ts) return AOG_OK;
-  int flag = 0;
-  AOG_CUDA(cudaMemcpy(&flag, ts->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) AOG_FAIL(AOG_ERR_CUDA, "tensor pipeline barrier timeout, code " + std::to_string(flag));
+  const int flag = ts->err_flag_host ? *(volatile int*)ts->err_flag_host : 0;
+  if (flag) AOG_FAIL(AOG_ERR_CUDA, "tensor pipeline barrier timeout, code " + std::to_string(flag) +
+                                       " (the kernel trapped: this process's CUDA context is no longer usable)");
   return AOG_OK;
 }
 
@@ -2026,11 +2039,11 @@ int launch_phase(aog_env* env, TensorState* ts, const FieldParams& p, int grid, 
   const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES(NOBS, MODE) + 1024 + FK_AUX_BAR +
                    (FUSED ? 1 + FK_JT : 1) * FK_PARTS * 128 * (int)sizeof(double2) +
                    (FUSED ? 0 : NOBS * TC_NP * (int)sizeof(float2)) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
-  static bool configured_on[64] = {};      // function attributes are per device: one flag per device ordinal
-  bool& configured = configured_on[env->cfg.device & 63];
-  if (!configured) {
+  static std::atomic<bool> configured_on[64];   // function attributes are per device: one flag per device ordinal
+  std::atomic<bool>& configured = configured_on[env->cfg.device & 63];
+  if (!configured.load(std::memory_order_acquire)) {
     AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.store(true, std::memory_order_release);
   }
   k_dm_phase_tc<STREHL, NOBS, MODE><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
   AOG_LAUNCH_CHECK();
@@ -2106,11 +2119,11 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       f1.num_items = nB;
       f1.apmask = ts->apmask;
       f1.dbg = tc_dbg; f1.err_flag = ts->err_flag;
-      static bool configured_on[64] = {};
-      bool& configured = configured_on[c.device & 63];
-      if (!configured) {
+      static std::atomic<bool> configured_on[64];
+      std::atomic<bool>& configured = configured_on[c.device & 63];
+      if (!configured.load(std::memory_order_acquire)) {
         AOG_CUDA(cudaFuncSetAttribute(k_field_mft1, cudaFuncAttributeMaxDynamicSharedMemorySize, F1_SMEM_BYTES));
-        configured = true;
+        configured.store(true, std::memory_order_release);
       }
       k_field_mft1<<<2 * std::min(max_clusters, nB), F1_THREADS, F1_SMEM_BYTES, st>>>(ts->tmA1_hi, ts->tmA1_lo, ts->tmPhi,
                                                                                    ts->tmTout_hi, ts->tmTout_lo, f1);

@@ -63,7 +63,11 @@ class _AOCore:
             setattr(self, k, getattr(cfg, k))
         self.num_focal_pixels_fiber = cfg.num_focal_pixels_fiber
         self.num_focal_pixels_fiber_subsample = cfg.obs_dim
-        self._seed = 0 if seed is None else int(seed)
+        # The reference draws its screens and noise from NumPy's unseeded global generator (every construction is a
+        # new atmosphere), so seed=None takes fresh entropy; only an explicit seed is deterministic.  The seed in
+        # use is kept on the env (``seed_used``) so a run can be reproduced afterwards.
+        self._seed = (int(np.random.SeedSequence().entropy) & (2 ** 63 - 1)) if seed is None else int(seed)
+        self.seed_used = self._seed
         rng = np.random.default_rng(self._seed)
         self.tables = build_tables(cfg, rng=rng, overrides=tables)
         t = self.tables
@@ -143,19 +147,35 @@ class _AOCore:
         self.timestep, self.timestep_render, self.episode_no = c.timestep, c.timestep_render, c.episode_no
 
     def get_state(self):
-        """Environment state (absent in the reference): screens, DM actuators, counters."""
+        """Environment state (absent in the reference): screens, DM actuators, the Shack-Hartmann integrator's own
+        mirror, counters, and the key + draw counters of every random stream -- a ``set_state`` of this dict on an
+        env built with the same kwargs continues bit for bit (device noise included)."""
         c = self._h.counters()
-        return dict(screens=self._h.get_screens(), actuators=self._h.get_actuators(),
-                    timestep=c.timestep, timestep_render=c.timestep_render, episode_no=c.episode_no,
-                    extrusions=c.extrusions)
+        st = dict(screens=self._h.get_screens(), actuators=self._h.get_actuators(),
+                  timestep=c.timestep, timestep_render=c.timestep_render, episode_no=c.episode_no,
+                  extrusions=c.extrusions, screen_draws=c.screen_draws, sh_draws=c.sh_draws, seed=self._seed)
+        if self.SH_operation:
+            st['sh_actuators'] = self._h.get_sh_actuators()
+        return st
 
     def set_state(self, state):
         self._h.set_counters(column_origin=0)
         self._h.set_screens(state['screens'])
         self._h.set_actuators(state['actuators'])
+        if 'seed' in state:
+            self._reseed(state['seed'])
+        if self.SH_operation and 'sh_actuators' in state:
+            self._h.set_sh_actuators(state['sh_actuators'])
         self._h.set_counters(timestep=state['timestep'], timestep_render=state['timestep_render'],
-                             episode_no=state['episode_no'], extrusions=state['extrusions'], column_origin=0)
+                             episode_no=state['episode_no'], extrusions=state['extrusions'], column_origin=0,
+                             screen_draws=state.get('screen_draws', 0), sh_draws=state.get('sh_draws', 0))
         self._sync_counters()
+
+    def _reseed(self, seed):
+        """Re-key the device's random streams (extrusion noise, screen synthesis, photon noise)."""
+        self._seed = int(seed) & (2 ** 63 - 1)
+        self.seed_used = self._seed
+        self._h.reseed(self._seed)
 
     def close(self):
         self._h.close()
@@ -193,7 +213,12 @@ class AOEnv(_AOCore, Env):
         self.last_ssim = None
 
     def reset(self, seed=None, options=None):
-        """AO_env.py:74-103 -> (float16 obs [obs_dim^2], {}); seed/options ignored as in the reference."""
+        """AO_env.py:74-103 -> (float16 obs [obs_dim^2], {}).  The reference ignores ``seed`` (its noise comes from
+        NumPy's global generator); here ``seed=s`` re-keys the device's random streams first, so everything drawn from
+        this reset on (a ``semi_dynamic`` screen, extrusion noise, photon noise) is reproducible.  ``options`` is
+        ignored as in the reference."""
+        if seed is not None:
+            self._reseed(seed)
         h = self._h.reset_host()
         self._sync_counters()
         self.last_obs_f64 = h['obs_f64'][0].copy()
@@ -267,6 +292,10 @@ class AOVecEnv(_AOCore):
     resets after ``done``, as with the single env).  Sharding across GPUs: one instance per rank
     with ``env_id_base = rank * num_envs`` (RNG stream = global env id); no collective on the
     step path.
+
+    The tensors returned by ``reset`` / ``step`` / ``SH_step`` (``obs``, ``reward``, ``power``, ``sh_action``, the
+    ``done`` masks) are VIEWS OF REUSED OUTPUT BUFFERS: the next call overwrites them in place.  A caller that keeps
+    them across calls (a replay buffer, ``next_obs`` bookkeeping) must ``.clone()`` them -- ``rollout.py`` does.
     """
 
     def __init__(self, num_envs, atm_type='quasi_static', atm_vel=0, atm_fried=0.15, act_type='num_actuators',
@@ -310,6 +339,8 @@ class AOVecEnv(_AOCore):
         return self._torch.cuda.current_stream(self.device).cuda_stream
 
     def reset(self, seed=None, options=None):
+        if seed is not None:
+            self._reseed(seed)
         self._h.reset_device(self._out, self._stream())
         self._sync_counters()
         return self.obs, {}

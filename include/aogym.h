@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define AOG_ABI_VERSION 1
+#define AOG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define AOG_API __attribute__((visibility("default")))
@@ -164,7 +164,9 @@ typedef struct aog_counters {
   int64_t timestep_render;  /* per episode (AO_env.py:83,124) */
   int64_t episode_no;       /* AO_env.py:149 */
   int64_t column_origin;    /* ring-buffer origin of the screens */
-  int64_t extrusions;       /* extrusions done so far */
+  int64_t extrusions;       /* extrusions done so far (Philox offset of the extrusion noise) */
+  int64_t screen_draws;     /* von-Karman syntheses done so far (Philox offset of the screen generator) */
+  int64_t sh_draws;         /* SH_step calls so far (Philox offset of the camera's photon noise) */
 } aog_counters;
 
 AOG_API const char* aog_version(void);
@@ -206,6 +208,21 @@ AOG_API int aog_set_counters(aog_env* env, const aog_counters* in);
 /* DM actuators [N][K] FP64 (state that survives reset when flat_mirror_start == 0) */
 AOG_API int aog_get_actuators(aog_env* env, double* host_out);
 AOG_API int aog_set_actuators(aog_env* env, const double* host_in);
+
+/* actuators [N][K] FP64 of the Shack-Hartmann integrator's own mirror (AO_env.py:266,284-287,431); needs
+ * aog_sh_configure */
+AOG_API int aog_get_sh_actuators(aog_env* env, double* host_out);
+AOG_API int aog_set_sh_actuators(aog_env* env, const double* host_in);
+
+/* Re-key every random stream of the handle (extrusion noise, screen synthesis, photon noise) and restart their
+ * draw counters: what AOEnv.reset(seed=s) does.  The reference ignores the seed (AO_env.py:74) and draws from
+ * NumPy's global generator; here a seeded reset makes everything after it reproducible.  State (screens,
+ * actuators, time) is untouched. */
+AOG_API int aog_reseed(aog_env* env, uint64_t seed);
+
+/* 0, or AOG_ERR_CUDA with aog_last_error naming the pipeline barrier that timed out (the tensor / fused kernels
+ * trap instead of hanging; the flag lives in mapped host memory and stays readable after the trap) */
+AOG_API int aog_health(aog_env* env);
 
 AOG_API int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size_t count);
 
