@@ -31,7 +31,7 @@ TABLE_IDS = {
 INT32_TABLES = ('ar_stencil', 'sh_pix_offsets', 'sh_pix_index')
 SH_NOISE = {'none': 0, 'poisson': 1, 'injected': 2}
 FIELD_IDS = {'screen': 0, 'pupil': 1, 'focal': 2, 'focal_power': 3, 'obs_power': 4, 'actuators': 5,
-             'tc_pupil': 6, 'tc_stage1': 7, 'sh_image': 8, 'sh_actuators': 9}
+             'tc_pupil': 6, 'tc_stage1': 7, 'sh_image': 8, 'sh_actuators': 9, 'sh_image_tc': 10}
 
 
 class AogConfig(C.Structure):
@@ -100,6 +100,7 @@ def load():
         'aog_health': (C.c_int, [P]),
         'aog_get_field': (C.c_int, [P, C.c_int, C.c_int, P, C.c_size_t]),
         'aog_debug_poisson': (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_uint64, P]),
+        'aog_debug_poisson_f32': (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_uint64, P]),
         'aog_launch_count': (C.c_int64, [P]),
         'aog_chunk_size': (C.c_int, [P]),
         'aog_set_timing': (C.c_int, [P, C.c_int]),
@@ -228,7 +229,7 @@ class Handle:
         c = self.cfg
         P, nf2, n2 = c.num_pupil_pixels ** 2, c.num_focal_pixels ** 2, c.obs_dim ** 2
         size = {'screen': P, 'pupil': 2 * P, 'focal': 2 * nf2, 'focal_power': nf2, 'obs_power': n2,
-                'actuators': c.num_modes, 'tc_pupil': 2 * P, 'sh_image': P, 'sh_actuators': c.num_modes,
+                'actuators': c.num_modes, 'tc_pupil': 2 * P, 'sh_image': P, 'sh_image_tc': P, 'sh_actuators': c.num_modes,
                 'tc_stage1': 2 * c.num_focal_pixels * c.num_pupil_pixels}[which]
         out = np.empty(size)
         self.check(self.lib.aog_get_field(self._h, FIELD_IDS[which], env_index, _ptr(out), size), 'aog_get_field')

@@ -783,9 +783,16 @@ int aog_sh_step(aog_env* env, int noise_mode, const double* noisy_image_dev, dou
   if (noise_mode < AOG_SH_NOISE_NONE || noise_mode > AOG_SH_NOISE_INJECTED) AOG_FAIL(AOG_ERR_INVALID, "noise_mode");
   if (noise_mode == AOG_SH_NOISE_INJECTED && !noisy_image_dev) AOG_FAIL(AOG_ERR_INVALID, "noisy image missing");
   AOG_DEVICE(c.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c.precision != AOG_PRECISION_F64 && noise_mode != AOG_SH_NOISE_INJECTED) {
+    // tensor / fused precision: the Fresnel products on tcgen05, FP32 camera (sh_tensor.cuh); tables without the
+    // structure those kernels need fall through to the FP64 kernels below
+    const int trc = aog_tensor_sh_step(env, noise_mode, action_out_dev, st);
+    if (trc == AOG_OK) { env->sh_draws++; return AOG_OK; }
+    if (trc != AOG_ERR_UNSUPPORTED) return trc;
+  }
   int rc = ensure_f64_scratch(env);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   const int Np = c.num_pupil_pixels, K = c.num_modes, P = env->P, B = c.num_envs, Nsub = env->sh_num_sub;
   const long long sB = (long long)Np * std::max(c.num_focal_pixels, Np);
   const long long sC = (long long)std::max<size_t>(env->NF2, P);
@@ -954,6 +961,11 @@ int aog_get_field(aog_env* env, int which, int env_index, double* host_out, size
                         cudaMemcpyDeviceToHost));
     return AOG_OK;
   }
+  if (which == AOG_FIELD_SH_IMAGE_TC) {   // the same image through the tensor-core kernels (tests)
+    if (c.precision == AOG_PRECISION_F64) AOG_FAIL(AOG_ERR_INVALID, "tensor-path field on an FP64 handle");
+    if (!env->act_sh) AOG_FAIL(AOG_ERR_STATE, "aog_sh_configure not called");
+    return aog_tensor_sh_image(env, env_index, host_out, count);
+  }
   if (which == AOG_FIELD_SH_IMAGE) {   // noise-free camera image (power x dt) for the current state
     if (!env->act_sh || !env->have[AOG_TABLE_SH_FRESNEL] || !env->have[AOG_TABLE_SH_MLA_PHASE])
       AOG_FAIL(AOG_ERR_STATE, "Shack-Hartmann tables not set");
@@ -1034,6 +1046,11 @@ int aog_debug_poisson(int device, double lambda, int n, uint64_t seed, double* h
   const cudaError_t e = cudaMemcpy(host_out, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d);
   return e == cudaSuccess ? AOG_OK : AOG_ERR_CUDA;
+}
+
+int aog_debug_poisson_f32(int device, double lambda, int n, uint64_t seed, double* host_out) {
+  if (!host_out || n < 1 || !(lambda >= 0.0)) return AOG_ERR_INVALID;
+  return aog_tensor_debug_poisson(device, lambda, n, seed, host_out);
 }
 
 int64_t aog_launch_count(const aog_env* env) { return env ? env->launches : -1; }

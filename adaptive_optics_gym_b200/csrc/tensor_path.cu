@@ -36,6 +36,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace {
@@ -96,6 +97,23 @@ struct TensorState {
   CUtensorMap tmT128_hi, tmT128_lo;
   CUtensorMap tmTout_hi, tmTout_lo;                   // stage-1 epilogue stores: 128 rows x 16 columns, SWIZZLE_32B                   // stage-1 product, one env (128 rows) per box
   CUtensorMap tmAct_hi, tmAct_lo, tmModes_hi, tmModes_lo;
+  // ---- Shack-Hartmann integrator on the tensor cores (sh_tensor.cuh) ----
+  std::vector<double> h_shC, h_shMla, h_shPx, h_shPy;  // host copies of the SH tables the operands are built from
+  std::vector<int> h_shOff, h_shPix;
+  bool sh_have[6] = {false, false, false, false, false, false};   // fresnel, mla, offsets, index, x, y
+  bool sh_ready = false, sh_unsupported = false;
+  std::string sh_why;                                 // why the tables do not qualify (the FP64 kernels run instead)
+  __half* shCE_hi[2] = {nullptr, nullptr};            // [stage][2 parities][re | im][128 rows][256 K] operator embeddings
+  __half* shCE_lo[2] = {nullptr, nullptr};
+  __half* shEB_hi = nullptr; __half* shEB_lo = nullptr;   // [chunk][p][q][128 x][256 K] folded field
+  __half* shYB_hi = nullptr; __half* shYB_lo = nullptr;   // [chunk][q][p][128 i'][256 K] first product
+  float* shG = nullptr;                               // [chunk][p][q][128 i'][re 128 | im 128] second product
+  int16_t* shSlot = nullptr;                          // [P] lenslet slot of each camera pixel
+  double* shSlotC = nullptr;                          // [Nsub][3]
+  double shScale[2] = {1.0, 1.0};                     // power-of-two scales of the two operator tables
+  double shX0 = 0, shdX = 0, shY0 = 0, shdY = 0;
+  CUtensorMap tmShCE_hi[2], tmShCE_lo[2], tmShEB_hi, tmShEB_lo, tmShYB_hi, tmShYB_lo, tmShYout_hi, tmShYout_lo;
+  bool sh_buffers = false;
   double pupil_weight = 0.0;                          // |M1| (grid weight folded in the table)
   double lpw_scale = 0.0;
   int num_sms = 148;
@@ -546,7 +564,7 @@ constexpr int FK_PARTS = FK_EPI_WARPS / 4;
 constexpr int FK_COL_STRIDE = 53;
 template <int MODE>
 __device__ __forceinline__ int fk_column(int item_in_block) {
-  return MODE == 0 ? item_in_block : (item_in_block * FK_COL_STRIDE) % TC_NP;
+  return (MODE == 0 || MODE == 3) ? item_in_block : (item_in_block * FK_COL_STRIDE) % TC_NP;
 }
 constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
 constexpr int FK_SLOTS = 64;                            // Strehl / fibre partial slots per env (>= CTAs touching an env block)
@@ -566,7 +584,8 @@ __host__ __device__ constexpr int FK_NT(int nobs) { return (nobs + FK_JT + 1 + 1
 // Record = FK_NF(n) floats: [a, b per pair | centre a | R_0..R_2 | aperture], padded to a multiple of 4.
 // The tables are checked for both properties when they are uploaded; tables without them run kernel MODE 1.
 __host__ __device__ constexpr int FK_NF(int nobs) { return (2 * (nobs / 2) + (nobs & 1) + FK_JT + 1 + 3) & ~3; }
-// kernel MODE: 0 = tensor path (stores the phase for the MFT stages), 1 = fused, 2 = fused + symmetric tables
+// kernel MODE: 0 = tensor path (stores the phase for the MFT stages), 1 = fused, 2 = fused + symmetric tables,
+// 3 = phase only (the Shack-Hartmann path, sh_tensor.cuh: stores the phase, no detector / Strehl sums)
 __host__ __device__ constexpr int FK_TAB_TILE(int nobs, int mode) {
   return mode == 1 ? 16 * FK_NT(nobs) * 8 : (mode == 2 ? 16 * FK_NF(nobs) * 4 : 0);
 }
@@ -656,7 +675,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
   uint8_t* pf = base + FK_STAGES * FK_STAGE_BYTES;                       // phase prefetch ring of the epilogue warps
-  constexpr bool FUSED = MODE != 0, SYM = MODE == 2;
+  constexpr bool FUSED = MODE == 1 || MODE == 2, SYM = MODE == 2, PHASE_ONLY = MODE == 3;
   constexpr int PF_SLOT = FK_PF_SLOT(NOBS, MODE);
   constexpr int NT = FK_NT(NOBS);
   uint8_t* aux = pf + FK_PF_BYTES(NOBS, MODE);
@@ -676,7 +695,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
   const int item_lo = blockIdx.x * p.items_per_cta;
   const int item_hi = min(p.num_items, item_lo + p.items_per_cta);
 
-  if (!FUSED)
+  if (!FUSED && !PHASE_ONLY)
     for (int i = threadIdx.x; i < NOBS * Np; i += blockDim.x) m1o_s[i] = p.m1o32[i];
   for (int i = threadIdx.x; i < Np * (Np / 16); i += blockDim.x) apmask_s[i] = p.apmask[i];
   for (int xx = threadIdx.x; xx < Np; xx += blockDim.x) {
@@ -1039,7 +1058,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
                 *reinterpret_cast<float4*>(row_odd + 8 * h8) = odd ? make_float4(a[4], a[5], a[6], a[7]) : make_float4(r[0], r[1], r[2], r[3]);
             }
           }
-          {
+          if constexpr (!PHASE_ONLY) {
             // obs arm: 16-pixel partial sums in FP32, folded into FP64 per chunk
             float ore[NOBS], oim[NOBS];
 #pragma unroll
@@ -1075,7 +1094,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);       // this warp is done with the accumulator
-      if (valid) {
+      if (valid && !PHASE_ONLY) {
         float2* r = p.R4 + (((size_t)env * Np + x) * FK_PARTS + q) * NOBS;
 #pragma unroll
         for (int v = 0; v < NOBS; ++v) r[v] = make_float2((float)obs_re[v], (float)obs_im[v]);
@@ -1678,6 +1697,10 @@ void aog_tensor_destroy(aog_env* env) {
                   ts->m2oT, ts->gfib, ts->fib_part, ts->lpphase_f};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  void* shp[] = {ts->shCE_hi[0], ts->shCE_hi[1], ts->shCE_lo[0], ts->shCE_lo[1], ts->shEB_hi, ts->shEB_lo, ts->shYB_hi,
+                 ts->shYB_lo, ts->shG, ts->shSlot, ts->shSlotC};
+  for (void* p : shp)
+    if (p) cudaFree(p);
   if (ts->err_flag_host) cudaFreeHost(ts->err_flag_host);
   delete ts;
   env->tensor_state = nullptr;
@@ -1811,10 +1834,13 @@ int build_fused_records(aog_env* env, TensorState* ts) {
 }
 }  // namespace
 
+int aog_tensor_sh_table(aog_env* env, int which, const void* host);   // sh_tensor.cuh
+
 int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
   TensorState* ts = TS(env);
   const aog_config& c = env->cfg;
   const int Np = TC_NP, Nf = TC_NF;
+  if (which >= AOG_TABLE_SH_MLA_PHASE && which <= AOG_TABLE_SH_ACT0) return aog_tensor_sh_table(env, which, host);
   if (ts->fused && which == AOG_TABLE_LP_PHASE) {
     const double* m = static_cast<const double*>(host);
     ts->h_lpphase.assign(m, m + (size_t)2 * c.num_lp_modes);
@@ -2035,7 +2061,7 @@ int aog_tensor_check(aog_env* env) {
 namespace {
 template <bool STREHL, int NOBS, int MODE>
 int launch_phase(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
-  constexpr bool FUSED = MODE != 0;
+  constexpr bool FUSED = MODE == 1 || MODE == 2;
   const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES(NOBS, MODE) + 1024 + FK_AUX_BAR +
                    (FUSED ? 1 + FK_JT : 1) * FK_PARTS * 128 * (int)sizeof(double2) +
                    (FUSED ? 0 : NOBS * TC_NP * (int)sizeof(float2)) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
@@ -2176,3 +2202,5 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
   }
   return AOG_OK;
 }
+
+#include "sh_tensor.cuh"

@@ -110,7 +110,8 @@ typedef enum aog_field {
   AOG_FIELD_TC_PUPIL = 6,    /* [P]       complex, unit modulus x aperture */
   AOG_FIELD_TC_STAGE1 = 7,   /* [Nf*Np]   complex stage-1 product M1~ . E~ (unit-modulus twiddles) */
   AOG_FIELD_SH_IMAGE = 8,    /* [P]       noise-free Shack-Hartmann camera image for the current state */
-  AOG_FIELD_SH_ACTUATORS = 9 /* [K]       actuators of the SH integrator's own mirror */
+  AOG_FIELD_SH_ACTUATORS = 9,/* [K]       actuators of the SH integrator's own mirror */
+  AOG_FIELD_SH_IMAGE_TC = 10 /* [P]       the same camera image through the tensor-core kernels (tensor / fused handles) */
 } aog_field;
 
 typedef struct aog_config {
@@ -229,6 +230,9 @@ AOG_API int aog_get_field(aog_env* env, int which, int env_index, double* host_o
 /* test hook: n draws of the Shack-Hartmann camera's photon-noise sampler at rate lambda (Poisson below 1e6, rounded
  * normal above -- hcipy large_poisson, AO_env.py:274), Philox subsequence i for draw i; host_out [n] */
 AOG_API int aog_debug_poisson(int device, double lambda, int n, uint64_t seed, double* host_out);
+
+/* the FP32 photon-noise sampler of the tensor / fused handles' Shack-Hartmann camera (same test hook) */
+AOG_API int aog_debug_poisson_f32(int device, double lambda, int n, uint64_t seed, double* host_out);
 
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 AOG_API int64_t aog_launch_count(const aog_env* env);
