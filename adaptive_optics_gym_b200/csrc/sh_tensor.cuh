@@ -54,8 +54,14 @@ struct ShGemmParams {
   int* err_flag;
 };
 
-__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// 256-bit stores (sm_100): one instruction writes a whole 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
 // STAGE 1: resident = A (M side: rows [Yr(i') | Yi(i')] of C1_parity, parity = p), streamed = B (N side: the folded
@@ -231,8 +237,8 @@ k_sh_gemm(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CU
             tc_wait_ld();
             if (row < SH_NH) {
 #pragma unroll
-              for (int k = 0; k < 32; k += 4)
-                if (i * 16 + k < SH_NH) st_global_v4(grow + i * 16 + k, v[k], v[k + 1], v[k + 2], v[k + 3]);
+              for (int k = 0; k < 32; k += 8)
+                if (i * 16 + k < SH_NH) st_global_v8(grow + i * 16 + k, v + k);
             }
           }
         }
@@ -314,13 +320,10 @@ k_sh_fold(const float* __restrict__ phi, const uint16_t* __restrict__ apmask, __
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     const size_t o = ((size_t)(env * 4 + b) * SH_HP + x) * SH_K + kb * KB;     // halves
-    uint4* dh = reinterpret_cast<uint4*>(e_hi + o);
-    uint4* dl = reinterpret_cast<uint4*>(e_lo + o);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      dh[k] = make_uint4(oh[b][4 * k], oh[b][4 * k + 1], oh[b][4 * k + 2], oh[b][4 * k + 3]);
-      dl[k] = make_uint4(ol[b][4 * k], ol[b][4 * k + 1], ol[b][4 * k + 2], ol[b][4 * k + 3]);
-    }
+    st_global_v8(e_hi + o, oh[b]);
+    st_global_v8(e_hi + o + 16, oh[b] + 8);
+    st_global_v8(e_lo + o, ol[b]);
+    st_global_v8(e_lo + o + 16, ol[b] + 8);
   }
 }
 
@@ -345,32 +348,24 @@ __device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5
 //                  (k = lam + sqrt(lam) z + (z^2 - 1) / 6 - (z^3 - 7 z) / (72 sqrt(lam)), rounded): mean, variance and
 //                  third moment of Poisson(lam) to O(1 / lam) -- the camera's pixels sit at 1e2 ... 1e7 photons
 //   10 <= lam < 64 Hoermann's PTRS (exact; NumPy's own algorithm), < 10 Knuth's product of uniforms (exact)
-// `first` is the counter block shared by a pixel PAIR (`which` selects this pixel's two words); the rare rejection
-// paths draw further blocks at ctr.w = 1 + 2 n + which.
-__device__ float poisson_f32(float lam, uint4 first, int which, uint4 ctr, uint2 key) {
+// The common branch takes one standard normal z (the caller makes four of them, for the four mirror pixels, from ONE
+// Philox block by two Box-Muller transforms); the rare small-rate branch draws its own blocks at ctr.w = 1 + 4 n + m.
+__device__ __noinline__ float poisson_small_f32(float lam, uint4 ctr, uint2 key, int m) {
   if (!(lam > 0.f)) return 0.f;
-  const uint32_t r0 = which ? first.z : first.x, r1 = which ? first.w : first.y;
-  if (lam >= 64.f) {
-    const float z = sqrtf(-2.f * __logf(u01(r0))) * __cosf(6.28318530718f * u01(r1));
-    const float sl = sqrtf(lam);
-    if (lam > 1e6f) return rintf(lam + sl * z);
-    const float z2 = z * z;
-    return fmaxf(rintf(lam + sl * z + (z2 - 1.f) * (1.f / 6.f) - (z2 * z - 7.f * z) / (72.f * sl)), 0.f);
-  }
-  uint32_t w[4] = {r0, r1, 0u, 0u};
-  int used = 0, end = 2;
+  uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+  int used = 4;
   uint32_t nblk = 0;
   auto next = [&]() -> float {
-    if (used == end) {
+    if (used == 4) {
       uint4 c2 = ctr;
-      c2.w = 1u + 2u * nblk + (uint32_t)which;
+      c2.w = 1u + 4u * nblk + (uint32_t)m;
       ++nblk;
-      const uint4 blk = philox4x32_10(c2, key);
-      w[0] = blk.x; w[1] = blk.y; w[2] = blk.z; w[3] = blk.w;
+      blk = philox4x32_10(c2, key);
       used = 0;
-      end = 4;
     }
-    return u01(w[used++]);
+    const uint32_t r = used == 0 ? blk.x : (used == 1 ? blk.y : (used == 2 ? blk.z : blk.w));
+    ++used;
+    return u01(r);
   };
   if (lam < 10.f) {
     const float enlam = __expf(-lam);
@@ -393,6 +388,21 @@ __device__ float poisson_f32(float lam, uint4 first, int which, uint4 ctr, uint2
     if (logf(V) + logf(invalpha) - logf(a / (us * us) + b) <= -lam + k * loglam - lgammaf(k + 1.f)) return k;
   }
 }
+__device__ __forceinline__ float poisson_large_f32(float lam, float z) {
+  const float sl = sqrtf(lam);
+  if (lam > 1e6f) return rintf(fmaf(sl, z, lam));
+  const float z2 = z * z;
+  return fmaxf(rintf(lam + sl * z + (z2 - 1.f) * (1.f / 6.f) - (z2 * z - 7.f * z) * __fdividef(1.f, 72.f * sl)), 0.f);
+}
+// four standard normals from one counter block
+__device__ __forceinline__ void normals4(uint4 r, float* z) {
+  const float ra = sqrtf(-2.f * __logf(u01(r.x))), rb = sqrtf(-2.f * __logf(u01(r.z)));
+  float s, c;
+  __sincosf(6.28318530718f * u01(r.y), &s, &c);
+  z[0] = ra * c; z[1] = ra * s;
+  __sincosf(6.28318530718f * u01(r.w), &s, &c);
+  z[2] = rb * c; z[3] = rb * s;
+}
 
 struct ShCamParams {
   const float* G;            // [env][p][q][128 i'][re 128 | im 128]
@@ -408,71 +418,92 @@ struct ShCamParams {
   unsigned long long seed, env_id_base, draw;
 };
 
-// Block per environment, thread = fold column u: walks the 120 fold rows, reads the four blocks (coalesced along u),
-// unfolds to the four mirror pixels, image = |F|^2 x scale, photon noise, and adds every pixel to its lenslet's
-// (flux, flux x col, flux x row) sums -- in 64-bit FIXED POINT through shared-memory atomics, so the sums do not
-// depend on the order of the additions (deterministic, like the FP64 path's per-lenslet warps).  A thread keeps the
-// running sums of its four pixel streams in registers and flushes them when the lenslet changes (every 20 rows).
-__global__ void __launch_bounds__(128) k_sh_camera_tc(const ShCamParams p) {
+// Block per environment, thread = (fold column u, one of CAM_PARTS row ranges): walks its fold rows, reads the four
+// blocks (coalesced along u), unfolds to the four mirror pixels, image = |F|^2 x scale, photon noise (one Philox
+// block per fold pixel), and adds every pixel to its lenslet's (flux, flux x col, flux x row) sums.  A thread keeps
+// the running sums of its four pixel streams in registers (FP64, fixed order) and, when the lenslet changes (every 20
+// rows), adds them to the block's sums in 64-bit FIXED POINT through shared-memory atomics: integer addition does
+// not depend on the order of the additions, so the result is deterministic like the FP64 path's per-lenslet warps.
+constexpr int CAM_PARTS = 2, CAM_THREADS = 128 * CAM_PARTS;
+__global__ void __launch_bounds__(CAM_THREADS) k_sh_camera_tc(const ShCamParams p) {
   constexpr int Np = TC_NP;
   extern __shared__ unsigned long long cam_acc[];       // [3 Nsub] fixed-point sums, then [2 Nsub] doubles (slopes)
   double* slopes = reinterpret_cast<double*>(cam_acc + 3 * p.Nsub);
-  const int b = blockIdx.x, u = threadIdx.x;
+  const int b = blockIdx.x, u = threadIdx.x & 127, part = threadIdx.x >> 7;
   for (int i = threadIdx.x; i < 3 * p.Nsub; i += blockDim.x) cam_acc[i] = 0ull;
   __syncthreads();
-  if (u < SH_NH) {
-    const float* g = p.G + (size_t)b * 4 * SH_HP * (2 * SH_HP);
-    const float qs = (float)(1u << p.qshift);
+  {
+    const bool active = u < SH_NH;
+    const int uu = active ? u : 0;
+    const int lane = threadIdx.x & 31;
+    const float* g = p.G + (size_t)b * 4 * SH_HP * (2 * SH_HP) + uu;
+    const double qs = (double)(1ull << p.qshift);
     const unsigned long long genv = p.env_id_base + p.env0 + b;
     const uint2 key = make_uint2((uint32_t)p.seed ^ (uint32_t)(genv >> 32), (uint32_t)(p.seed >> 32) ^ (uint32_t)(p.draw >> 32));
+    const bool noisy = p.noise_mode == AOG_SH_NOISE_POISSON;
     int cur[4] = {-1, -1, -1, -1};
-    long long f[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0};
-    auto flush = [&](int m) {
-      if (cur[m] >= 0 && f[m] != 0) {
-        atomicAdd(&cam_acc[3 * cur[m]], (unsigned long long)f[m]);
-        atomicAdd(&cam_acc[3 * cur[m] + 1], (unsigned long long)sx[m]);
-        atomicAdd(&cam_acc[3 * cur[m] + 2], (unsigned long long)sy[m]);
+    double f[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0};
+    // Warp-collective flush of stream m for the lanes with `need`: the lanes of a warp that sit in the same lenslet
+    // are neighbours, so a segmented scan over equal slots leaves each lenslet's total in its last lane, which alone
+    // touches shared memory (<= 3 atomics per warp and sum instead of 32 colliding ones).
+    auto flush = [&](int m, bool need) {
+      const bool give = need && cur[m] >= 0 && f[m] != 0.0;
+      const int k = give ? cur[m] : -1 - lane;                       // distinct negative keys: never merged
+      const int col = (m & 2) ? Np - 1 - uu : uu;
+      long long a = give ? __double2ll_rn(f[m] * qs) : 0ll;
+      long long bx = a * col;                                        // the column is fixed along a stream
+      long long cy = give ? __double2ll_rn(sy[m] * qs) : 0ll;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ko = __shfl_up_sync(0xffffffffu, k, o);
+        const long long ao = __shfl_up_sync(0xffffffffu, a, o), bo = __shfl_up_sync(0xffffffffu, bx, o),
+                        co = __shfl_up_sync(0xffffffffu, cy, o);
+        if (lane >= o && ko == k) { a += ao; bx += bo; cy += co; }
       }
-      f[m] = sx[m] = sy[m] = 0;
+      const int kn = __shfl_down_sync(0xffffffffu, k, 1);
+      if (give && (lane == 31 || kn != k)) {
+        atomicAdd(&cam_acc[3 * k], (unsigned long long)a);
+        atomicAdd(&cam_acc[3 * k + 1], (unsigned long long)bx);
+        atomicAdd(&cam_acc[3 * k + 2], (unsigned long long)cy);
+      }
+      if (need) f[m] = sy[m] = 0.0;
     };
-    for (int i = 0; i < SH_NH; ++i) {
+    constexpr int ROWS = SH_NH / CAM_PARTS;
+    for (int i = part * ROWS; i < (part + 1) * ROWS; ++i) {
       float re[4], im[4];
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
-        const float* r = g + ((size_t)blk * SH_HP + i) * (2 * SH_HP) + u;
+        const float* r = g + ((size_t)blk * SH_HP + i) * (2 * SH_HP);
         re[blk] = __ldg(r);
         im[blk] = __ldg(r + SH_HP);
       }
       // blocks: 0 = (p+, q+), 1 = (p+, q-), 2 = (p-, q+), 3 = (p-, q-);  p = row fold, q = column fold
+      // pixel m: 0 = (i, u), 1 = (N-1-i, u), 2 = (i, N-1-u), 3 = (N-1-i, N-1-u)
       const float fr[4] = {(re[0] + re[1]) + (re[2] + re[3]), (re[0] + re[1]) - (re[2] + re[3]),
                            (re[0] - re[1]) + (re[2] - re[3]), (re[0] - re[1]) - (re[2] - re[3])};
       const float fi[4] = {(im[0] + im[1]) + (im[2] + im[3]), (im[0] + im[1]) - (im[2] + im[3]),
                            (im[0] - im[1]) + (im[2] - im[3]), (im[0] - im[1]) - (im[2] - im[3])};
-      // pixel m: 0 = (i, u), 1 = (N-1-i, u), 2 = (i, N-1-u), 3 = (N-1-i, N-1-u)
-      uint4 rnd[2], ctr[2];
-      if (p.noise_mode == AOG_SH_NOISE_POISSON) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {      // one counter block per pixel PAIR (m = 2 h, 2 h + 1) and SH_step call
-          ctr[h] = make_uint4((uint32_t)((i * SH_NH + u) * 2 + h), (uint32_t)genv, (uint32_t)p.draw, 0u);
-          rnd[h] = philox4x32_10(ctr[h], key);
-        }
-      }
+      float z[4];
+      uint4 ctr = make_uint4((uint32_t)(i * SH_NH + uu), (uint32_t)genv, (uint32_t)p.draw, 0u);
+      if (noisy) normals4(philox4x32_10(ctr, key), z);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const int row = (m & 1) ? Np - 1 - i : i, col = (m & 2) ? Np - 1 - u : u;
-        const int sl = p.slot[row * Np + col];
-        if (sl != cur[m]) { flush(m); cur[m] = sl; }
+        const int row = (m & 1) ? Np - 1 - i : i, col = (m & 2) ? Np - 1 - uu : uu;
+        const int sl = active ? (int)p.slot[row * Np + col] : -1;
+        const bool need = sl != cur[m];
+        if (__any_sync(0xffffffffu, need)) {           // lenslet rows end together: normally the whole warp at once
+          flush(m, need);
+          if (need) cur[m] = sl;
+        }
         if (sl < 0) continue;
         float v = (fr[m] * fr[m] + fi[m] * fi[m]) * p.img_scale;
-        if (p.noise_mode == AOG_SH_NOISE_POISSON) v = poisson_f32(v, rnd[m >> 1], m & 1, ctr[m >> 1], key);
-        const long long vq = __float2ll_rn(v * qs);
-        f[m] += vq;
-        sx[m] += vq * col;
-        sy[m] += vq * row;
+        if (noisy) v = v >= 64.f ? poisson_large_f32(v, z[m]) : poisson_small_f32(v, ctr, key, m);
+        f[m] += (double)v;
+        sy[m] = fma((double)v, (double)row, sy[m]);
       }
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) flush(m);
+    for (int m = 0; m < 4; ++m) flush(m, true);
   }
   __syncthreads();
   const double inv_q = 1.0 / (double)(1ull << p.qshift);
@@ -504,8 +535,10 @@ __global__ void k_debug_poisson_f32(float lam, int n, unsigned long long seed, d
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  const uint4 ctr = make_uint4((uint32_t)i, 0x51u, 0u, 0u);
-  out[i] = (double)poisson_f32(lam, philox4x32_10(ctr, key), i & 1, ctr, key);
+  const uint4 ctr = make_uint4((uint32_t)(i >> 2), 0x51u, 0u, 0u);
+  float z[4];
+  normals4(philox4x32_10(ctr, key), z);
+  out[i] = (double)(lam >= 64.f ? poisson_large_f32(lam, z[i & 3]) : poisson_small_f32(lam, ctr, key, i & 3));
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -764,7 +797,7 @@ int aog_tensor_sh_step(aog_env* env, int noise_mode, double* action_out_dev, cud
     cp.X0 = ts->shX0; cp.dX = ts->shdX; cp.Y0 = ts->shY0; cp.dY = ts->shdY;
     cp.seed = c.seed ^ 0xD1B54A32D192ED03ull; cp.env_id_base = (unsigned long long)c.env_id_base;
     cp.draw = (unsigned long long)env->sh_draws;
-    k_sh_camera_tc<<<nB, 128, (size_t)Nsub * (3 * sizeof(unsigned long long) + 2 * sizeof(double)), st>>>(cp);
+    k_sh_camera_tc<<<nB, CAM_THREADS, (size_t)Nsub * (3 * sizeof(unsigned long long) + 2 * sizeof(double)), st>>>(cp);
     AOG_LAUNCH_CHECK();
   }
   return AOG_OK;

@@ -186,7 +186,8 @@ class AOEnv(_AOCore, Env):
 
     Extra optional kwargs (defaults = reference constants): ``device``, ``seed``, ``precision``
     ('f64' exact arithmetic | 'tensor' split-fp16 tcgen05 MFT), ``tables`` (override any set-up
-    table), ``initial_screen``, ``num_pupil_pixels``, ``num_focal_pixels_fiber``.
+    table), ``initial_screen``, ``num_pupil_pixels``, ``num_focal_pixels_fiber``, ``env_id_base`` (the global
+    id of this env: the key of its device random streams, so that a single env can replay env i of an ``AOVecEnv``).
     """
 
     metadata = {'render_modes': ['human']}
@@ -195,7 +196,7 @@ class AOEnv(_AOCore, Env):
                  obs_dim=2, rew_type='strehl_ratio', rew_threshold=None, timesteps_per_episode=20,
                  flat_mirror_start_per_episode=True, SH_operation=False, *, device=0, seed=None,
                  precision='f64', tables=None, initial_screen=None, num_pupil_pixels=240,
-                 num_focal_pixels_fiber=128):
+                 num_focal_pixels_fiber=128, env_id_base=0):
         super().__init__()
         self._setup(atm_type=atm_type, atm_vel=atm_vel, atm_fried=atm_fried, act_type=act_type, act_dim=act_dim,
                     obs_dim=obs_dim, rew_type=rew_type, rew_threshold=rew_threshold,
@@ -203,7 +204,7 @@ class AOEnv(_AOCore, Env):
                     flat_mirror_start_per_episode=flat_mirror_start_per_episode, SH_operation=SH_operation,
                     num_envs=1, device=device, seed=seed, precision=precision, tables=tables,
                     initial_screens=initial_screen, num_pupil_pixels=num_pupil_pixels,
-                    num_focal_pixels_fiber=num_focal_pixels_fiber, env_id_base=0)
+                    num_focal_pixels_fiber=num_focal_pixels_fiber, env_id_base=env_id_base)
         # AO_env.py:45-46
         self.observation_space = spaces.Box(low=-1, high=1, shape=(self.num_focal_pixels_fiber_subsample ** 2,),
                                             dtype=np.float16)
