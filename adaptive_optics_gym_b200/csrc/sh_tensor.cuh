@@ -344,59 +344,45 @@ __device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5
 
 // Photon count at rate lam (hcipy large_poisson, AO_env.py:274) in FP32 arithmetic:
 //   lam > 1e6      rounded normal, as large_poisson itself does
-//   lam >= 64      normal quantile with the Cornish-Fisher skewness and kurtosis terms of the Poisson law
-//                  (k = lam + sqrt(lam) z + (z^2 - 1) / 6 - (z^3 - 7 z) / (72 sqrt(lam)), rounded): mean, variance and
-//                  third moment of Poisson(lam) to O(1 / lam) -- the camera's pixels sit at 1e2 ... 1e7 photons
-//   10 <= lam < 64 Hoermann's PTRS (exact; NumPy's own algorithm), < 10 Knuth's product of uniforms (exact)
+//   lam >= 10      normal quantile with the Cornish-Fisher skewness and kurtosis terms of the Poisson law
+//                  (k = lam + sqrt(lam) z + (z^2 - 1) / 6 - (z^3 - z) / (72 sqrt(lam)), rounded): mean, variance and
+//                  third moment of Poisson(lam) to O(1 / lam) -- the camera's pixels sit at 1e1 ... 1e7 photons
+//   lam < 10       Knuth's product of uniforms (exact)
 // The common branch takes one standard normal z (the caller makes four of them, for the four mirror pixels, from ONE
 // Philox block by two Box-Muller transforms); the rare small-rate branch draws its own blocks at ctr.w = 1 + 4 n + m.
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __noinline__ float poisson_small_f32(float lam, uint4 ctr, uint2 key, int m) {
   if (!(lam > 0.f)) return 0.f;
-  uint4 blk = make_uint4(0u, 0u, 0u, 0u);
-  int used = 4;
-  uint32_t nblk = 0;
-  auto next = [&]() -> float {
-    if (used == 4) {
-      uint4 c2 = ctr;
-      c2.w = 1u + 4u * nblk + (uint32_t)m;
-      ++nblk;
-      blk = philox4x32_10(c2, key);
-      used = 0;
-    }
-    const uint32_t r = used == 0 ? blk.x : (used == 1 ? blk.y : (used == 2 ? blk.z : blk.w));
-    ++used;
-    return u01(r);
-  };
-  if (lam < 10.f) {
-    const float enlam = __expf(-lam);
-    float prod = 1.f;
-    int k = 0;
-    while (true) {
-      prod *= next();
+  const float enlam = __expf(-lam);
+  float prod = 1.f;
+  int k = 0;
+  for (uint32_t nblk = 0;; ++nblk) {
+    uint4 c2 = ctr;
+    c2.w = 1u + 4u * nblk + (uint32_t)m;
+    const uint4 blk = philox4x32_10(c2, key);
+    const uint32_t w[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      prod *= u01(w[j]);
       if (prod > enlam) ++k; else return (float)k;
     }
   }
-  const float slam = sqrtf(lam), loglam = logf(lam);
-  const float b = 0.931f + 2.53f * slam, a = -0.059f + 0.02483f * b;
-  const float invalpha = 1.1239f + 1.1328f / (b - 3.4f), vr = 0.9277f - 3.6224f / (b - 2.f);
-  while (true) {
-    const float U = next() - 0.5f, V = next();
-    const float us = 0.5f - fabsf(U);
-    const float k = floorf((2.f * a / us + b) * U + lam + 0.43f);
-    if (us >= 0.07f && V <= vr) return k;
-    if (k < 0.f || (us < 0.013f && V > us)) continue;
-    if (logf(V) + logf(invalpha) - logf(a / (us * us) + b) <= -lam + k * loglam - lgammaf(k + 1.f)) return k;
-  }
 }
 __device__ __forceinline__ float poisson_large_f32(float lam, float z) {
-  const float sl = sqrtf(lam);
-  if (lam > 1e6f) return rintf(fmaf(sl, z, lam));
+  // rounding to an integer adds 1/12 of variance: taken off the normal's scale, so that var = lam
+  const float sl = sqrt_fast(lam - (1.f / 12.f));
   const float z2 = z * z;
-  return fmaxf(rintf(lam + sl * z + (z2 - 1.f) * (1.f / 6.f) - (z2 * z - 7.f * z) * __fdividef(1.f, 72.f * sl)), 0.f);
+  // above 1e6 the correction terms are below the rounding of lam itself: large_poisson's plain rounded normal
+  const float corr = lam > 1e6f ? 0.f : (z2 - 1.f) * (1.f / 6.f) - (z2 * z - z) * __fdividef(1.f, 72.f * sl);
+  return fmaxf(rintf(fmaf(sl, z, lam) + corr), 0.f);
 }
 // four standard normals from one counter block
 __device__ __forceinline__ void normals4(uint4 r, float* z) {
-  const float ra = sqrtf(-2.f * __logf(u01(r.x))), rb = sqrtf(-2.f * __logf(u01(r.z)));
+  const float ra = sqrt_fast(-2.f * __logf(u01(r.x))), rb = sqrt_fast(-2.f * __logf(u01(r.z)));
   float s, c;
   __sincosf(6.28318530718f * u01(r.y), &s, &c);
   z[0] = ra * c; z[1] = ra * s;
@@ -425,7 +411,7 @@ struct ShCamParams {
 // rows), adds them to the block's sums in 64-bit FIXED POINT through shared-memory atomics: integer addition does
 // not depend on the order of the additions, so the result is deterministic like the FP64 path's per-lenslet warps.
 constexpr int CAM_PARTS = 2, CAM_THREADS = 128 * CAM_PARTS;
-__global__ void __launch_bounds__(CAM_THREADS) k_sh_camera_tc(const ShCamParams p) {
+__global__ void __launch_bounds__(CAM_THREADS, 3) k_sh_camera_tc(const ShCamParams p) {
   constexpr int Np = TC_NP;
   extern __shared__ unsigned long long cam_acc[];       // [3 Nsub] fixed-point sums, then [2 Nsub] doubles (slopes)
   double* slopes = reinterpret_cast<double*>(cam_acc + 3 * p.Nsub);
@@ -469,14 +455,28 @@ __global__ void __launch_bounds__(CAM_THREADS) k_sh_camera_tc(const ShCamParams 
       if (need) f[m] = sy[m] = 0.0;
     };
     constexpr int ROWS = SH_NH / CAM_PARTS;
-    for (int i = part * ROWS; i < (part + 1) * ROWS; ++i) {
-      float re[4], im[4];
+    float nre[4], nim[4];                 // the next row's blocks, loaded one row ahead of the arithmetic
+    int nsl[4];
+    auto fetch = [&](int i) {
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
         const float* r = g + ((size_t)blk * SH_HP + i) * (2 * SH_HP);
-        re[blk] = __ldg(r);
-        im[blk] = __ldg(r + SH_HP);
+        nre[blk] = __ldg(r);
+        nim[blk] = __ldg(r + SH_HP);
       }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int row = (m & 1) ? Np - 1 - i : i, col = (m & 2) ? Np - 1 - uu : uu;
+        nsl[m] = active ? (int)__ldg(p.slot + row * Np + col) : -1;
+      }
+    };
+    fetch(part * ROWS);
+    for (int i = part * ROWS; i < (part + 1) * ROWS; ++i) {
+      float re[4], im[4];
+      int slv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { re[k] = nre[k]; im[k] = nim[k]; slv[k] = nsl[k]; }
+      if (i + 1 < (part + 1) * ROWS) fetch(i + 1);
       // blocks: 0 = (p+, q+), 1 = (p+, q-), 2 = (p-, q+), 3 = (p-, q-);  p = row fold, q = column fold
       // pixel m: 0 = (i, u), 1 = (N-1-i, u), 2 = (i, N-1-u), 3 = (N-1-i, N-1-u)
       const float fr[4] = {(re[0] + re[1]) + (re[2] + re[3]), (re[0] + re[1]) - (re[2] + re[3]),
@@ -488,8 +488,8 @@ __global__ void __launch_bounds__(CAM_THREADS) k_sh_camera_tc(const ShCamParams 
       if (noisy) normals4(philox4x32_10(ctr, key), z);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const int row = (m & 1) ? Np - 1 - i : i, col = (m & 2) ? Np - 1 - uu : uu;
-        const int sl = active ? (int)p.slot[row * Np + col] : -1;
+        const int row = (m & 1) ? Np - 1 - i : i;
+        const int sl = slv[m];
         const bool need = sl != cur[m];
         if (__any_sync(0xffffffffu, need)) {           // lenslet rows end together: normally the whole warp at once
           flush(m, need);
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(CAM_THREADS) k_sh_camera_tc(const ShCamParams 
         }
         if (sl < 0) continue;
         float v = (fr[m] * fr[m] + fi[m] * fi[m]) * p.img_scale;
-        if (noisy) v = v >= 64.f ? poisson_large_f32(v, z[m]) : poisson_small_f32(v, ctr, key, m);
+        if (noisy) v = v >= 10.f ? poisson_large_f32(v, z[m]) : poisson_small_f32(v, ctr, key, m);
         f[m] += (double)v;
         sy[m] = fma((double)v, (double)row, sy[m]);
       }
@@ -538,7 +538,7 @@ __global__ void k_debug_poisson_f32(float lam, int n, unsigned long long seed, d
   const uint4 ctr = make_uint4((uint32_t)(i >> 2), 0x51u, 0u, 0u);
   float z[4];
   normals4(philox4x32_10(ctr, key), z);
-  out[i] = (double)(lam >= 64.f ? poisson_large_f32(lam, z[i & 3]) : poisson_small_f32(lam, ctr, key, i & 3));
+  out[i] = (double)(lam >= 10.f ? poisson_large_f32(lam, z[i & 3]) : poisson_small_f32(lam, ctr, key, i & 3));
 }
 
 // ----------------------------------------------------------------------------- host side

@@ -425,13 +425,13 @@ def test_shack_hartmann_tensor_cores_vec_matches_single_and_f64(precision):
 
 def test_device_poisson_sampler_f32_statistics():
     """The FP32 photon-noise sampler of the tensor / fused camera: mean, variance and skewness of Poisson(lambda) in
-    every branch (Knuth, PTRS, Cornish-Fisher normal, rounded normal above 1e6 as hcipy large_poisson)."""
+    every branch (Knuth below 10, Cornish-Fisher normal, rounded normal above 1e6 as hcipy large_poisson)."""
     import ctypes as C
     from adaptive_optics_gym_b200 import _lib
     lib = _lib.load()
     n = 400000
     out = np.empty(n)
-    for k, lam in enumerate((0.3, 4.0, 9.99, 10.0, 37.5, 63.9, 64.0, 640.0, 3999.0, 2.5e5, 5e6)):
+    for k, lam in enumerate((0.3, 4.0, 9.99, 10.0, 15.0, 37.5, 64.0, 640.0, 3999.0, 2.5e5, 5e6)):
         rc = lib.aog_debug_poisson_f32(0, C.c_double(lam), n, C.c_uint64(77 + k), out.ctypes.data_as(C.c_void_p))
         assert rc == 0
         assert np.all(out >= 0) and np.all(out == np.round(out))
