@@ -105,6 +105,7 @@ def load():
         'aog_chunk_size': (C.c_int, [P]),
         'aog_set_timing': (C.c_int, [P, C.c_int]),
         'aog_last_mft_ms': (C.c_double, [P]),
+        'aog_last_timings': (C.c_int, [P, C.POINTER(C.c_double), C.c_int]),
         'aog_last_kernel_ms': (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
@@ -320,6 +321,14 @@ class Handle:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self.check(self.lib.aog_last_kernel_ms(self._h, C.byref(a), C.byref(b), C.byref(c)), 'aog_last_kernel_ms')
         return dict(field=a.value, stage1=b.value, stage2=c.value)
+
+    def last_timings(self):
+        """{'extrusions_ms', 'extrusions', 'sh_phase', 'sh_fold', 'sh_gemm1', 'sh_gemm2', 'sh_camera'} of the last
+        timed step (ms; -1 = not recorded)"""
+        buf = (C.c_double * 7)()
+        self.check(self.lib.aog_last_timings(self._h, buf, 7), 'aog_last_timings')
+        names = ('extrusions_ms', 'extrusions', 'sh_phase', 'sh_fold', 'sh_gemm1', 'sh_gemm2', 'sh_camera')
+        return dict(zip(names, (float(v) for v in buf)))
 
     def last_mft_ms(self):
         return float(self.lib.aog_last_mft_ms(self._h))

@@ -336,6 +336,7 @@ int aog_create(const aog_config* cfg, aog_env** out) {
   AOG_CUDA(cudaEventCreate(&env->ev1));
   AOG_CUDA(cudaEventCreate(&env->evf));
   AOG_CUDA(cudaEventCreate(&env->evm));
+  for (auto& e : env->tev) AOG_CUDA(cudaEventCreate(&e));
   return AOG_OK;
 }
 
@@ -362,6 +363,8 @@ void aog_destroy(aog_env* env) {
   if (env->ev1) cudaEventDestroy(env->ev1);
   if (env->evf) cudaEventDestroy(env->evf);
   if (env->evm) cudaEventDestroy(env->evm);
+  for (auto& e : env->tev)
+    if (e) cudaEventDestroy(e);
   delete env;
 }
 
@@ -697,8 +700,15 @@ int aog_step(aog_env* env, const void* actions_dev, int act_dtype, const double*
   const int64_t old_t = env->cnt.timestep;
   env->cnt.timestep += 1;
   env->cnt.timestep_render += 1;
+  if (env->timing) AOG_CUDA(cudaEventRecord(env->tev[0], st));
+  const int64_t ext_before = env->cnt.extrusions;
   int rc = evolve_to(env, env->cnt.timestep, old_t, noise_dev, st);
   if (rc) return rc;
+  if (env->timing) {
+    AOG_CUDA(cudaEventRecord(env->tev[1], st));
+    env->last_extrusions = (int)(env->cnt.extrusions - ext_before);
+    env->tev_ext_valid = true;
+  }
   // AO_env.py:132-144
   aog_outputs o{};
   if (out_dev) o = *out_dev;
@@ -1061,6 +1071,7 @@ int aog_set_timing(aog_env* env, int enabled) {
   if (!env) return AOG_ERR_INVALID;
   env->timing = enabled != 0;
   env->ev_valid = false;
+  env->tev_ext_valid = env->tev_sh_valid = false;
   return AOG_OK;
 }
 
@@ -1075,6 +1086,26 @@ int aog_last_kernel_ms(aog_env* env, double* field_ms, double* stage1_ms, double
   if (field_ms) *field_ms = a;
   if (stage1_ms) *stage1_ms = b;
   if (stage2_ms) *stage2_ms = c;
+  return AOG_OK;
+}
+
+int aog_last_timings(aog_env* env, double* out_ms, int n) {
+  if (!env || !out_ms || n < 7) return AOG_ERR_INVALID;
+  for (int i = 0; i < n; ++i) out_ms[i] = -1.0;
+  float ms = 0.f;
+  if (env->tev_ext_valid) {
+    AOG_CUDA(cudaEventSynchronize(env->tev[1]));
+    AOG_CUDA(cudaEventElapsedTime(&ms, env->tev[0], env->tev[1]));
+    out_ms[0] = ms;
+    out_ms[1] = (double)env->last_extrusions;
+  }
+  if (env->tev_sh_valid) {
+    AOG_CUDA(cudaEventSynchronize(env->tev[7]));
+    for (int k = 0; k < 5; ++k) {
+      AOG_CUDA(cudaEventElapsedTime(&ms, env->tev[2 + k], env->tev[3 + k]));
+      out_ms[2 + k] = ms;
+    }
+  }
   return AOG_OK;
 }
 

@@ -103,6 +103,11 @@ struct aog_env {
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evf = nullptr, evm = nullptr;   // evf: before the field kernel, evm: between the MFT stages
   bool ev_valid = false;
+  // aog_last_timings: [0,1] around the extrusions of the last step; [2..7] boundaries of the five kernels of the
+  // tensor-core Shack-Hartmann step (last chunk)
+  cudaEvent_t tev[8] = {};
+  bool tev_ext_valid = false, tev_sh_valid = false;
+  int last_extrusions = 0;
 };
 
 // tensor_path.cu: appends the code of a timed-out pipeline barrier (if one fired) to env->err -- a trap surfaces as a

@@ -709,6 +709,7 @@ int ensure_sh_tensor_buffers(aog_env* env, TensorState* ts) {
 int sh_tensor_optics(aog_env* env, TensorState* ts, int e0, int nB, cudaStream_t st) {
   const aog_config& c = env->cfg;
   const int Np = TC_NP, K = c.num_modes;
+  if (env->timing) AOG_CUDA(cudaEventRecord(env->tev[2], st));
   {   // the SH mirror's actuators -> half-turns of DM phase per unit mode, split fp16 (the DM GEMM's A operand)
     const int rows = cdiv(nB, 128) * 128;
     k_act_pack<<<cdiv(rows * ts->kpad, 256), 256, 0, st>>>(env->act_sh, ts->act_hi, ts->act_lo, K, ts->kpad, e0, nB, rows,
@@ -729,8 +730,10 @@ int sh_tensor_optics(aog_env* env, TensorState* ts, int e0, int nB, cudaStream_t
     int rc = launch_phase<false, 1, 3>(env, ts, fp, cdiv(fp.num_items, fp.items_per_cta), st);
     if (rc) return rc;
   }
+  if (env->timing) AOG_CUDA(cudaEventRecord(env->tev[3], st));
   k_sh_fold<<<dim3(SH_NKB, nB), 128, 0, st>>>(ts->phi, ts->apmask, ts->shEB_hi, ts->shEB_lo, nB);
   AOG_LAUNCH_CHECK();
+  if (env->timing) AOG_CUDA(cudaEventRecord(env->tev[4], st));
   ShGemmParams gp{};
   gp.num_envs = nB;
   gp.G = ts->shG;
@@ -741,9 +744,11 @@ int sh_tensor_optics(aog_env* env, TensorState* ts, int e0, int nB, cudaStream_t
   k_sh_gemm<1><<<2 * clusters, SG_THREADS, SG_SMEM_BYTES, st>>>(ts->tmShCE_hi[0], ts->tmShCE_lo[0], ts->tmShEB_hi, ts->tmShEB_lo,
                                                                 ts->tmShYout_hi, ts->tmShYout_lo, gp);
   AOG_LAUNCH_CHECK();
+  if (env->timing) AOG_CUDA(cudaEventRecord(env->tev[5], st));
   k_sh_gemm<2><<<2 * clusters, SG_THREADS, SG_SMEM_BYTES, st>>>(ts->tmShCE_hi[1], ts->tmShCE_lo[1], ts->tmShYB_hi, ts->tmShYB_lo,
                                                                 ts->tmShYout_hi, ts->tmShYout_lo, gp);
   AOG_LAUNCH_CHECK();
+  if (env->timing) AOG_CUDA(cudaEventRecord(env->tev[6], st));
   return AOG_OK;
 }
 
@@ -799,6 +804,7 @@ int aog_tensor_sh_step(aog_env* env, int noise_mode, double* action_out_dev, cud
     cp.draw = (unsigned long long)env->sh_draws;
     k_sh_camera_tc<<<nB, CAM_THREADS, (size_t)Nsub * (3 * sizeof(unsigned long long) + 2 * sizeof(double)), st>>>(cp);
     AOG_LAUNCH_CHECK();
+    if (env->timing) { AOG_CUDA(cudaEventRecord(env->tev[7], st)); env->tev_sh_valid = true; }
   }
   return AOG_OK;
 }

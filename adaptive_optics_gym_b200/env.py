@@ -14,6 +14,7 @@ no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -43,6 +44,13 @@ class _AOCore:
                precision, tables, initial_screens, num_pupil_pixels, num_focal_pixels_fiber, env_id_base):
         if atm_type not in _lib.ATM:
             raise ValueError(f'atm_type must be one of {list(_lib.ATM)}')
+        # arithmetic of the step path: the kwarg, else $AOG_PRECISION (so that the reference's unchanged
+        # ``gym.make('AO-v0', ...)`` call can select the fast path), else the exact FP64 kernels
+        if precision is None:
+            precision = os.environ.get('AOG_PRECISION', 'f64')
+        if precision not in _lib.PRECISION:
+            raise ValueError(f'precision must be one of {list(_lib.PRECISION)}')
+        self.precision = precision
         self.atm_type = atm_type
         self.rew_type = rew_type
         self.act_type = act_type
@@ -185,7 +193,8 @@ class AOEnv(_AOCore, Env):
     """Single ``AO-v0`` environment, NumPy in / NumPy out (reference ``AO_env.py:16-503``).
 
     Extra optional kwargs (defaults = reference constants): ``device``, ``seed``, ``precision``
-    ('f64' exact arithmetic | 'tensor' split-fp16 tcgen05 MFT), ``tables`` (override any set-up
+    ('f64' exact arithmetic, the default | 'fused' one tcgen05 optics kernel per step, ~1e-5 | 'tensor' split-fp16
+    tcgen05 matrix Fourier transform, ~1e-5; default taken from ``$AOG_PRECISION``), ``tables`` (override any set-up
     table), ``initial_screen``, ``num_pupil_pixels``, ``num_focal_pixels_fiber``, ``env_id_base`` (the global
     id of this env: the key of its device random streams, so that a single env can replay env i of an ``AOVecEnv``).
     """
@@ -195,7 +204,7 @@ class AOEnv(_AOCore, Env):
     def __init__(self, atm_type='quasi_static', atm_vel=0, atm_fried=0.15, act_type='num_actuators', act_dim=64,
                  obs_dim=2, rew_type='strehl_ratio', rew_threshold=None, timesteps_per_episode=20,
                  flat_mirror_start_per_episode=True, SH_operation=False, *, device=0, seed=None,
-                 precision='f64', tables=None, initial_screen=None, num_pupil_pixels=240,
+                 precision=None, tables=None, initial_screen=None, num_pupil_pixels=240,
                  num_focal_pixels_fiber=128, env_id_base=0):
         super().__init__()
         self._setup(atm_type=atm_type, atm_vel=atm_vel, atm_fried=atm_fried, act_type=act_type, act_dim=act_dim,
@@ -301,7 +310,7 @@ class AOVecEnv(_AOCore):
 
     def __init__(self, num_envs, atm_type='quasi_static', atm_vel=0, atm_fried=0.15, act_type='num_actuators',
                  act_dim=64, obs_dim=2, rew_type='strehl_ratio', rew_threshold=None, timesteps_per_episode=20,
-                 flat_mirror_start_per_episode=True, SH_operation=False, *, device=0, seed=None, precision='f64',
+                 flat_mirror_start_per_episode=True, SH_operation=False, *, device=0, seed=None, precision=None,
                  tables=None, initial_screens=None, num_pupil_pixels=240, num_focal_pixels_fiber=128,
                  env_id_base=0):
         import torch

@@ -246,6 +246,11 @@ AOG_API double aog_last_mft_ms(aog_env* env);
  * path) of the last timed chunk, milliseconds */
 AOG_API int aog_last_kernel_ms(aog_env* env, double* field_ms, double* stage1_ms, double* stage2_ms);
 
+/* more device times [ms] of the last timed step (negative = not recorded), out_ms[n >= 7]:
+ *   [0] all column extrusions of the last aog_step, [1] how many there were,
+ *   [2..6] the tensor-core Shack-Hartmann step's kernels (last chunk): phase, fold, first product, second product, camera */
+AOG_API int aog_last_timings(aog_env* env, double* out_ms, int n);
+
 #ifdef __cplusplus
 }
 #endif

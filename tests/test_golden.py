@@ -73,7 +73,8 @@ def test_cuda_path_matches_golden(name, precision):
         for t in range(T):
             if case['action'] == 'sh':
                 a = env.SH_step(noise='none')[0]
-                assert np.max(np.abs(a - z['actions'][i])) < 1e-7 * np.max(np.abs(z['actions'][i]))
+                # FP64 SH kernels 1e-7; tensor / fused handles run SH_step on the tensor cores (2e-6, sh_tensor.cuh)
+                assert np.max(np.abs(a - z['actions'][i])) < (1e-7 if precision == 'f64' else 2e-6) * np.max(np.abs(z['actions'][i]))
             else:
                 a = z['actions'][i]
             cnt = int(z['noise_counts'][i]) * 240
@@ -90,3 +91,108 @@ def test_cuda_path_matches_golden(name, precision):
             i += 1
     assert env.timestep == int(z['final_timestep']) and env.episode_no == int(z['final_episode_no'])
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Golden data exported from the REAL reference (tools/export_hcipy_tables.py on a machine with hcipy==0.5.1).  None
+# is committed yet (hcipy is not installable in the build image): these tests pick up tests/golden/hcipy_golden_*.npz
+# or $AOG_HCIPY_GOLDEN/hcipy_golden_*.npz the moment they exist, and until then the dry run below keeps the export
+# tool and both replays exercised against an hcipy-shaped stand-in (the oracle).
+HCIPY_DIRS = [d for d in (os.environ.get('AOG_HCIPY_GOLDEN'), os.path.join(HERE, 'golden')) if d]
+HCIPY_FILES = sorted(f for d in HCIPY_DIRS for f in glob.glob(os.path.join(d, 'hcipy_golden_*.npz')))
+
+
+def _static_kw(kw):
+    """The replay injects the recorded screen before every step, so the layer itself must not move."""
+    kw = dict(kw)
+    kw.update(atm_type='quasi_static', atm_vel=0)
+    return kw
+
+
+def replay_through_oracle(golden, tables=None, rtol=1e-9):
+    from oracle.ao_oracle import OracleAOEnv
+    kw = json.loads(str(golden['kw']))
+    ref = OracleAOEnv(**_static_kw(kw), initial_screen=golden['reset_screens'][0])
+    T = len(golden['actions']) // int(golden['episodes'])
+    i = 0
+    for ep in range(int(golden['episodes'])):
+        ref.layer.achromatic_screen = np.array(golden['reset_screens'][ep], dtype=np.float64)
+        ref.reset()
+        assert _rel(ref.last_obs_f64, golden['reset_obs'][ep]) < rtol, ('reset obs', ep)
+        for t in range(T):
+            ref.layer.achromatic_screen = np.array(golden['screens'][i], dtype=np.float64)
+            o, r, d, _, info = ref.step(golden['actions'][i])
+            assert d == bool(golden['done'][i])
+            assert _rel(ref.last_obs_f64, golden['obs'][i]) < rtol, ('obs', i)
+            assert _rel(r, golden['reward'][i]) < rtol and _rel(info['power'], golden['power'][i]) < rtol, i
+            i += 1
+
+
+def replay_through_cuda(golden, tables, precision):
+    from adaptive_optics_gym_b200 import AOEnv
+    kw = json.loads(str(golden['kw']))
+    tabs = {k: tables[k] for k in ('dm_modes', 'dm_gram') if tables is not None and k in tables} or None
+    env = AOEnv(**_static_kw(kw), initial_screen=golden['reset_screens'][0], precision=precision, tables=tabs)
+    rtol = {'f64': 1e-7, 'tensor': 1e-5, 'fused': 1e-5}[precision]
+    T = len(golden['actions']) // int(golden['episodes'])
+    i = 0
+    for ep in range(int(golden['episodes'])):
+        env._h.set_screens(golden['reset_screens'][ep])
+        env.reset()
+        assert _rel(env.last_obs_f64, golden['reset_obs'][ep]) < rtol
+        for t in range(T):
+            env._h.set_screens(golden['screens'][i])
+            o, r, d, _, info = env.step(golden['actions'][i])
+            assert d == bool(golden['done'][i])
+            assert _rel(env.last_obs_f64, golden['obs'][i]) < rtol, ('obs', i)
+            assert _rel(r, golden['reward'][i]) < rtol and _rel(info['power'], golden['power'][i]) < rtol, i
+            i += 1
+    env.close()
+
+
+def _tables_for(path):
+    p = path.replace('hcipy_golden_', 'hcipy_tables_')
+    return np.load(p) if os.path.exists(p) else None
+
+
+@pytest.mark.parametrize('path', HCIPY_FILES)
+def test_oracle_matches_hcipy_golden(path):
+    """THE pin of the oracle: its restated set-up and arithmetic against trajectories of the real reference."""
+    replay_through_oracle(np.load(path))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['f64', 'tensor', 'fused'])
+@pytest.mark.parametrize('path', HCIPY_FILES)
+def test_cuda_path_matches_hcipy_golden(path, precision):
+    replay_through_cuda(np.load(path), _tables_for(path), precision)
+
+
+def _dry_run_files(tmp_path, name='config3', steps=3):
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle.ao_oracle import OracleAOEnv
+    from tools import export_hcipy_tables as X
+    kw = dict(X.CONFIGS[name], timesteps_per_episode=steps)
+    env = OracleAOEnv(**kw, seed=3)          # hcipy-shaped: same attribute names as the reference env
+    tables, golden = X.collect(env, kw, episodes=2, seed=5)
+    X.write(name, tables, golden, str(tmp_path))
+    return os.path.join(str(tmp_path), f'hcipy_golden_{name}.npz')
+
+
+def test_hcipy_export_dry_run(tmp_path):
+    """tools/export_hcipy_tables.py against an hcipy-shaped object (the oracle): every attribute path it uses
+    exists, the files have the layout the replays expect, and the oracle replay of its own export is exact."""
+    path = _dry_run_files(tmp_path)
+    g, t = np.load(path), _tables_for(path)
+    assert t['dm_modes'].shape == (64, 57600) and t['ar_A'].shape[0] == 240 and t['ar_stencil'].dtype == np.int32
+    assert g['screens'].shape == (6, 57600) and g['obs'].shape == (6, 25) and g['done'].tolist() == [0, 0, 1, 0, 0, 1]
+    assert np.abs(g['screens'][1] - g['screens'][0]).max() > 0          # dynamic: the layer moved between steps
+    replay_through_oracle(g, t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['f64', 'fused'])
+def test_hcipy_replay_through_cuda_dry_run(tmp_path, precision):
+    path = _dry_run_files(tmp_path)
+    replay_through_cuda(np.load(path), _tables_for(path), precision)

@@ -28,6 +28,18 @@ def _screen(seed, r0=0.15, n=240):
     return von_karman_screen(g, cn2, 10.0, np.random.default_rng(seed))
 
 
+def _close_obs(got, want, what):
+    """Detector powers of the tensor / fused kernels against FP64: 1e-5 relative plus the amplitude floor of the
+    fixed-point phase (2^-22 half-turns) and the SFU's sin / cos (2^-21.4): every detector AMPLITUDE carries an
+    absolute error of up to ~1e-8 of the peak amplitude (tools/dark_pixel_error_model.py), i.e. a power error of
+    2e-8 sqrt(P P_max) -- 2e-8 relative on the brightest pixel, 2e-6 on a pixel at 1e-4 of it, 2e-5 at 1e-6."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    peak = want.max(axis=-1, keepdims=True)
+    tol = 1e-5 * want + 2e-8 * np.sqrt(want * peak)
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), f'{what}: {np.abs(got - want)[bad]} > {tol[bad]} at brightness {(want / peak)[bad]}'
+
+
 def _close(a, b, rtol, what):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
@@ -621,3 +633,164 @@ def test_fused_and_tensor_match_f64_on_other_detector_sizes(obs_dim, act_type, K
             _close(envs[p].reward.cpu().numpy(), ref.reward.cpu().numpy(), 1e-5, f'{p} reward')
     for e in envs.values():
         e.close()
+
+
+@pytest.mark.parametrize('precision', ['fused', 'tensor'])
+@pytest.mark.parametrize('obs_dim,act_type,K,rew_type', [(2, 'num_actuators', 64, 'strehl_ratio'), (5, 'zernike', 6, 'smf_ssim')])
+@pytest.mark.parametrize('r0', [0.05, 0.08, 0.10, 0.20])
+def test_fried_parameter_sweep_against_oracle(precision, obs_dim, act_type, K, rew_type, r0):
+    """r0 in {0.05 ... 0.20} m x detector {2x2, 5x5} x {tensor, fused} against the oracle.  Tolerance: 1e-5 relative
+    on Strehl, reward and fibre power; detector pixels 1e-5 relative plus the amplitude floor of ``_close_obs``
+    (1e-8 of the peak amplitude: it only matters for speckle pixels below ~1e-4 of the brightest one)."""
+    from oracle.ao_oracle import OracleAOEnv
+    kw = dict(atm_type='quasi_static', atm_vel=0, atm_fried=r0, act_type=act_type, act_dim=K, obs_dim=obs_dim,
+              rew_type=rew_type, timesteps_per_episode=4)
+    scr = _screen(int(1000 * r0) + obs_dim, r0)
+    env = _mk(precision, **kw, initial_screen=scr)
+    ref = OracleAOEnv(**kw, initial_screen=scr)
+    rng = np.random.default_rng(int(1000 * r0))
+
+    def check_obs(what):
+        _close_obs(env.last_obs_f64, ref.last_obs_f64, what)
+
+    env.reset(), ref.reset()
+    check_obs('reset obs')
+    for t in range(3):
+        a = rng.normal(0, 0.7, K).astype(np.float32)
+        o, r, d, _, info = env.step(a)
+        ro, rr, rd, _, rinfo = ref.step(a)
+        assert d == rd
+        check_obs(f'obs step {t}')
+        _close(r, rr, 1e-5, 'reward')
+        _close(info['power'], rinfo['power'], 1e-5, 'power')
+        if rew_type == 'strehl_ratio':
+            _close(env.last_strehl, ref.last_strehl, 1e-5, 'strehl')
+        else:
+            _close(env.last_ssim, ref.last_ssim, 1e-5, 'ssim')
+    env.close()
+
+
+@pytest.mark.parametrize('precision', ['fused', 'tensor'])
+def test_full_size_batch_config2_zernike_ssim(precision):
+    """BASELINE configs[1] at its stated size: 4096 envs, Zernike K = 6, 5x5 detector, smf_ssim.  Replication property
+    as in test_full_size_batch_properties: env i carries case i % 8, all 512 copies of a case agree, and the 8 cases
+    agree with an 8-env FP64 run within 1e-5 (observations, reward, fibre power, SSIM)."""
+    import torch
+    from adaptive_optics_gym_b200 import AOVecEnv
+    B, R = 4096, 8
+    kw = dict(atm_fried=0.15, act_type='zernike', act_dim=6, obs_dim=5, rew_type='smf_ssim', timesteps_per_episode=4)
+    scr = np.stack([_screen(160 + i, r0=0.15) for i in range(R)])
+    rng = np.random.default_rng(19)
+    acts = rng.normal(0, 0.7, (3, R, 6)).astype(np.float32)
+    big = AOVecEnv(B, **kw, initial_screens=np.tile(scr, (B // R, 1)), precision=precision)
+    ref = AOVecEnv(R, **kw, initial_screens=scr, precision='f64')
+    big.reset(), ref.reset()
+    for t in range(3):
+        obs, rew, done, _, info = big.step(torch.from_numpy(np.tile(acts[t], (B // R, 1))).cuda())
+        ref.step(torch.from_numpy(acts[t]).cuda())
+        torch.cuda.synchronize()
+        o64 = big.obs_f64.reshape(B // R, R, 25)
+        for x in (o64, rew.reshape(-1, R), info['power'].reshape(-1, R), big.ssim.reshape(-1, R)):
+            x0 = x[:1].expand_as(x)
+            assert torch.all((x - x0).abs() <= 1e-12 * x0.abs()), f'copies of one case differ (step {t})'
+        _close_obs(o64[0].cpu().numpy(), ref.obs_f64.cpu().numpy(), f'obs step {t}')
+        _close(rew[:R].cpu().numpy(), ref.reward.cpu().numpy(), 1e-5, f'reward step {t}')
+        _close(info['power'][:R].cpu().numpy(), ref.power.cpu().numpy(), 1e-5, f'power step {t}')
+        _close(big.ssim[:R].cpu().numpy(), ref.ssim.cpu().numpy(), 1e-5, f'ssim step {t}')
+        assert bool(done.all()) == (t == 3)
+    big.close(), ref.close()
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_render_fields_match_oracle(precision):
+    """AOEnv.render (AO_env.py:156-194): the three panels against the oracle's fields -- the phase-screen OPD
+    (:128-129), the 128 x 128 focal-plane power ``wf_wfs_after_foc.power`` (:174) and the detector power (:181)."""
+    from oracle.ao_oracle import OracleAOEnv
+    kw = dict(atm_type='dynamic', atm_vel=5, atm_fried=0.15, act_type='zernike', act_dim=6, obs_dim=5,
+              rew_type='smf_ssim', timesteps_per_episode=4)
+    scr = _screen(77, 0.15)
+    ref = OracleAOEnv(**kw, initial_screen=scr, seed=4)
+    lay = ref.layer
+    tabs = dict(ar_stencil=np.flatnonzero(lay.stencil_left).astype(np.int32), ar_A=lay.A_horizontal, ar_B=lay.B_horizontal)
+    env = _mk(precision, **kw, initial_screen=scr, tables=tabs)
+    rng = np.random.default_rng(3)
+    env.reset(), ref.reset()
+    for t in range(2):
+        a = rng.normal(0, 0.7, 6).astype(np.float32)
+        noise = rng.standard_normal((ref.num_extrusions_for_next_step(), 240))
+        env.step(a, extrusion_noise=noise)
+        ref.step(a, extrusion_noise=noise)
+        env.render()
+        want_fp = np.asarray(ref.wf_wfs_after_foc.power)
+        np.testing.assert_allclose(env.last_render['focal_power'], want_fp, rtol=0, atol=1e-9 * want_fp.max())
+        np.testing.assert_allclose(env.last_render['phase_screen_opd'], np.asarray(ref.phase_screen_opd), rtol=0,
+                                   atol=1e-9 * np.abs(ref.phase_screen_opd).max())
+        np.testing.assert_allclose(env.last_render['obs_power'], ref.last_obs_f64, rtol=1e-9)
+    env.close()
+
+
+def test_seeded_reset_replays_device_noise_and_state_carries_sh_mirror():
+    """reset(seed=s) re-keys the device's random streams (the reference ignores the seed, AO_env.py:74): two envs
+    reset with the same seed draw the same screens (semi_dynamic), extrusion noise (dynamic) and photon noise; and
+    get_state / set_state carry the SH integrator's mirror and the draw counters."""
+    kw = dict(atm_type='semi_dynamic', atm_fried=0.15, act_dim=64, obs_dim=2, timesteps_per_episode=3)
+    a = _mk('f64', **kw, seed=1)
+    b = _mk('f64', **kw, seed=2)
+    o1, _ = a.reset(seed=123)
+    o2, _ = b.reset(seed=123)
+    assert np.array_equal(a.get_state()['screens'], b.get_state()['screens']) and np.array_equal(o1, o2)
+    o3, _ = b.reset(seed=124)
+    assert not np.array_equal(a.get_state()['screens'], b.get_state()['screens'])
+    a.close(), b.close()
+    kw = dict(atm_type='dynamic', atm_vel=20, atm_fried=0.10, act_dim=64, obs_dim=2, timesteps_per_episode=3,
+              SH_operation=True, seed=6)
+    scr = _screen(5, 0.10)
+    for precision in ('f64', 'fused'):
+        e = _mk(precision, **kw, initial_screen=scr)
+        e.reset(seed=77)
+        runs = []
+        for rep in range(2):
+            if rep:
+                e.set_state(st)
+            else:
+                e.step(e.SH_step()[0])
+                st = e.get_state()
+                assert st['sh_draws'] == 1 and np.abs(st['sh_actuators']).max() > 0 and st['seed'] == 77
+            acts, rews = [], []
+            for t in range(2):
+                act, _ = e.SH_step()                      # device photon noise
+                _, r, _, _, _ = e.step(act)               # device extrusion noise
+                acts.append(act), rews.append(r)
+            runs.append((np.array(acts), np.array(rews)))
+        assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+        e.close()
+
+
+@pytest.mark.parametrize('Np,Nf,obs_dim,act_type,K,rew_type', [(128, 64, 2, 'num_actuators', 64, 'strehl_ratio'),
+                                                             (256, 256, 5, 'zernike', 6, 'smf_ssim'),
+                                                             (96, 32, 3, 'zernike', 10, 'smf_ssim')])
+def test_other_grid_sizes_f64_against_oracle(Np, Nf, obs_dim, act_type, K, rew_type):
+    """BASELINE configs[4], the pupil / focal grid axis (reference constants AO_env.py:216,234-235): the FP64 path at
+    pupil 128^2 / focal 64^2, 256^2 / 256^2 and 96^2 / 32^2 against OracleAOEnv built with the same sizes (1e-9)."""
+    from oracle.ao_oracle import OracleAOEnv, hcipy_make_pupil_grid, hcipy_Cn_squared_from_fried_parameter, von_karman_screen
+    kw = dict(atm_type='quasi_static', atm_fried=0.15, act_type=act_type, act_dim=K, obs_dim=obs_dim, rew_type=rew_type,
+              timesteps_per_episode=3, num_pupil_pixels=Np, num_focal_pixels_fiber=Nf)
+    g = hcipy_make_pupil_grid(Np, 0.5)
+    scr = von_karman_screen(g, hcipy_Cn_squared_from_fried_parameter(0.15, 2.2e-6), 10.0, np.random.default_rng(Np))
+    env = _mk('f64', **kw, initial_screen=scr)
+    ref = OracleAOEnv(**kw, initial_screen=scr)
+    rng = np.random.default_rng(Nf)
+    env.reset(), ref.reset()
+    _close(env.last_obs_f64, ref.last_obs_f64, 1e-9, 'reset obs')
+    for t in range(3):
+        a = rng.uniform(-1, 1, K).astype(np.float32)
+        o, r, d, _, info = env.step(a)
+        ro, rr, rd, _, rinfo = ref.step(a)
+        assert d == rd and np.array_equal(o.view(np.uint16), ro.view(np.uint16))
+        _close(env.last_obs_f64, ref.last_obs_f64, 1e-9, 'obs')
+        _close(r, rr, 1e-9, 'reward')
+        _close(info['power'], rinfo['power'], 1e-9, 'power')
+    env.render()
+    want = np.asarray(ref.wf_wfs_after_foc.power)
+    np.testing.assert_allclose(env.last_render['focal_power'], want, rtol=0, atol=1e-9 * want.max())
+    env.close()

@@ -4,17 +4,25 @@
 Run this on a machine where the reference imports (``pip install hcipy==0.5.1 gymnasium scikit-image`` and the
 reference checkout on PYTHONPATH); it is NOT runnable in the build image (no hcipy, no network).  It writes
 
-  hcipy_tables_<config>.npz   every table ``AOEnv(tables=...)`` accepts, taken from the reference env's own hcipy
-                              objects (names = adaptive_optics_gym_b200._lib.TABLE_IDS plus the scalars)
-  hcipy_golden_<config>.npz   screens, actions, extrusion noise, observations, rewards, power for a few episodes
+  hcipy_tables_<config>.npz   the set-up tables whose restatement is uncertain (SURVEY App. A [VERIFY]): the DM mode
+                              matrix (read through the PUBLIC hcipy API: one ``dm.actuators = e_k; dm.surface`` probe
+                              per mode), the AR extrusion stencil / A / B when the layer exposes them, the SH
+                              reconstruction matrix and reference slopes; names as ``AOEnv(tables=...)`` takes them
+  hcipy_golden_<config>.npz   per step: the achromatic screen the optics saw, the action, observation (before the
+                              float16 cast), reward, info["power"], done
 
-which turn "parity unpinned"  into pinned: commit the .npz under tests/golden/ and point
-tests/test_golden.py at them.  Noise is made reproducible by seeding NumPy's global RNG (the only RNG hcipy uses,
-SURVEY.md section 5) and recording the screen before every step.
+Dropping both files into ``tests/golden/`` (or ``$AOG_HCIPY_GOLDEN``) turns "parity unpinned" into pinned without a
+code change: ``tests/test_golden.py`` replays every ``hcipy_golden_*.npz`` through the CPU oracle (1e-9) and through
+the CUDA path (FP64 1e-7, tensor / fused 1e-5).  The replay feeds the recorded screen before every step, so it does
+not depend on reproducing hcipy's random draws.
+
+``collect`` only touches attributes that the oracle (an hcipy-shaped restatement) has too, which is how the CPU test
+``test_hcipy_export_dry_run`` exercises this file end to end without hcipy.
 
     python tools/export_hcipy_tables.py --out tests/golden --config config1
 """
 import argparse
+import json
 import os
 
 import numpy as np
@@ -31,46 +39,77 @@ CONFIGS = {
 }
 
 
-def export(name, kw, out, episodes=2, seed=0):
-    import gymnasium as gym
-    import gym_AO  # noqa: F401  (the reference package: registers AO-v0)
-    np.random.seed(seed)
-    env = gym.make('AO-v0', **kw).unwrapped
-    grid = env.wf_wfs_fiber.electric_field.grid
-    Np = int(round(np.sqrt(grid.size)))
-    t = {}
-    t['aperture'] = np.asarray(env.wf_wfs_fiber.electric_field != 0, dtype=np.float64)
-    t['dm_modes'] = np.asarray(env.deformable_mirror.influence_functions.transformation_matrix.T.todense()
-                               if hasattr(env.deformable_mirror.influence_functions.transformation_matrix, 'todense')
-                               else env.deformable_mirror.influence_functions.transformation_matrix.T)
-    m = t['dm_modes']
-    t['dm_gram'] = m @ m.T / m.shape[1] - np.outer(m.mean(1), m.mean(1))
-    for key, prop in (('fib', env.propagator_fiber), ('obs', env.propagator_fiber_subsample)):
-        prop(env.wf_wfs_fiber)                                    # builds and caches the MatrixFourierTransform
-        ft = prop.fourier_transform if hasattr(prop, 'fourier_transform') else prop._fourier_transform
-        t[f'mft_{key}_1'], t[f'mft_{key}_2'] = np.asarray(ft.M1), np.asarray(ft.M2)
-    lay = env.layer
-    if kw['atm_type'] == 'dynamic':
-        t['ar_stencil'] = np.flatnonzero(lay.new_col_stencil if hasattr(lay, 'new_col_stencil') else lay.stencil_left)
-        t['ar_A'], t['ar_B'] = np.asarray(lay.A_horizontal), np.asarray(lay.B_horizontal)
-    np.savez_compressed(os.path.join(out, f'hcipy_tables_{name}.npz'), **t)
+def _screen(env):
+    """Achromatic screen S (phase = S / lambda) of the env's atmospheric layer: hcipy ``phase_for(1)``."""
+    return np.array(env.layer.phase_for(1.0), dtype=np.float64).ravel()
 
-    rec = dict(screens=[], actions=[], obs=[], reward=[], power=[], done=[])
+
+def collect(env, kw, episodes=2, steps=None, seed=0):
+    """(tables, golden) from a reference-shaped env (``gym.make('AO-v0', **kw).unwrapped``)."""
+    t = {}
+    dm = env.deformable_mirror
+    K = int(kw.get('act_dim', 64))
+    cols = []
+    for k in range(K):                      # public API probe: column k of the influence matrix
+        a = np.zeros(K)
+        a[k] = 1.0
+        dm.actuators = a
+        cols.append(np.array(dm.surface, dtype=np.float64).ravel())
+    dm.flatten()
+    m = np.stack(cols)                      # [K, P]
+    t['dm_modes'] = m
+    t['dm_gram'] = m @ m.T / m.shape[1] - np.outer(m.mean(1), m.mean(1))
+    lay = env.layer
+    if kw.get('atm_type') == 'dynamic':
+        for names, key in ((('stencil_left', 'new_col_stencil'), 'ar_stencil'), (('A_horizontal',), 'ar_A'),
+                           (('B_horizontal',), 'ar_B')):
+            for n in names:
+                if hasattr(lay, n):
+                    v = np.asarray(getattr(lay, n))
+                    t[key] = np.flatnonzero(v).astype(np.int32) if key == 'ar_stencil' else v.astype(np.float64)
+                    break
+    if kw.get('SH_operation'):
+        t['sh_recon'] = np.asarray(env.reconstruction_matrix, dtype=np.float64)
+        t['sh_slopes_ref'] = np.asarray(env.slopes_ref, dtype=np.float64)
+
+    rec = dict(reset_screens=[], reset_obs=[], screens=[], actions=[], obs=[], reward=[], power=[], done=[])
     rng = np.random.default_rng(seed + 1)
+    T = int(steps or kw['timesteps_per_episode'])
     for ep in range(episodes):
         env.reset()
-        for step in range(kw['timesteps_per_episode']):
-            rec['screens'].append(np.asarray(lay.phase_for(1.0), dtype=np.float64))     # achromatic screen S
-            a = env.SH_step()[0] if kw.get('SH_operation') else rng.uniform(-1, 1, kw['act_dim']).astype(np.float32)
+        rec['reset_screens'].append(_screen(env))
+        rec['reset_obs'].append(np.array(env.wf_wfs_after_foc_subsample.power, dtype=np.float64))
+        for step in range(T):
+            a = env.SH_step()[0] if kw.get('SH_operation') else rng.uniform(-1, 1, K).astype(np.float32)
+            a = np.array(a, dtype=np.float64)
             o, r, d, _, info = env.step(a)
-            rec['actions'].append(np.asarray(a, dtype=np.float64))
-            rec['obs'].append(np.asarray(env.wf_wfs_after_foc_subsample.power, dtype=np.float64))
+            rec['screens'].append(_screen(env))            # after the layer moved: what this step's optics saw
+            rec['actions'].append(a)
+            rec['obs'].append(np.array(env.wf_wfs_after_foc_subsample.power, dtype=np.float64))
             rec['reward'].append(float(r))
             rec['power'].append(float(info['power']))
             rec['done'].append(bool(d))
-    np.savez_compressed(os.path.join(out, f'hcipy_golden_{name}.npz'), kw=np.array(repr(kw)),
-                        **{k: np.array(v) for k, v in rec.items()})
-    print(name, 'exported', {k: np.array(v).shape for k, v in rec.items()})
+            if d:
+                break
+    g = {k: np.array(v) for k, v in rec.items()}
+    g['kw'] = np.array(json.dumps(kw))
+    g['episodes'] = np.array(episodes)
+    return t, g
+
+
+def write(name, tables, golden, out):
+    np.savez_compressed(os.path.join(out, f'hcipy_tables_{name}.npz'), **tables)
+    np.savez_compressed(os.path.join(out, f'hcipy_golden_{name}.npz'), **golden)
+
+
+def export(name, kw, out, episodes=2, seed=0):
+    import gymnasium as gym
+    import gym_AO  # noqa: F401  (the reference package: registers AO-v0)
+    np.random.seed(seed)                    # hcipy draws from NumPy's global generator
+    env = gym.make('AO-v0', **kw).unwrapped
+    tables, golden = collect(env, kw, episodes=episodes, seed=seed)
+    write(name, tables, golden, out)
+    print(name, 'exported', {k: v.shape for k, v in golden.items()})
 
 
 if __name__ == '__main__':
