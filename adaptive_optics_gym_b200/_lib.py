@@ -255,6 +255,19 @@ class Handle:
         self.check(self.lib.aog_reset_host(self._h, C.byref(o)), 'aog_reset_host')
         return h
 
+    def step_host_fast(self, a):
+        """``step_host`` for the single-env hot loop: ``a`` is a C-contiguous float32 / float64 array of the right size,
+        no extrusion noise; ctypes arguments are built once."""
+        if not hasattr(self, '_fast'):
+            h, o = self._host_outputs()
+            done = C.c_int32(0)
+            self._fast = (h, C.byref(o), done, C.byref(done), self.lib.aog_step_host)
+        h, o_ref, done, done_ref, fn = self._fast
+        rc = fn(self._h, a.ctypes.data, DTYPE_F32 if a.dtype == np.float32 else DTYPE_F64, None, o_ref, done_ref)
+        if rc != 0:
+            self.check(rc, 'aog_step_host')
+        return h, done.value != 0
+
     def step_host(self, actions, noise=None):
         a = np.asarray(actions)
         if a.dtype == np.float32:

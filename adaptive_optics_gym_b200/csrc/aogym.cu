@@ -183,46 +183,50 @@ int optics_all(aog_env* env, bool flat_dm, bool with_reward, const aog_outputs& 
   return AOG_OK;
 }
 
+// device-side outputs of the *_host variants: one allocation [obs64 | reward | power | strehl | ssim | obs16], so that a
+// step's results reach the host with ONE device->host copy
 int alloc_host_outputs(aog_env* env) {
   const size_t B = env->cfg.num_envs, n2 = env->n2;
-  if (env->o_obs16) return AOG_OK;
+  if (env->o_pack) return AOG_OK;
+  const size_t bytes = B * n2 * sizeof(double) + 4 * B * sizeof(double) + B * n2 * sizeof(uint16_t);
   int rc;
-  if ((rc = dev_alloc(env, &env->o_obs16, B * n2))) return rc;
-  if ((rc = dev_alloc(env, &env->o_obs64, B * n2))) return rc;
-  if ((rc = dev_alloc(env, &env->o_reward, B))) return rc;
-  if ((rc = dev_alloc(env, &env->o_power, B))) return rc;
-  if ((rc = dev_alloc(env, &env->o_strehl, B))) return rc;
-  if ((rc = dev_alloc(env, &env->o_ssim, B))) return rc;
-  AOG_CUDA(cudaMemset(env->o_strehl, 0, B * sizeof(double)));
-  AOG_CUDA(cudaMemset(env->o_ssim, 0, B * sizeof(double)));
+  if ((rc = dev_alloc(env, &env->o_pack, bytes))) return rc;
+  env->o_pack_bytes = bytes;
+  AOG_CUDA(cudaMemset(env->o_pack, 0, bytes));
+  char* p = env->o_pack;
+  env->o_obs64 = (double*)p;   p += B * n2 * sizeof(double);
+  env->o_reward = (double*)p;  p += B * sizeof(double);
+  env->o_power = (double*)p;   p += B * sizeof(double);
+  env->o_strehl = (double*)p;  p += B * sizeof(double);
+  env->o_ssim = (double*)p;    p += B * sizeof(double);
+  env->o_obs16 = (uint16_t*)p;
   return AOG_OK;
 }
 
-// D2H of the outputs the caller asked for, through one pinned staging block.
-int copy_outputs_to_host(aog_env* env, const aog_outputs* out, cudaStream_t st) {
+// the packed block (already in pinned memory) -> the arrays the caller asked for
+void scatter_host_outputs(aog_env* env, const aog_outputs* out) {
+  if (!out) return;
   const size_t B = env->cfg.num_envs, n2 = env->n2;
-  if (!out) { AOG_CUDA(cudaStreamSynchronize(st)); return AOG_OK; }
-  const size_t bytes = B * n2 * (sizeof(uint16_t) + sizeof(double)) + 4 * B * sizeof(double) + 64;
-  int rc = ensure_pinned(env, bytes);
-  if (rc) return rc;
-  char* h = (char*)env->h_pinned;
-  size_t off = 0;
-  struct Item { void* dst; const void* src; size_t bytes; size_t off; };
-  std::vector<Item> items;
-  auto add = [&](void* dst, const void* src, size_t b) {
-    if (!dst) return;
-    items.push_back({dst, src, b, off});
-    off += (b + 15) & ~size_t(15);
+  const char* h = (const char*)env->h_pinned;
+  auto take = [&](void* dst, const void* dev, size_t b) {
+    if (dst) std::memcpy(dst, h + ((const char*)dev - env->o_pack), b);
   };
-  add(out->obs_f64, env->o_obs64, B * n2 * sizeof(double));
-  add(out->reward, env->o_reward, B * sizeof(double));
-  add(out->power, env->o_power, B * sizeof(double));
-  add(out->strehl, env->o_strehl, B * sizeof(double));
-  add(out->ssim, env->o_ssim, B * sizeof(double));
-  add(out->obs_f16, env->o_obs16, B * n2 * sizeof(uint16_t));
-  for (auto& it : items) AOG_CUDA(cudaMemcpyAsync(h + it.off, it.src, it.bytes, cudaMemcpyDeviceToHost, st));
+  take(out->obs_f64, env->o_obs64, B * n2 * sizeof(double));
+  take(out->reward, env->o_reward, B * sizeof(double));
+  take(out->power, env->o_power, B * sizeof(double));
+  take(out->strehl, env->o_strehl, B * sizeof(double));
+  take(out->ssim, env->o_ssim, B * sizeof(double));
+  take(out->obs_f16, env->o_obs16, B * n2 * sizeof(uint16_t));
+}
+
+// D2H of the outputs through one pinned staging block (one copy), then a stream synchronise.
+int copy_outputs_to_host(aog_env* env, const aog_outputs* out, cudaStream_t st) {
+  if (!out) { AOG_CUDA(cudaStreamSynchronize(st)); return AOG_OK; }
+  int rc = ensure_pinned(env, env->o_pack_bytes);
+  if (rc) return rc;
+  AOG_CUDA(cudaMemcpyAsync(env->h_pinned, env->o_pack, env->o_pack_bytes, cudaMemcpyDeviceToHost, st));
   AOG_CUDA(cudaStreamSynchronize(st));
-  for (auto& it : items) std::memcpy(it.dst, h + it.off, it.bytes);
+  scatter_host_outputs(env, out);
   return AOG_OK;
 }
 
@@ -349,8 +353,8 @@ void aog_destroy(aog_env* env) {
                   env->t_lpw, env->t_lpphase, env->t_lpgram, env->t_stencil, env->t_arA, env->t_arB, env->t_arW,
                   env->t_scrC1, env->t_scrW1, env->t_scrW1T, env->t_scrC2, env->t_scrW2, env->t_scrW2T,
                   env->screens, env->act, env->bufA, env->bufB, env->bufC, env->bufR, env->coef,
-                  env->strehl_part, env->arZ, env->arNew, env->act_in, env->noise_in, env->o_obs16, env->o_obs64,
-                  env->o_reward, env->o_power, env->o_strehl, env->o_ssim, env->t_sh_mla, env->t_sh_C, env->t_sh_CT,
+                  env->strehl_part, env->arZ, env->arNew, env->act_in, env->noise_in, env->o_pack,
+                  env->t_sh_mla, env->t_sh_C, env->t_sh_CT,
                   env->t_sh_off, env->t_sh_pix, env->t_sh_px, env->t_sh_py, env->t_sh_offset, env->t_sh_recon,
                   env->t_sh_act0, env->act_sh, env->o_action, env->sh_noisy_in, env->t_sh_Cf[0], env->t_sh_Cf[1],
                   env->t_sh_Cf[2], env->t_sh_Cf[3], env->t_scrWst[0], env->t_scrWst[1], env->t_scrWrT[0], env->t_scrWrT[1],
@@ -358,6 +362,8 @@ void aog_destroy(aog_env* env) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (env->h_pinned) cudaFreeHost(env->h_pinned);
+  if (env->h_act) cudaFreeHost(env->h_act);
+  if (env->step_graph) cudaGraphExecDestroy(env->step_graph);
   if (env->own_stream) cudaStreamDestroy(env->own_stream);
   if (env->ev0) cudaEventDestroy(env->ev0);
   if (env->ev1) cudaEventDestroy(env->ev1);
@@ -411,6 +417,7 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
                                   " elements, got " + std::to_string(count));
   AOG_CUDA(cudaMemcpy(dst, host, want * esz, cudaMemcpyHostToDevice));
   env->have[which] = true;
+  if (env->step_graph) { cudaGraphExecDestroy(env->step_graph); env->step_graph = nullptr; }   // captured launches hold table-derived arguments
   if ((which == AOG_TABLE_AR_A || which == AOG_TABLE_AR_B) && env->have[AOG_TABLE_AR_A] && env->have[AOG_TABLE_AR_B]) {
     const int tot = (int)((Ns + Np) * Np);
     k_build_arW<<<cdiv(tot, 256), 256>>>(env->t_arA, env->t_arB, env->t_arW, (int)Np, (int)Ns);
@@ -727,8 +734,60 @@ int aog_step_host(aog_env* env, const void* actions_host, int act_dtype, const d
   const aog_config& c = env->cfg;
   AOG_DEVICE(c.device);
   cudaStream_t st = env->own_stream;
+  if (act_dtype != AOG_DTYPE_F32 && act_dtype != AOG_DTYPE_F64) AOG_FAIL(AOG_ERR_INVALID, "act_dtype");
   const size_t esz = act_dtype == AOG_DTYPE_F32 ? sizeof(float) : sizeof(double);
   const size_t abytes = (size_t)c.num_envs * c.num_modes * esz;
+  // Small batches on a static atmosphere: the whole step (H2D, kernels, D2H) is a CUDA graph captured on the second
+  // call and relaunched afterwards -- the step of a single env is launch-bound (4 kernels + 2 copies).
+  const bool no_graph = getenv("AOG_NO_GRAPH") != nullptr;
+  if (c.num_envs <= 256 && c.precision != AOG_PRECISION_F64 && c.velocity == 0.0 && !noise_host && !env->timing &&
+      !env->graph_failed && !no_graph && tables_ready(env)) {
+    int rc;
+    if (!env->h_act) AOG_CUDA(cudaMallocHost(&env->h_act, (size_t)c.num_envs * c.num_modes * sizeof(double)));
+    if ((rc = ensure_pinned(env, env->o_pack_bytes))) return rc;
+    std::memcpy(env->h_act, actions_host, abytes);
+    aog_outputs d = device_outputs(env);
+    if (env->step_graph && env->graph_dtype == act_dtype) {
+      // host bookkeeping of aog_step (AO_env.py:123-124, 147-151); the device work is the graph
+      env->cnt.timestep += 1;
+      env->cnt.timestep_render += 1;
+      int done = 0;
+      if (env->cnt.timestep_render == c.max_steps) { done = 1; env->cnt.episode_no += 1; }
+      if (done_out) *done_out = done;
+      AOG_CUDA(cudaGraphLaunch(env->step_graph, st));
+      env->launches += env->graph_launches;
+    } else if (env->graph_warm >= 1) {
+      if (env->step_graph) { cudaGraphExecDestroy(env->step_graph); env->step_graph = nullptr; }
+      cudaGraph_t graph = nullptr;
+      const int64_t l0 = env->launches;
+      AOG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      cudaError_t e = cudaMemcpyAsync(env->act_in, env->h_act, abytes, cudaMemcpyHostToDevice, st);
+      rc = e == cudaSuccess ? aog_step(env, env->act_in, act_dtype, nullptr, &d, done_out, st) : AOG_ERR_CUDA;
+      if (rc == AOG_OK) e = cudaMemcpyAsync(env->h_pinned, env->o_pack, env->o_pack_bytes, cudaMemcpyDeviceToHost, st);
+      const cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+      if (rc != AOG_OK || e != cudaSuccess || e2 != cudaSuccess || !graph ||
+          cudaGraphInstantiate(&env->step_graph, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        env->step_graph = nullptr;
+        env->graph_failed = true;                      // this handle keeps to plain launches
+        if (rc != AOG_OK) return rc;                   // (aog_step's own error; its bookkeeping has not been undone)
+        AOG_FAIL(AOG_ERR_CUDA, "CUDA graph capture of the step failed");
+      }
+      cudaGraphDestroy(graph);
+      env->graph_dtype = act_dtype;
+      env->graph_launches = (int)(env->launches - l0);
+      AOG_CUDA(cudaGraphLaunch(env->step_graph, st));  // the capture recorded the work, this runs it
+    } else {
+      env->graph_warm++;                               // first call: plain launches (function attributes, lazy set-up)
+      AOG_CUDA(cudaMemcpyAsync(env->act_in, env->h_act, abytes, cudaMemcpyHostToDevice, st));
+      if ((rc = aog_step(env, env->act_in, act_dtype, nullptr, &d, done_out, st))) return rc;
+      AOG_CUDA(cudaMemcpyAsync(env->h_pinned, env->o_pack, env->o_pack_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    AOG_CUDA(cudaStreamSynchronize(st));
+    scatter_host_outputs(env, out_host);
+    return AOG_OK;
+  }
   AOG_CUDA(cudaMemcpyAsync(env->act_in, actions_host, abytes, cudaMemcpyHostToDevice, st));
   const double* nz = nullptr;
   if (noise_host) {

@@ -89,8 +89,15 @@ struct aog_env {
   // device-side outputs used by the *_host variants
   uint16_t* o_obs16 = nullptr; double* o_obs64 = nullptr; double* o_reward = nullptr;
   double* o_power = nullptr; double* o_strehl = nullptr; double* o_ssim = nullptr;
+  char* o_pack = nullptr; size_t o_pack_bytes = 0;   // the six arrays above are slices of this one allocation (one D2H copy)
   // pinned host staging
   void* h_pinned = nullptr; size_t h_pinned_cap = 0;
+  // small batches (<= 256 envs, static atmosphere): the host-buffer step (H2D actions, kernels, D2H outputs) is
+  // captured once in a CUDA graph and relaunched -- one driver call instead of ~8 launches + copies
+  void* h_act = nullptr;                // pinned staging of the actions (the graph's H2D source)
+  cudaGraphExec_t step_graph = nullptr;
+  int graph_dtype = -1, graph_warm = 0, graph_launches = 0;
+  bool graph_failed = false;
 
   // ---- counters (host; all envs run in lock-step) ----
   aog_counters cnt{};

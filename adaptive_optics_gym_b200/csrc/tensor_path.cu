@@ -567,8 +567,8 @@ __device__ __forceinline__ int fk_column(int item_in_block) {
   return (MODE == 0 || MODE == 3) ? item_in_block : (item_in_block * FK_COL_STRIDE) % TC_NP;
 }
 constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
-constexpr int FK_SLOTS = 64;                            // Strehl / fibre partial slots per env (>= CTAs touching an env block)
-constexpr int FK_MIN_ITEMS = 4;                         // items per CTA at least (bounds the slots: 240 / 4 = 60 <= FK_SLOTS); small batches spread over more SMs
+constexpr int FK_SLOTS = 128;                           // Strehl / fibre partial slots per env (>= CTAs touching an env block)
+constexpr int FK_MIN_ITEMS = 2;                         // items per CTA at least (bounds the slots: 240 / 2 + 1 = 121 <= FK_SLOTS); small batches spread over more SMs
 constexpr int FK_PF_TILE = 32 * 16 * 4;                 // 2 KB: 32 envs x 16 pixels of phase (one bulk copy)
 constexpr int FK_JT = 3;                                // fibre modes of the fused kernel (LP01 + 2 x LP11, AO_env.py:393)
 // Fused kernel: per pixel one record of FK_NT(n) float2 = [n obs-arm twiddles | FK_JT back-projected fibre modes |

@@ -243,8 +243,13 @@ class AOEnv(_AOCore, Env):
         a = np.asarray(action)
         if a.dtype != np.float32:
             a = a.astype(np.float64)
-        h, done = self._h.step_host(a.reshape(1, -1), extrusion_noise)
-        self._sync_counters()
+        if extrusion_noise is None and a.size == self.num_modes:
+            h, done = self._h.step_host_fast(np.ascontiguousarray(a))
+        else:
+            h, done = self._h.step_host(a.reshape(1, -1), extrusion_noise)
+        self.timestep += 1                       # AO_env.py:123-124, 149 (the handle keeps the same counters)
+        self.timestep_render += 1
+        self.episode_no += int(done)
         self.last_obs_f64 = h['obs_f64'][0].copy()
         self.last_strehl = float(h['strehl'][0])
         self.last_ssim = float(h['ssim'][0])

@@ -794,3 +794,33 @@ def test_other_grid_sizes_f64_against_oracle(Np, Nf, obs_dim, act_type, K, rew_t
     want = np.asarray(ref.wf_wfs_after_foc.power)
     np.testing.assert_allclose(env.last_render['focal_power'], want, rtol=0, atol=1e-9 * want.max())
     env.close()
+
+
+@pytest.mark.parametrize('precision', ['fused', 'tensor'])
+def test_small_batch_cuda_graph_step_equals_plain_launches(precision, monkeypatch):
+    """Host-buffer steps of small batches on a static atmosphere run as ONE captured CUDA graph (aog_step_host): the
+    results, the done flags and the counters are those of the plain launches, across episode boundaries and resets."""
+    kw = dict(atm_type='quasi_static', atm_fried=0.15, act_type='zernike', act_dim=6, obs_dim=5, rew_type='smf_ssim',
+              timesteps_per_episode=4)
+    scr = _screen(91, 0.15)
+    rng = np.random.default_rng(2)
+    acts = rng.normal(0, 0.7, (10, 6))
+    out = {}
+    for mode in ('graph', 'plain'):
+        if mode == 'plain':
+            monkeypatch.setenv('AOG_NO_GRAPH', '1')
+        env = _mk(precision, **kw, initial_screen=scr)
+        rows = []
+        env.reset()
+        for t in range(10):
+            a = acts[t].astype(np.float32) if t % 2 else acts[t]        # both action dtypes: the graph is re-captured
+            o, r, d, _, info = env.step(a)
+            rows.append((o.copy(), r, d, info['power'], env.last_ssim, env.timestep, env.timestep_render, env.episode_no))
+            if d:
+                env.reset()
+        launches = env._h.launch_count()
+        out[mode] = (rows, launches)
+        env.close()
+    for g, p in zip(out['graph'][0], out['plain'][0]):
+        assert np.array_equal(g[0], p[0]) and g[1:] == p[1:]
+    assert out['graph'][1] == out['plain'][1]            # the launch counter counts the graph's kernels too
