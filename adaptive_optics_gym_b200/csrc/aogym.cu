@@ -55,7 +55,7 @@ int dmma_configure(aog_env* env) {
   static std::atomic<bool> done_on[64];    // function attributes are per device: one flag per device ordinal
   std::atomic<bool>& done = done_on[env->cfg.device & 63];
   if (done.load(std::memory_order_acquire)) return AOG_OK;
-  AOG_CUDA(cudaFuncSetAttribute(k_ar_step, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
+  AOG_CUDA(cudaFuncSetAttribute(k_ar_step, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM));
   AOG_CUDA(cudaFuncSetAttribute(k_dgemm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
   done.store(true, std::memory_order_release);
   return AOG_OK;
@@ -86,9 +86,9 @@ int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long
       continue;
     }
     // GEMM with the scatter into the ring slot (and the phase-tile refresh of the tensor / fused paths) in its epilogue
-    dim3 g2(cdiv(Np, 64), cdiv(nB, 128));
+    dim3 g2(cdiv(Np, 64), cdiv(nB, AR_TM));
     { int rc = dmma_configure(env); if (rc) return rc; }
-    k_ar_step<<<g2, DmmaCfg<1>::THREADS, DmmaCfg<1>::SMEM, st>>>(env->arZ, env->t_arW, env->screens, env->phase_tiles, nB, Np, Ns + Np, env->P, e0, phys,
+    k_ar_step<<<g2, AR_THREADS, AR_SMEM, st>>>(env->arZ, env->t_arW, env->screens, env->phase_tiles, nB, Np, Ns + Np, env->P, e0, phys,
                                   flipped, 1.0 / (c.wavelength_wfs * 3.14159265358979323846), env->phase_tiles_unit);
     AOG_LAUNCH_CHECK();
   }
@@ -350,7 +350,7 @@ void aog_destroy(aog_env* env) {
   cudaDeviceSynchronize();
   aog_tensor_destroy(env);
   void* ptrs[] = {env->t_aperture, env->t_modes, env->t_gram, env->t_m1f, env->t_m2f, env->t_m1o, env->t_m2o,
-                  env->t_lpw, env->t_lpphase, env->t_lpgram, env->t_stencil, env->t_arA, env->t_arB, env->t_arW,
+                  env->t_lpw, env->t_lpphase, env->t_lpgram, env->t_stencil, env->t_stencil_perm, env->t_arA, env->t_arB, env->t_arW,
                   env->t_scrC1, env->t_scrW1, env->t_scrW1T, env->t_scrC2, env->t_scrW2, env->t_scrW2T,
                   env->screens, env->act, env->bufA, env->bufB, env->bufC, env->bufR, env->coef,
                   env->strehl_part, env->arZ, env->arNew, env->act_in, env->noise_in, env->o_pack,
@@ -415,12 +415,31 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
   if (count != want)
     AOG_FAIL(AOG_ERR_INVALID, "table " + std::to_string(which) + ": expected " + std::to_string(want) +
                                   " elements, got " + std::to_string(count));
-  AOG_CUDA(cudaMemcpy(dst, host, want * esz, cudaMemcpyHostToDevice));
+  if (which == AOG_TABLE_AR_STENCIL) {
+    // gather order = by column, then row: the first stencil columns become contiguous runs of the column-major
+    // screens (coalesced gather); the rows of W follow the same permutation (k_build_arW)
+    const int32_t* st = static_cast<const int32_t*>(host);
+    std::vector<int> perm(Ns), sorted(Ns);
+    for (size_t j = 0; j < Ns; ++j) perm[j] = (int)j;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+      const long long ka = (long long)(st[a] % (int)Np) * (long long)Np + st[a] / (int)Np;
+      const long long kb = (long long)(st[b] % (int)Np) * (long long)Np + st[b] / (int)Np;
+      return ka < kb;
+    });
+    for (size_t j = 0; j < Ns; ++j) sorted[j] = st[perm[j]];
+    int rc = dev_alloc(env, &env->t_stencil_perm, Ns);
+    if (rc) return rc;
+    AOG_CUDA(cudaMemcpy(env->t_stencil_perm, perm.data(), Ns * sizeof(int), cudaMemcpyHostToDevice));
+    AOG_CUDA(cudaMemcpy(dst, sorted.data(), Ns * sizeof(int), cudaMemcpyHostToDevice));
+  } else {
+    AOG_CUDA(cudaMemcpy(dst, host, want * esz, cudaMemcpyHostToDevice));
+  }
   env->have[which] = true;
   if (env->step_graph) { cudaGraphExecDestroy(env->step_graph); env->step_graph = nullptr; }   // captured launches hold table-derived arguments
-  if ((which == AOG_TABLE_AR_A || which == AOG_TABLE_AR_B) && env->have[AOG_TABLE_AR_A] && env->have[AOG_TABLE_AR_B]) {
+  if ((which == AOG_TABLE_AR_A || which == AOG_TABLE_AR_B || which == AOG_TABLE_AR_STENCIL) && env->have[AOG_TABLE_AR_A] &&
+      env->have[AOG_TABLE_AR_B] && env->have[AOG_TABLE_AR_STENCIL]) {
     const int tot = (int)((Ns + Np) * Np);
-    k_build_arW<<<cdiv(tot, 256), 256>>>(env->t_arA, env->t_arB, env->t_arW, (int)Np, (int)Ns);
+    k_build_arW<<<cdiv(tot, 256), 256>>>(env->t_arA, env->t_arB, env->t_stencil_perm, env->t_arW, (int)Np, (int)Ns);
     AOG_LAUNCH_CHECK();
   }
   if (which == AOG_TABLE_SCR_W1) {
@@ -520,24 +539,25 @@ int aog_set_screens(aog_env* env, const void* src, int dtype, int src_on_device,
   const size_t nel = (size_t)count * env->P;
   double* dst = env->screens + (size_t)first_env * env->P;
   if (env->cnt.column_origin != 0) AOG_FAIL(AOG_ERR_STATE, "set_screens after extrusions: reset counters first");
-  if (dtype == AOG_DTYPE_F64) {
-    AOG_CUDA(cudaMemcpy(dst, src, nel * sizeof(double), src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-  } else if (dtype == AOG_DTYPE_F32) {
-    const float* s = (const float*)src;
-    float* tmp = nullptr;
+  if (dtype != AOG_DTYPE_F64 && dtype != AOG_DTYPE_F32) AOG_FAIL(AOG_ERR_INVALID, "dtype");
+  {
+    // the caller's screens are [y][x] (hcipy Field order); the device keeps them column-major
+    const size_t esz = dtype == AOG_DTYPE_F64 ? sizeof(double) : sizeof(float);
+    const void* s = src;
+    void* tmp = nullptr;
     if (!src_on_device) {
-      AOG_CUDA(cudaMalloc((void**)&tmp, nel * sizeof(float)));
-      cudaError_t e = cudaMemcpy(tmp, src, nel * sizeof(float), cudaMemcpyHostToDevice);
+      AOG_CUDA(cudaMalloc(&tmp, nel * esz));
+      cudaError_t e = cudaMemcpy(tmp, src, nel * esz, cudaMemcpyHostToDevice);
       if (e != cudaSuccess) { cudaFree(tmp); env->err = cudaGetErrorString(e); return AOG_ERR_CUDA; }
       s = tmp;
     }
-    k_f32_to_f64<<<(unsigned)((nel + 255) / 256), 256>>>(s, dst, nel);
+    const unsigned grid = (unsigned)((nel + 255) / 256);
+    if (dtype == AOG_DTYPE_F64) k_screens_in<double><<<grid, 256>>>((const double*)s, dst, c.num_pupil_pixels, nel);
+    else k_screens_in<float><<<grid, 256>>>((const float*)s, dst, c.num_pupil_pixels, nel);
     env->launches++;
     cudaError_t e = cudaDeviceSynchronize();
     if (tmp) cudaFree(tmp);
     if (e != cudaSuccess) { env->err = cudaGetErrorString(e); return AOG_ERR_CUDA; }
-  } else {
-    AOG_FAIL(AOG_ERR_INVALID, "dtype");
   }
   if (c.precision != AOG_PRECISION_F64) return aog_tensor_screens_updated(env);
   return AOG_OK;
@@ -556,7 +576,7 @@ int aog_get_screens(aog_env* env, double* host_out, int first_env, int count) {
   for (int b = 0; b < count; ++b)
     for (int y = 0; y < Np; ++y)
       for (int x = 0; x < Np; ++x)
-        host_out[(size_t)b * env->P + (size_t)y * Np + x] = tmp[(size_t)b * env->P + (size_t)y * Np + (x + org) % Np];
+        host_out[(size_t)b * env->P + (size_t)y * Np + x] = tmp[(size_t)b * env->P + (size_t)((x + org) % Np) * Np + y];
   return AOG_OK;
 }
 

@@ -26,7 +26,8 @@ struct aog_env {
   double* t_lpw = nullptr;         // [J][Nf*Nf]
   double2* t_lpphase = nullptr;    // [J]
   double* t_lpgram = nullptr;      // [J][J]
-  int* t_stencil = nullptr;        // [Ns]
+  int* t_stencil = nullptr;        // [Ns] flat pixel indices in GATHER order (sorted by column, then row)
+  int* t_stencil_perm = nullptr;   // [Ns] gather position -> index into the uploaded (row-major sorted) stencil
   double* t_arA = nullptr;         // [Np][Ns] as uploaded
   double* t_arB = nullptr;         // [Np][Np] as uploaded
   double* t_arW = nullptr;         // [(Ns+Np)][Np] = [A^T ; B^T]  (GEMM operand)
@@ -69,7 +70,8 @@ struct aog_env {
   int64_t sh_draws = 0;
 
   // ---- per-env state (device) ----
-  double* screens = nullptr;       // [B][P], ring-buffered along x (column_origin)
+  double* screens = nullptr;       // [B][Np x][Np y] COLUMN-major (a pupil column is contiguous: the extrusion reads and
+                                   // writes whole columns), ring-buffered along x (column_origin)
   double* act = nullptr;           // [B][K] DM actuators (after normalisation)
 
   // ---- scratch for one chunk of envs ----

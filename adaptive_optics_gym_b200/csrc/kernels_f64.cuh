@@ -90,7 +90,7 @@ static __global__ void k_field_f64(const double* __restrict__ screens, const dou
   for (int e = 0; e < ET; ++e) {
     double2 st = make_double2(0.0, 0.0);
     if (valid && e0 + e < nB) {
-      const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)y * Np + xp];
+      const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)xp * Np + y];
       double sn, cs;
       sincos(S / l_wfs + 2.0 * s[e] * kw, &sn, &cs);
       E[(size_t)(e0 + e) * P + p] = make_double2(amp * ap * cs, amp * ap * sn);
@@ -546,16 +546,18 @@ static __global__ void k_ar_gather(const double* __restrict__ screens, const int
     if (flipped) { y = Np - 1 - y; x = Np - 1 - x; }
     x += col_origin;
     if (x >= Np) x -= Np;
-    v = screens[(size_t)(env0 + b) * P + (size_t)y * Np + x];
+    v = screens[(size_t)(env0 + b) * P + (size_t)x * Np + y];
   } else {
     const int i = j - Ns;
     double xi;
     if (noise) {
       xi = noise[(size_t)(env0 + b) * noise_stride + i];
     } else {
+      // one Philox block (4 words) makes TWO normals: neighbouring threads (i, i ^ 1) share the draw of pair i / 2
       curandStatePhilox4_32_10_t st;
-      curand_init(seed, env_id_base + env0 + b, (draw_index * (unsigned long long)Np + i) * 4ull, &st);
-      xi = curand_normal_double(&st);
+      curand_init(seed, env_id_base + env0 + b, (draw_index * (unsigned long long)Np + (unsigned long long)(i & ~1)) * 4ull, &st);
+      const double2 z = curand_normal2_double(&st);
+      xi = (i & 1) ? z.y : z.x;
     }
     v = sqrt_cn2 * xi;
   }
@@ -569,7 +571,7 @@ static __global__ void k_ar_gather(const double* __restrict__ screens, const int
 // which leaves the slots for the operand traffic.  Block tile 128 envs x 64 pixels, warp tile 32 x 32 = 4 x 4
 // fragments.  ncu: DMMA pipe 50 % of the active cycles, 128 blocks on 148 SMs; splitting K over a second group of
 // 8 warps per tile (dmma_mainloop<2>) measured no gain (140 vs 135 us), so the plain form is used.
-//   screens[(env0 + b) P + y Np + phys_col] = new[b][flipped ? Np - 1 - y : y]
+//   screens[(env0 + b) P + phys_col Np + y] = new[b][flipped ? Np - 1 - y : y]      (screens are [x][y]: a column is contiguous)
 //   tiles (TensorState::hwt layout) [env / 32][phys_col][y / 16][env % 32][piece][y % 4] = fixed(new / (lambda_wfs pi))
 // Main loop shared by the FP64 tensor-core GEMMs: acc (warp tile 32 x 32 at (wm, wn) of the 128 x 64 block tile at
 // (m0, n0)) = A[M x Kd] (row stride lda) . B[Kd x N] (row stride ldb).  lda, ldb, Kd, N even, rows 16-byte aligned.
@@ -702,30 +704,87 @@ k_dgemm_mma(const double* __restrict__ A, const double* __restrict__ B, double* 
   }
 }
 
-static __global__ void __launch_bounds__(256)
+// The extrusion GEMM's own tiling: 112 envs x 64 pixels per block, 7 warps of 16 x 64 (2 x 8 fragments).  4096 envs
+// are 37 x 4 = 148 such tiles -- one per SM of a B200 in a single wave (the shared 128 x 64 tile gave 128 blocks).
+constexpr int AR_TM = 112, AR_THREADS = 224, AR_LDA = 8 + 4, AR_A_STAGE = AR_TM * AR_LDA, AR_B_STAGE = 8 * DMMA_LDB;
+constexpr int AR_SMEM = DMMA_STAGES * (AR_A_STAGE + AR_B_STAGE) * (int)sizeof(double);
+static __global__ void __launch_bounds__(AR_THREADS)
 k_ar_step(const double* __restrict__ Z, const double* __restrict__ W, double* __restrict__ screens,
           int32_t* __restrict__ tiles, int nB, int Np, int Kd, int P, int env0, int phys_col, int flipped,
           double inv_w, double phi_one) {
-  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 64;
-  double acc[4][4][2];
-  dmma_mainloop<1>(Z, Kd, nB, W, Np, Np, Kd, m0, n0, acc);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  extern __shared__ __align__(16) double dmma_smem[];
+  double* As = dmma_smem;                                      // [stage][112][AR_LDA]
+  double* Bs = dmma_smem + DMMA_STAGES * AR_A_STAGE;           // [stage][8][DMMA_LDB]
+  const int m0 = blockIdx.y * AR_TM, n0 = blockIdx.x * 64;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, gid = lane >> 2, tig = lane & 3;
+  const int wm = warp * 16;
+  auto issue = [&](int ks) {                                   // K step ks (8 deep) -> ring slot ks % DMMA_STAGES
+    const int k0 = ks * 8, st = ks % DMMA_STAGES;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                              // A: 112 rows x 4 chunks of 2 doubles
+      const int c = t + AR_THREADS * i, row = c >> 2, kc = (c & 3) * 2;
+      const bool ok = m0 + row < nB && k0 + kc < Kd;
+      cp_async16(As + st * AR_A_STAGE + row * AR_LDA + kc, Z + (size_t)(ok ? m0 + row : 0) * Kd + (ok ? k0 + kc : 0), ok);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                              // B: 8 rows x 32 chunks of 2 doubles
+      const int c = t + AR_THREADS * i;
+      if (c < 256) {
+        const int row = c >> 5, nc = (c & 31) * 2;
+        const bool ok = k0 + row < Kd && n0 + nc < Np;
+        cp_async16(Bs + st * AR_B_STAGE + row * DMMA_LDB + nc, W + (size_t)(ok ? k0 + row : 0) * Np + (ok ? n0 + nc : 0), ok);
+      }
+    }
+  };
+  double acc[2][8][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int nk = (Kd + 7) / 8;
+#pragma unroll
+  for (int s0 = 0; s0 < DMMA_STAGES - 1; ++s0) {
+    if (s0 < nk) issue(s0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int ks = 0; ks < nk; ++ks) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(DMMA_STAGES - 2) : "memory");   // K step ks has landed
+    __syncthreads();                                            // ... for every thread; slot (ks - 1) % STAGES is free
+    if (ks + DMMA_STAGES - 1 < nk) issue(ks + DMMA_STAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* as = As + (ks % DMMA_STAGES) * AR_A_STAGE;
+    const double* bs = Bs + (ks % DMMA_STAGES) * AR_B_STAGE;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; k4 += 4) {
+      double a[2], b[8];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = as[(wm + 8 * i + gid) * AR_LDA + k4 + tig];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = bs[(k4 + tig) * DMMA_LDB + 8 * j + gid];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   // C fragment: row gid, columns 2 tig + {0, 1}
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const int b = m0 + wm + 8 * i + gid;
     if (b >= nB) continue;
     const size_t env = (size_t)env0 + b;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int e2 = 0; e2 < 2; ++e2) {
-        const int n = n0 + wn + 8 * j + 2 * tig + e2;
+        const int n = n0 + 8 * j + 2 * tig + e2;
         if (n >= Np) continue;
         const int y = flipped ? Np - 1 - n : n;
         const double S = acc[i][j][e2];
-        screens[env * P + (size_t)y * Np + phys_col] = S;
+        screens[env * P + (size_t)phys_col * Np + y] = S;          // the ring slot is one contiguous column
         if (tiles) {
           double f = S * inv_w * phi_one;
           f = fmin(fmax(f, -2147483000.0), 2147483000.0);
@@ -743,7 +802,7 @@ static __global__ void k_ar_scatter(double* __restrict__ screens, const double* 
   const int y = blockIdx.x * blockDim.x + threadIdx.x;
   if (y >= Np) return;
   const int src = flipped ? (Np - 1 - y) : y;
-  screens[(size_t)(env0 + b) * P + (size_t)y * Np + phys_col] = newcol[(size_t)b * Np + src];
+  screens[(size_t)(env0 + b) * P + (size_t)phys_col * Np + y] = newcol[(size_t)b * Np + src];
 }
 
 // --------------------------------------------------------------------------------------
@@ -789,13 +848,13 @@ static __global__ void k_scr_combine4(double* __restrict__ screens, const double
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
-  const int y = q / Nh, x = q - y * Nh;
-  const double* p = Pq + (size_t)b * strideP + q;
+  const int x = q / Nh, y = q - x * Nh;                // consecutive threads -> consecutive y: contiguous stores
+  const double* p = Pq + (size_t)b * strideP + (size_t)y * Nh + x;
   const double p1 = p[0], p2 = p[Q], p3 = p[2 * Q], p4 = p[3 * Q];
-  double* s = screens + (size_t)(env0 + b) * Np * Np;
+  double* s = screens + (size_t)(env0 + b) * Np * Np;  // [x][y]
   const double v[4] = {(p1 - p2) - (p3 + p4), (p1 - p2) + (p3 + p4), (p1 + p2) - (p3 - p4), (p1 + p2) + (p3 - p4)};
-  const size_t idx[4] = {(size_t)y * Np + x, (size_t)y * Np + (Np - 1 - x), (size_t)(Np - 1 - y) * Np + x,
-                         (size_t)(Np - 1 - y) * Np + (Np - 1 - x)};
+  const size_t idx[4] = {(size_t)x * Np + y, (size_t)(Np - 1 - x) * Np + y, (size_t)x * Np + (Np - 1 - y),
+                         (size_t)(Np - 1 - x) * Np + (Np - 1 - y)};
 #pragma unroll
   for (int c = 0; c < 4; ++c) s[idx[c]] = accumulate ? (s[idx[c]] + scale * v[c]) : scale * v[c];
 }
@@ -805,7 +864,11 @@ static __global__ void k_scr_combine(double* __restrict__ screens, const double2
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  const double v = scale * Y[(size_t)b * strideY + p].x;
+  // thread p = (x, y) with y fastest (contiguous stores into the column-major screens); Y is [y][x]
+  int Np = 1;
+  while (Np * Np < P) ++Np;
+  const int x = p / Np, y = p - x * Np;
+  const double v = scale * Y[(size_t)b * strideY + (size_t)y * Np + x].x;
   double* s = screens + (size_t)(env0 + b) * P + p;
   *s = accumulate ? (*s + v) : v;
 }
@@ -845,7 +908,7 @@ static __global__ void k_sh_field_f64(const double* __restrict__ screens, const 
 #pragma unroll
   for (int e = 0; e < ET; ++e)
     if (e0 + e < nB) {
-      const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)y * Np + xp];
+      const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)xp * Np + y];
       double sn, cs;
       sincos(S / l_wfs + 2.0 * s[e] * kw + ml, &sn, &cs);
       E[(size_t)(e0 + e) * P + p] = make_double2(amp * ap * cs, amp * ap * sn);
@@ -897,7 +960,7 @@ static __global__ void k_sh_field_fold(const double* __restrict__ screens, const
         const int y = pix[c] / Np;
         int xp = pix[c] - y * Np + col_origin;
         if (xp >= Np) xp -= Np;
-        const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)y * Np + xp];
+        const double S = screens[(size_t)(env0 + e0 + e) * P + (size_t)xp * Np + y];
         const double ap = aperture[pix[c]];
         double sn, cs;
         sincos(S / l_wfs + 2.0 * s[c][e] * kw + mla_phase[pix[c]], &sn, &cs);
@@ -1029,9 +1092,14 @@ static __global__ void k_broadcast_rows(const double* __restrict__ row, double* 
 }
 
 // misc ---------------------------------------------------------------------------------
-static __global__ void k_f32_to_f64(const float* __restrict__ in, double* __restrict__ out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (double)in[i];
+// caller's screens [count][y][x] (row-major, as hcipy's Field) -> device screens [count][x][y] FP64
+template <typename T>
+static __global__ void k_screens_in(const T* __restrict__ in, double* __restrict__ out, int Np, size_t n) {
+  const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  const size_t P = (size_t)Np * Np, b = o / P, r = o - b * P;
+  const int x = (int)(r / Np), y = (int)(r - (size_t)x * Np);
+  out[o] = (double)in[b * P + (size_t)y * Np + x];
 }
 
 static __global__ void k_transpose_z(const double2* __restrict__ in, double2* __restrict__ out, int rows, int cols) {
@@ -1039,13 +1107,13 @@ static __global__ void k_transpose_z(const double2* __restrict__ in, double2* __
   if (i < rows * cols) { int r = i / cols, c = i - r * cols; out[(size_t)c * rows + r] = in[i]; }
 }
 
-static __global__ void k_build_arW(const double* __restrict__ A, const double* __restrict__ Bm, double* __restrict__ W,
-                            int Np, int Ns) {
-  // W[j][y] = A[y][j] (j < Ns);  W[Ns + j][y] = B[y][j]
+static __global__ void k_build_arW(const double* __restrict__ A, const double* __restrict__ Bm, const int* __restrict__ perm,
+                            double* __restrict__ W, int Np, int Ns) {
+  // W[j][y] = A[y][perm[j]] (j < Ns: stencil point j of the gather order);  W[Ns + j][y] = B[y][j]
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (Ns + Np) * Np) return;
   int j = i / Np, y = i - j * Np;
-  W[i] = (j < Ns) ? A[(size_t)y * Ns + j] : Bm[(size_t)y * Np + (j - Ns)];
+  W[i] = (j < Ns) ? A[(size_t)y * Ns + perm[j]] : Bm[(size_t)y * Np + (j - Ns)];
 }
 
 static __global__ void k_focal_power(const double2* __restrict__ F, double* __restrict__ out, int n, double2 norm, double w) {

@@ -1497,7 +1497,7 @@ __global__ void k_act_pack(const double* __restrict__ act, __half* __restrict__ 
   a_lo[i] = __float2half_rn((float)(v - (double)__half2float(h)));
 }
 
-// screens FP64 [B][y][xp] -> tiled fixed-point phase at lambda_wfs (layout: TensorState::hwt).
+// screens FP64 [B][xp][y] -> tiled fixed-point phase at lambda_wfs (layout: TensorState::hwt).
 // One thread per output int, output-ordered (coalesced writes, strided reads).
 __device__ __forceinline__ int32_t phase_fixed(double S, double inv) {
   double a = S * inv * (double)PHI_ONE;                  // half-turns x 2^22
@@ -1516,7 +1516,7 @@ __global__ void k_screens_to_tiles(const double* __restrict__ src, int32_t* __re
   const size_t env = (t2 / Np) * 32 + l;
   const int y = ci * 16 + ((piece ^ ((l >> 1) & 3)) << 2) + e;
   int32_t v = 0;
-  if (env < (size_t)B) v = phase_fixed(src[(env * Np + y) * Np + xp], inv_w);
+  if (env < (size_t)B) v = phase_fixed(src[(env * Np + xp) * Np + y], inv_w);      // screens are [env][x][y]
   hwt[o] = v;
 }
 // one physical column refresh after an extrusion
@@ -1525,7 +1525,7 @@ __global__ void k_column_to_tiles(const double* __restrict__ src, int32_t* __res
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // over B * Np
   if (i >= B * Np) return;
   const int env = i / Np, y = i - env * Np;
-  const double S = src[((size_t)env * Np + y) * Np + phys_col];
+  const double S = src[((size_t)env * Np + phys_col) * Np + y];
   const int l = env & 31, ci = y >> 4, piece = ((y >> 2) & 3) ^ ((l >> 1) & 3), e = y & 3;
   const size_t tile = (((size_t)(env >> 5) * Np + phys_col) * (Np / 16) + ci) * (32 * 16);
   hwt[tile + (size_t)l * 16 + piece * 4 + e] = phase_fixed(S, inv_w);
