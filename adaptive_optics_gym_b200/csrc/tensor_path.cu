@@ -562,9 +562,9 @@ constexpr int FK_PARTS = FK_EPI_WARPS / 4;
 // (The tensor path's phase kernel keeps the natural order: its phase stores of neighbouring columns are neighbours
 // in HBM, and striding them costs more DRAM page misses than the imbalance does.)
 constexpr int FK_COL_STRIDE = 53;
-template <int MODE>
+template <int MODE, int NP>
 __device__ __forceinline__ int fk_column(int item_in_block) {
-  return (MODE == 0 || MODE == 3) ? item_in_block : (item_in_block * FK_COL_STRIDE) % TC_NP;
+  return (MODE == 0 || MODE == 3) ? item_in_block : (item_in_block * FK_COL_STRIDE) % NP;   // 53 is prime: coprime with every NP
 }
 constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
 constexpr int FK_SLOTS = 128;                           // Strehl / fibre partial slots per env (>= CTAs touching an env block)
@@ -664,12 +664,15 @@ struct FieldParams {
   int* err_flag;
 };
 
-template <bool STREHL, int NOBS, int MODE>
+// NP = pupil pixels per side: 240 (the reference, AO_env.py:216) for every mode; 128 and 256 for the fused modes
+// (BASELINE configs[4], the pupil-grid axis).  Any multiple of 16 up to 256 fits the tiles (N of the MMA, TMEM columns).
+template <bool STREHL, int NOBS, int MODE, int NP = TC_NP>
 __global__ void __launch_bounds__(FK_THREADS, 1)
 k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constant__ CUtensorMap tmAct_lo,
               const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
               const FieldParams p) {
-  constexpr int Np = TC_NP;
+  static_assert(NP % 16 == 0 && NP <= 256, "pupil size of the phase kernel");
+  constexpr int Np = NP;
   constexpr uint32_t TX_BYTES = 2 * FK_A_TILE + 2 * Np * 64 * 2;
   constexpr uint32_t IDESC = umma_idesc_f16(128, Np);
   extern __shared__ uint8_t smem_raw[];
@@ -731,7 +734,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int item = item_lo; item < item_hi; ++item) {
-        const int eb = item / Np, x = fk_column<MODE>(item - eb * Np);
+        const int eb = item / Np, x = fk_column<MODE, NP>(item - eb * Np);
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait<200>(&empty[stage], phase ^ 1, p.err_flag, 11);
           mbar_expect_tx(&full[stage], TX_BYTES);
@@ -815,7 +818,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
       while (n_ci >= n_end) {
         n_base = (n_base + n_cnt) % FK_PARTS;
         if (++n_item >= item_hi) return false;
-        n_x = fk_column<MODE>(n_item - (n_item / Np) * Np);
+        n_x = fk_column<MODE, NP>(n_item - (n_item / Np) * Np);
         n_cnt = run_s[2 * n_x + 1];
         n_ci = run_s[2 * n_x] + (q + FK_PARTS - n_base) % FK_PARTS;
         n_end = run_s[2 * n_x] + n_cnt;
@@ -880,7 +883,7 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
     };
 
     for (int item = item_lo; item < item_hi; ++item, ++it) {
-      const int eb = item / Np, x = fk_column<MODE>(item - eb * Np);
+      const int eb = item / Np, x = fk_column<MODE, NP>(item - eb * Np);
       if ((STREHL || FUSED) && eb != cur_eb) {
         if (cur_eb >= 0) flush_strehl(cur_eb);
         cur_eb = eb;
@@ -1608,9 +1611,13 @@ int upload_split(aog_env* env, const std::vector<double>& m, __half* d_hi, __hal
 // =============================================================================================
 int aog_tensor_create(aog_env* env) {
   const aog_config& c = env->cfg;
-  if (c.num_pupil_pixels != TC_NP || c.num_focal_pixels != TC_NF)
-    AOG_FAIL(AOG_ERR_UNSUPPORTED, "tensor precision path is built for num_pupil_pixels=240, num_focal_pixels=128; "
-                                  "use precision='f64' for other grids");
+  const int NPc = c.num_pupil_pixels;
+  if (c.precision == AOG_PRECISION_TENSOR && (NPc != TC_NP || c.num_focal_pixels != TC_NF))
+    AOG_FAIL(AOG_ERR_UNSUPPORTED, "precision='tensor' (matrix-Fourier-transform GEMMs) is built for num_pupil_pixels=240, "
+                                  "num_focal_pixels=128; use precision='fused' (pupil 128 / 240 / 256, any focal grid) or 'f64'");
+  if (c.precision == AOG_PRECISION_FUSED && NPc != TC_NP && !((NPc == 128 || NPc == 256) && (c.obs_dim == 2 || c.obs_dim == 5)))
+    AOG_FAIL(AOG_ERR_UNSUPPORTED, "precision='fused' supports num_pupil_pixels=240 (any obs_dim <= 8) and 128 / 256 (obs_dim 2 "
+                                  "or 5), with any focal grid; use precision='f64' for other grids");
   TensorState* ts = new TensorState();
   env->tensor_state = ts;
   ts->fused = c.precision == AOG_PRECISION_FUSED;
@@ -1647,7 +1654,7 @@ int aog_tensor_create(aog_env* env) {
   ts->kpad = ((c.num_modes + 63) / 64) * 64;
   ts->act_rows = (int)((ch + 127) / 128) * 128;
   {
-    const size_t tiles = ((B + 127) / 128) * 4 * TC_NP * (TC_NP / 16);   // whole 128-env blocks: the prefetch reads them all
+    const size_t tiles = ((B + 127) / 128) * 4 * NPc * (NPc / 16);       // whole 128-env blocks: the prefetch reads them all
     A(talloc(env, &ts->hwt, tiles * 512));
     AOG_CUDA(cudaMemset(ts->hwt, 0, tiles * 512 * sizeof(int32_t)));
     env->phase_tiles = ts->hwt;
@@ -1659,10 +1666,10 @@ int aog_tensor_create(aog_env* env) {
   A(talloc(env, &ts->act_lo, (size_t)ts->act_rows * ts->kpad));
   AOG_CUDA(cudaMemset(ts->act_hi, 0, (size_t)ts->act_rows * ts->kpad * sizeof(__half)));
   AOG_CUDA(cudaMemset(ts->act_lo, 0, (size_t)ts->act_rows * ts->kpad * sizeof(__half)));
-  A(talloc(env, &ts->apmask, (size_t)TC_NP * (TC_NP / 16)));
-  A(talloc(env, &ts->m1o32, (size_t)c.obs_dim * TC_NP));
-  A(talloc(env, &ts->R4, ch * TC_NP * FK_PARTS * c.obs_dim));
-  A(talloc(env, &ts->m2oT, (size_t)c.obs_dim * TC_NP));
+  A(talloc(env, &ts->apmask, (size_t)NPc * (NPc / 16)));
+  A(talloc(env, &ts->m1o32, (size_t)c.obs_dim * NPc));
+  A(talloc(env, &ts->R4, ch * NPc * FK_PARTS * c.obs_dim));
+  A(talloc(env, &ts->m2oT, (size_t)c.obs_dim * NPc));
   // barrier-timeout code: mapped pinned HOST memory, so that the host can still read it after the trap that follows
   // a timeout has poisoned the CUDA context (aog_health)
   AOG_CUDA(cudaHostAlloc((void**)&ts->err_flag_host, sizeof(int), cudaHostAllocMapped));
@@ -1681,8 +1688,8 @@ int aog_tensor_create(aog_env* env) {
   }
   A(make_map(env, &ts->tmAct_hi, ts->act_hi, ts->act_rows, 128, ts->kpad, 64));
   A(make_map(env, &ts->tmAct_lo, ts->act_lo, ts->act_rows, 128, ts->kpad, 64));
-  A(make_map(env, &ts->tmModes_hi, ts->modesK_hi, P, TC_NP, ts->kpad, 64));
-  A(make_map(env, &ts->tmModes_lo, ts->modesK_lo, P, TC_NP, ts->kpad, 64));
+  A(make_map(env, &ts->tmModes_hi, ts->modesK_hi, P, NPc, ts->kpad, 64));
+  A(make_map(env, &ts->tmModes_lo, ts->modesK_lo, P, NPc, ts->kpad, 64));
 #undef A
   AOG_CUDA(cudaFuncSetAttribute(k_mft2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
   AOG_CUDA(cudaFuncSetAttribute(k_mft2<AOG_MAX_LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, M2_SMEM_BYTES));
@@ -1712,7 +1719,7 @@ namespace {
 //       = norm sum_{y,x} E[y][x] G_j[y][x],          G_j = M1^T (mode_j w) M2^T
 // so the coupling coefficients are J inner products over the pupil and the focal plane is never formed.
 int build_backprojected_modes(aog_env* env, TensorState* ts) {
-  const int Np = TC_NP, Nf = TC_NF, J = env->cfg.num_lp_modes;
+  const int Np = env->cfg.num_pupil_pixels, Nf = env->cfg.num_focal_pixels, J = env->cfg.num_lp_modes;
   const std::vector<double>&m1 = ts->h_m1, &m2 = ts->h_m2, &lp = ts->h_lp;
   std::vector<double> H((size_t)2 * Nf * Np), G((size_t)2 * J * Np * Np);
   double gmax = 0.0;
@@ -1767,7 +1774,7 @@ int build_backprojected_modes(aog_env* env, TensorState* ts) {
 // per-pixel records of the fused kernel (TensorState::gfib), once G, the obs-arm table and the aperture are known
 int build_fused_records(aog_env* env, TensorState* ts) {
   if (!(ts->have_G && ts->have_m1o && ts->have_ap && ts->have_lpphase)) return AOG_OK;
-  const int Np = TC_NP, J = env->cfg.num_lp_modes, n = env->cfg.obs_dim, NT = FK_NT(n);
+  const int Np = env->cfg.num_pupil_pixels, J = env->cfg.num_lp_modes, n = env->cfg.obs_dim, NT = FK_NT(n);
   // do the obs-arm rows come in conjugate pairs (real centre row)?
   bool obs_sym = true;
   {
@@ -1839,7 +1846,7 @@ int aog_tensor_sh_table(aog_env* env, int which, const void* host);   // sh_tens
 int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
   TensorState* ts = TS(env);
   const aog_config& c = env->cfg;
-  const int Np = TC_NP, Nf = TC_NF;
+  const int Np = c.num_pupil_pixels, Nf = c.num_focal_pixels;     // the tensor-precision branches below run at 240 / 128 only
   if (which >= AOG_TABLE_SH_MLA_PHASE && which <= AOG_TABLE_SH_ACT0) return aog_tensor_sh_table(env, which, host);
   if (ts->fused && which == AOG_TABLE_LP_PHASE) {
     const double* m = static_cast<const double*>(host);
@@ -1964,7 +1971,7 @@ int aog_tensor_table_updated(aog_env* env, int which, const void* host) {
 
 int aog_tensor_screens_updated(aog_env* env) {
   TensorState* ts = TS(env);
-  const int Np = TC_NP, B = env->cfg.num_envs;
+  const int Np = env->cfg.num_pupil_pixels, B = env->cfg.num_envs;
   const double pi = 3.14159265358979323846;
   const size_t total = (size_t)((B + 127) / 128) * 4 * Np * (Np / 16) * 512;
   k_screens_to_tiles<<<(unsigned)((total + 255) / 256), 256>>>(env->screens, ts->hwt, Np, B, total,
@@ -1978,7 +1985,7 @@ int aog_tensor_column_updated(aog_env* env, int phys_col, cudaStream_t st) {
   TensorState* ts = TS(env);
   const int B = env->cfg.num_envs;
   const double pi = 3.14159265358979323846;
-  k_column_to_tiles<<<cdiv(B * TC_NP, 256), 256, 0, st>>>(env->screens, ts->hwt, TC_NP, B, phys_col,
+  k_column_to_tiles<<<cdiv(B * env->cfg.num_pupil_pixels, 256), 256, 0, st>>>(env->screens, ts->hwt, env->cfg.num_pupil_pixels, B, phys_col,
                                                           1.0 / (env->cfg.wavelength_wfs * pi));
   AOG_LAUNCH_CHECK();
   return AOG_OK;
@@ -2059,24 +2066,35 @@ int aog_tensor_check(aog_env* env) {
 }
 
 namespace {
-template <bool STREHL, int NOBS, int MODE>
+template <bool STREHL, int NOBS, int MODE, int NP = TC_NP>
 int launch_phase(aog_env* env, TensorState* ts, const FieldParams& p, int grid, cudaStream_t st) {
   constexpr bool FUSED = MODE == 1 || MODE == 2;
   const int smem = FK_STAGES * FK_STAGE_BYTES + FK_PF_BYTES(NOBS, MODE) + 1024 + FK_AUX_BAR +
                    (FUSED ? 1 + FK_JT : 1) * FK_PARTS * 128 * (int)sizeof(double2) +
-                   (FUSED ? 0 : NOBS * TC_NP * (int)sizeof(float2)) + TC_NP * (TC_NP / 16) * (int)sizeof(uint16_t) + 2 * TC_NP;
+                   (FUSED ? 0 : NOBS * NP * (int)sizeof(float2)) + NP * (NP / 16) * (int)sizeof(uint16_t) + 2 * NP;
   static std::atomic<bool> configured_on[64];   // function attributes are per device: one flag per device ordinal
   std::atomic<bool>& configured = configured_on[env->cfg.device & 63];
   if (!configured.load(std::memory_order_acquire)) {
-    AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AOG_CUDA(cudaFuncSetAttribute(k_dm_phase_tc<STREHL, NOBS, MODE, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured.store(true, std::memory_order_release);
   }
-  k_dm_phase_tc<STREHL, NOBS, MODE><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
+  k_dm_phase_tc<STREHL, NOBS, MODE, NP><<<grid, FK_THREADS, smem, st>>>(ts->tmAct_hi, ts->tmAct_lo, ts->tmModes_hi, ts->tmModes_lo, p);
   AOG_LAUNCH_CHECK();
   return AOG_OK;
 }
 template <bool STREHL, int MODE>
 int launch_phase_n(aog_env* env, TensorState* ts, const FieldParams& p, int n, int grid, cudaStream_t st) {
+  const int Np = env->cfg.num_pupil_pixels;
+  if (Np != TC_NP) {
+    // the pupil-grid axis of BASELINE configs[4]: fused kernels for 128^2 and 256^2 pupils, detectors 2x2 and 5x5
+    if constexpr (MODE == 1 || MODE == 2) {
+      if (Np == 128 && n == 2) return launch_phase<STREHL, 2, MODE, 128>(env, ts, p, grid, st);
+      if (Np == 128 && n == 5) return launch_phase<STREHL, 5, MODE, 128>(env, ts, p, grid, st);
+      if (Np == 256 && n == 2) return launch_phase<STREHL, 2, MODE, 256>(env, ts, p, grid, st);
+      if (Np == 256 && n == 5) return launch_phase<STREHL, 5, MODE, 256>(env, ts, p, grid, st);
+    }
+    AOG_FAIL(AOG_ERR_UNSUPPORTED, "fused kernels for pupils other than 240^2 are built for 128^2 / 256^2 with obs_dim 2 or 5");
+  }
   switch (n) {
     case 1: return launch_phase<STREHL, 1, MODE>(env, ts, p, grid, st);
     case 2: return launch_phase<STREHL, 2, MODE>(env, ts, p, grid, st);
@@ -2099,7 +2117,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     AOG_FAIL(AOG_ERR_STATE, "tensor path tables incomplete");
   const bool fused = ts->fused;
   (void)flat_dm;                         // the caller has already zeroed the actuators of a flattened mirror
-  const int Np = TC_NP, n = c.obs_dim, K = c.num_modes, J = c.num_lp_modes, B = c.num_envs;
+  const int Np = c.num_pupil_pixels, n = c.obs_dim, K = c.num_modes, J = c.num_lp_modes, B = c.num_envs;
   const bool strehl = with_reward && c.rew_type == AOG_REW_STREHL_RATIO;
   const double2 norm = make_double2(c.mft_norm_re * c.amp_fiber, c.mft_norm_im * c.amp_fiber);
   int slot_ipc = 1;
@@ -2118,7 +2136,7 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       FieldParams fp{};
       fp.num_envs = nB;
       fp.num_items = cdiv(nB, 128) * Np;
-      fp.items_per_cta = std::max(FK_MIN_ITEMS, cdiv(fp.num_items, ts->num_sms));
+      fp.items_per_cta = std::max(Np / FK_MIN_ITEMS + 1 <= FK_SLOTS ? FK_MIN_ITEMS : FK_MIN_ITEMS + 1, cdiv(fp.num_items, ts->num_sms));   // CTAs per env block <= FK_SLOTS
       fp.nkb = ts->kpad / 64;
       fp.col_origin = (int)env->cnt.column_origin;
       fp.env0 = e0;

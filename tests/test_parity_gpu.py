@@ -824,3 +824,40 @@ def test_small_batch_cuda_graph_step_equals_plain_launches(precision, monkeypatc
     for g, p in zip(out['graph'][0], out['plain'][0]):
         assert np.array_equal(g[0], p[0]) and g[1:] == p[1:]
     assert out['graph'][1] == out['plain'][1]            # the launch counter counts the graph's kernels too
+
+
+@pytest.mark.parametrize('Np,Nf,obs_dim,act_type,K,rew_type', [(128, 64, 2, 'num_actuators', 64, 'strehl_ratio'),
+                                                             (256, 256, 5, 'zernike', 6, 'smf_ssim'),
+                                                             (128, 256, 5, 'num_actuators', 64, 'strehl_ratio'),
+                                                             (256, 64, 2, 'zernike', 10, 'strehl_ratio')])
+def test_other_grid_sizes_fused_against_oracle(Np, Nf, obs_dim, act_type, K, rew_type):
+    """BASELINE configs[4] on the fast path: the fused tcgen05 kernel at pupil 128^2 / 256^2 (template parameter of
+    k_dm_phase_tc) with focal grids 64^2 ... 256^2 (the fused path never forms the focal plane: any focal grid is a
+    host-side table) against OracleAOEnv built with the same sizes, 1e-5; a 3-env batch equals its single envs."""
+    import torch
+    from adaptive_optics_gym_b200 import AOVecEnv
+    from oracle.ao_oracle import OracleAOEnv, hcipy_make_pupil_grid, hcipy_Cn_squared_from_fried_parameter, von_karman_screen
+    kw = dict(atm_type='quasi_static', atm_fried=0.15, act_type=act_type, act_dim=K, obs_dim=obs_dim, rew_type=rew_type,
+              timesteps_per_episode=3, num_pupil_pixels=Np, num_focal_pixels_fiber=Nf)
+    g = hcipy_make_pupil_grid(Np, 0.5)
+    cn2 = hcipy_Cn_squared_from_fried_parameter(0.15, 2.2e-6)
+    scr = np.stack([von_karman_screen(g, cn2, 10.0, np.random.default_rng(Np + Nf + i)) for i in range(3)])
+    env = _mk('fused', **kw, initial_screen=scr[0])
+    vec = AOVecEnv(3, **kw, precision='fused', initial_screens=scr)
+    ref = OracleAOEnv(**kw, initial_screen=scr[0])
+    rng = np.random.default_rng(Nf)
+    env.reset(), ref.reset(), vec.reset()
+    _close_obs(env.last_obs_f64, ref.last_obs_f64, 'reset obs')
+    for t in range(3):
+        a = rng.normal(0, 0.7, (3, K)).astype(np.float32)
+        o, r, d, _, info = env.step(a[0])
+        ro, rr, rd, _, rinfo = ref.step(a[0])
+        vo, vr, vd, _, vinfo = vec.step(torch.from_numpy(a).cuda())
+        torch.cuda.synchronize()
+        assert d == rd == bool(vd[0])
+        _close_obs(env.last_obs_f64, ref.last_obs_f64, f'obs step {t}')
+        _close(r, rr, 1e-5, 'reward')
+        _close(info['power'], rinfo['power'], 1e-5, 'power')
+        assert vr[0].item() == r and vinfo['power'][0].item() == info['power']
+        assert np.array_equal(vo[0].cpu().numpy().view(np.uint16), o.view(np.uint16))
+    env.close(), vec.close()
