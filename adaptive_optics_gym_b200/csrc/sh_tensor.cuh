@@ -411,7 +411,7 @@ struct ShCamParams {
 // rows), adds them to the block's sums in 64-bit FIXED POINT through shared-memory atomics: integer addition does
 // not depend on the order of the additions, so the result is deterministic like the FP64 path's per-lenslet warps.
 constexpr int CAM_PARTS = 2, CAM_THREADS = 128 * CAM_PARTS;
-__global__ void __launch_bounds__(CAM_THREADS, 3) k_sh_camera_tc(const ShCamParams p) {
+__global__ void __launch_bounds__(CAM_THREADS, 2) k_sh_camera_tc(const ShCamParams p) {
   constexpr int Np = TC_NP;
   extern __shared__ unsigned long long cam_acc[];       // [3 Nsub] fixed-point sums, then [2 Nsub] doubles (slopes)
   double* slopes = reinterpret_cast<double*>(cam_acc + 3 * p.Nsub);
@@ -483,23 +483,45 @@ __global__ void __launch_bounds__(CAM_THREADS, 3) k_sh_camera_tc(const ShCamPara
                            (re[0] - re[1]) + (re[2] - re[3]), (re[0] - re[1]) - (re[2] - re[3])};
       const float fi[4] = {(im[0] + im[1]) + (im[2] + im[3]), (im[0] + im[1]) - (im[2] + im[3]),
                            (im[0] - im[1]) + (im[2] - im[3]), (im[0] - im[1]) - (im[2] - im[3])};
-      float z[4];
-      uint4 ctr = make_uint4((uint32_t)(i * SH_NH + uu), (uint32_t)genv, (uint32_t)p.draw, 0u);
-      if (noisy) normals4(philox4x32_10(ctr, key), z);
+      float v[4];
+      bool small = false;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) v[m] = slv[m] >= 0 ? (fr[m] * fr[m] + fi[m] * fi[m]) * p.img_scale : 0.f;
+      // lenslet rows end together: one vote per row, and normally the whole warp flushes at once
+      const bool changed = slv[0] != cur[0] || slv[1] != cur[1] || slv[2] != cur[2] || slv[3] != cur[3];
+      if (__any_sync(0xffffffffu, changed)) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const bool need = slv[m] != cur[m];
+          flush(m, need);
+          cur[m] = slv[m];
+        }
+      }
+      if (noisy) {
+        const uint4 ctr = make_uint4((uint32_t)(i * SH_NH + uu), (uint32_t)genv, (uint32_t)p.draw, 0u);
+        float z[4];
+        normals4(philox4x32_10(ctr, key), z);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          small |= v[m] > 0.f && v[m] < 10.f;
+          v[m] = v[m] > 0.f ? poisson_large_f32(fmaxf(v[m], 10.f), z[m]) : 0.f;      // (rates below 10 are redone exactly below)
+        }
+        if (__any_sync(0xffffffffu, small)) {                        // rare: a pixel with fewer than 10 photons
+#pragma unroll 1
+          for (int m = 0; m < 4; ++m) {
+            const float lam = slv[m] >= 0 ? (fr[m] * fr[m] + fi[m] * fi[m]) * p.img_scale : 0.f;
+            if (lam > 0.f && lam < 10.f) {
+              const float k = poisson_small_f32(lam, ctr, key, m);
+              if (m == 0) v[0] = k; else if (m == 1) v[1] = k; else if (m == 2) v[2] = k; else v[3] = k;
+            }
+          }
+        }
+      }
+      const double r0 = (double)i, r1 = (double)(Np - 1 - i);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const int row = (m & 1) ? Np - 1 - i : i;
-        const int sl = slv[m];
-        const bool need = sl != cur[m];
-        if (__any_sync(0xffffffffu, need)) {           // lenslet rows end together: normally the whole warp at once
-          flush(m, need);
-          if (need) cur[m] = sl;
-        }
-        if (sl < 0) continue;
-        float v = (fr[m] * fr[m] + fi[m] * fi[m]) * p.img_scale;
-        if (noisy) v = v >= 10.f ? poisson_large_f32(v, z[m]) : poisson_small_f32(v, ctr, key, m);
-        f[m] += (double)v;
-        sy[m] = fma((double)v, (double)row, sy[m]);
+        f[m] += (double)v[m];
+        sy[m] = fma((double)v[m], (m & 1) ? r1 : r0, sy[m]);
       }
     }
 #pragma unroll
