@@ -412,6 +412,7 @@ static __global__ void k_finalize(FinalizeArgs a) {
 static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
   extern __shared__ double2 fin_R[];                   // [Np][n] column sums
   __shared__ double obs[AOG_MAX_OBS * AOG_MAX_OBS];
+  __shared__ double2 pre[AOG_MAX_LP + 1];              // slot sums of the fibre projections and of the Strehl sum
   const int b = blockIdx.x, n = a.n, n2 = n * n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   if (a.act) {
@@ -432,7 +433,36 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
       return;
     }
   }
+  // The block is one long latency chain (slot sums -> column sums -> contraction -> reward): warps 1 and 2 fetch and
+  // reduce the per-CTA partial slots of the fibre projections / Strehl sum FIRST, so that their DRAM round trips run
+  // under the column-sum loads of the whole block.
+  const int eb = b >> 7;
+  const int nslots = ((eb + 1) * a.slot_items - 1) / a.slot_ipc - (eb * a.slot_items) / a.slot_ipc + 1;
+  if (a.compute_reward && warp == 1) {
+    for (int j = 0; j < a.J; ++j) {
+      double2 cj = make_double2(0.0, 0.0);
+      if (a.coef_is_raw == 2) {
+        const double* c4 = a.coef4 + ((size_t)b * a.J + j) * 4;
+        cj = make_double2(c4[0] + c4[1], c4[2] + c4[3]);
+      } else {
+        const double2* fp = a.fib_part + (size_t)b * a.fib_slots * a.fib_stride + j;
+        for (int i = lane; i < nslots; i += 32) { cj.x += fp[i * a.fib_stride].x; cj.y += fp[i * a.fib_stride].y; }
+        cj.x = warp_sum(cj.x);
+        cj.y = warp_sum(cj.y);
+      }
+      if (lane == 0) pre[j] = cj;
+    }
+  }
+  if (a.compute_reward && warp == 2 && a.rew_type == AOG_REW_STREHL_RATIO) {
+    double sr = 0.0, si = 0.0;
+    const double2* sp = a.strehl_part + (size_t)b * a.strehl_blocks;
+    for (int i = lane; i < nslots; i += 32) { sr += sp[i].x; si += sp[i].y; }
+    sr = warp_sum(sr);
+    si = warp_sum(si);
+    if (lane == 0) pre[AOG_MAX_LP] = make_double2(sr, si);
+  }
   const float2* r4 = a.R4 + (size_t)b * a.Np * a.r4_parts * n;
+#pragma unroll 2
   for (int i = threadIdx.x; i < a.Np * n; i += blockDim.x) {
     const int x = i / n, v = i - x * n;
     double ex = 0.0, ey = 0.0;
@@ -465,21 +495,10 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
   }
   __syncthreads();
   if (warp != 0 || !a.compute_reward) return;
-  const int eb = b >> 7;
-  const int nslots = ((eb + 1) * a.slot_items - 1) / a.slot_ipc - (eb * a.slot_items) / a.slot_ipc + 1;
   // fibre: out = M (c e^{i beta L});  total power = c'^H G c'
   double2 c[AOG_MAX_LP];
   for (int j = 0; j < a.J; ++j) {
-    double2 cj = make_double2(0.0, 0.0);
-    if (a.coef_is_raw == 2) {
-      const double* c4 = a.coef4 + ((size_t)b * a.J + j) * 4;
-      cj = make_double2(c4[0] + c4[1], c4[2] + c4[3]);
-    } else {
-      const double2* fp = a.fib_part + (size_t)b * a.fib_slots * a.fib_stride + j;
-      for (int i = lane; i < nslots; i += 32) { cj.x += fp[i * a.fib_stride].x; cj.y += fp[i * a.fib_stride].y; }
-      cj.x = warp_sum(cj.x);
-      cj.y = warp_sum(cj.y);
-    }
+    double2 cj = pre[j];
     cj = make_double2(cj.x * a.coef_scale.x - cj.y * a.coef_scale.y, cj.x * a.coef_scale.y + cj.y * a.coef_scale.x);
     const double2 ph = a.lpphase[j];
     c[j] = make_double2(cj.x * ph.x - cj.y * ph.y, cj.x * ph.y + cj.y * ph.x);
@@ -490,11 +509,7 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
       power += a.lpgram[j * a.J + k] * (c[j].x * c[k].x + c[j].y * c[k].y);
   double reward;
   if (a.rew_type == AOG_REW_STREHL_RATIO) {
-    double sr = 0.0, si = 0.0;
-    const double2* sp = a.strehl_part + (size_t)b * a.strehl_blocks;
-    for (int i = lane; i < nslots; i += 32) { sr += sp[i].x; si += sp[i].y; }
-    sr = warp_sum(sr);
-    si = warp_sum(si);
+    const double sr = pre[AOG_MAX_LP].x, si = pre[AOG_MAX_LP].y;
     const double strehl = a.strehl_scale * (sr * sr + si * si);
     if (lane == 0 && a.strehl) a.strehl[b] = strehl;
     reward = -(100.0 - strehl);
