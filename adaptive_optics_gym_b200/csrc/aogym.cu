@@ -336,6 +336,15 @@ int aog_create(const aog_config* cfg, aog_env** out) {
   if (c.precision != AOG_PRECISION_F64) A(aog_tensor_create(env));
 #undef A
   AOG_CUDA(cudaStreamCreate(&env->own_stream));   // blocking: ordered with the default stream
+  {
+    // highest priority: its (few, compute-bound) blocks are placed as soon as an SM has room, next to the HBM-bound
+    // blocks of the kernels they overlap with
+    int lo = 0, hi = 0;
+    AOG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    AOG_CUDA(cudaStreamCreateWithPriority(&env->side_stream, cudaStreamNonBlocking, hi));
+  }
+  AOG_CUDA(cudaEventCreateWithFlags(&env->ev_sh_phase, cudaEventDisableTiming));
+  AOG_CUDA(cudaEventCreateWithFlags(&env->ev_ext_done, cudaEventDisableTiming));
   AOG_CUDA(cudaEventCreate(&env->ev0));
   AOG_CUDA(cudaEventCreate(&env->ev1));
   AOG_CUDA(cudaEventCreate(&env->evf));
@@ -365,6 +374,9 @@ void aog_destroy(aog_env* env) {
   if (env->h_act) cudaFreeHost(env->h_act);
   if (env->step_graph) cudaGraphExecDestroy(env->step_graph);
   if (env->own_stream) cudaStreamDestroy(env->own_stream);
+  if (env->side_stream) cudaStreamDestroy(env->side_stream);
+  if (env->ev_sh_phase) cudaEventDestroy(env->ev_sh_phase);
+  if (env->ev_ext_done) cudaEventDestroy(env->ev_ext_done);
   if (env->ev0) cudaEventDestroy(env->ev0);
   if (env->ev1) cudaEventDestroy(env->ev1);
   if (env->evf) cudaEventDestroy(env->evf);
@@ -729,8 +741,21 @@ int aog_step(aog_env* env, const void* actions_dev, int act_dtype, const double*
   env->cnt.timestep_render += 1;
   if (env->timing) AOG_CUDA(cudaEventRecord(env->tev[0], st));
   const int64_t ext_before = env->cnt.extrusions;
-  int rc = evolve_to(env, env->cnt.timestep, old_t, noise_dev, st);
-  if (rc) return rc;
+  int rc;
+  static const bool no_overlap = getenv("AOG_NO_OVERLAP") != nullptr;
+  if (env->sh_phase_pending && env->sh_phase_stream == st && c.velocity != 0.0 && !env->timing && !no_overlap) {
+    // SH_step's phase kernel was the last reader of the screens: extrude on the side stream, under SH_step's
+    // remaining kernels (which are still running or queued on `st`), and join before the optics
+    AOG_CUDA(cudaStreamWaitEvent(env->side_stream, env->ev_sh_phase, 0));
+    rc = evolve_to(env, env->cnt.timestep, old_t, noise_dev, env->side_stream);
+    if (rc) return rc;
+    AOG_CUDA(cudaEventRecord(env->ev_ext_done, env->side_stream));
+    AOG_CUDA(cudaStreamWaitEvent(st, env->ev_ext_done, 0));
+  } else {
+    rc = evolve_to(env, env->cnt.timestep, old_t, noise_dev, st);
+    if (rc) return rc;
+  }
+  env->sh_phase_pending = false;
   if (env->timing) {
     AOG_CUDA(cudaEventRecord(env->tev[1], st));
     env->last_extrusions = (int)(env->cnt.extrusions - ext_before);

@@ -109,6 +109,12 @@ struct aog_env {
   int32_t* phase_tiles = nullptr;   // TensorState::hwt (tiled fixed-point phase) for k_ar_step's epilogue, else null
   double phase_tiles_unit = 0.0;    // fixed-point units per half-turn (PHI_ONE)
   cudaStream_t own_stream = nullptr;
+  // configs[3]: the column extrusions of step t only wait for the PHASE kernel of SH_step t (the last reader of the
+  // screens / phase tiles), so they run on a side stream under SH_step's remaining, HBM-bound kernels
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_sh_phase = nullptr, ev_ext_done = nullptr;
+  bool sh_phase_pending = false;
+  cudaStream_t sh_phase_stream = nullptr;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evf = nullptr, evm = nullptr;   // evf: before the field kernel, evm: between the MFT stages
   bool ev_valid = false;

@@ -497,6 +497,8 @@ __global__ void __launch_bounds__(CAM_THREADS, 2) k_sh_camera_tc(const ShCamPara
           cur[m] = slv[m];
         }
       }
+      // rows / warps that only see unselected lenslets (the aperture's rim and corners) have nothing to add
+      if (!__any_sync(0xffffffffu, slv[0] >= 0 || slv[1] >= 0 || slv[2] >= 0 || slv[3] >= 0)) continue;
       if (noisy) {
         const uint4 ctr = make_uint4((uint32_t)(i * SH_NH + uu), (uint32_t)genv, (uint32_t)p.draw, 0u);
         float z[4];
@@ -751,6 +753,13 @@ int sh_tensor_optics(aog_env* env, TensorState* ts, int e0, int nB, cudaStream_t
     fp.strehl_part = env->strehl_part; fp.gfib = nullptr; fp.fib_part = nullptr; fp.err_flag = ts->err_flag;
     int rc = launch_phase<false, 1, 3>(env, ts, fp, cdiv(fp.num_items, fp.items_per_cta), st);
     if (rc) return rc;
+    // nothing after this kernel reads the screens or the phase tiles: the next aog_step may extrude concurrently
+    // (single-chunk handles; see aog_step)
+    if (nB == c.num_envs) {
+      AOG_CUDA(cudaEventRecord(env->ev_sh_phase, st));
+      env->sh_phase_pending = true;
+      env->sh_phase_stream = st;
+    }
   }
   if (env->timing) AOG_CUDA(cudaEventRecord(env->tev[3], st));
   k_sh_fold<<<dim3(SH_NKB, nB), 128, 0, st>>>(ts->phi, ts->apmask, ts->shEB_hi, ts->shEB_lo, nB);
