@@ -477,10 +477,12 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
   for (int t = warp; t < n2; t += nwarps) {
     const int v = t / n, u = t - v * n;
     double re = 0.0, im = 0.0;
-    for (int y = lane; y < a.Np; y += 32) {
-      const double2 m = a.m1o[(size_t)v * a.Np + y], e = fin_R[y * n + u];
-      re += m.x * e.x - m.y * e.y;
-      im += m.x * e.y + m.y * e.x;
+    const double2* mp = a.m1o + (size_t)v * a.Np + lane;
+    const double2* ep = fin_R + lane * n + u;
+    for (int y = lane; y < a.Np; y += 32, mp += 32, ep += 32 * n) {
+      const double2 m = *mp, e = *ep;
+      re = fma(m.x, e.x, fma(-m.y, e.y, re));
+      im = fma(m.x, e.y, fma(m.y, e.x, im));
     }
     re = warp_sum(re);
     im = warp_sum(im);

@@ -41,7 +41,10 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if src.endswith('.csv'):       # already exported on the GPU box: ncu -i X.ncu-rep --page raw --csv > X.raw.csv
+        out = open(src).read()
+    else:
+        out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(dst, 'w') as f:
