@@ -135,3 +135,22 @@ def test_vec_rollout_collector_layout_matches_reference_rollout():
     assert col.num_episodes == 6
     with pytest.raises(ValueError):
         VecRolloutCollector(env, None)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm): one JSON line with the base contract's keys, timed on
+    the CPU oracle with one single-thread env per worker process (2 here), no GPU and no library needed."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AOG_REF_THREADS='2')
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '1'], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'env-steps/sec' and line['unit'] == 'env-steps/s'
+    assert line['higher_is_better'] is True and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
+    assert line['cpu_baseline']['cores'] == 2 and line['e2e']['h2d_bytes_per_step'] == 0
+    assert 'quasi_static' in line['config']['workload']
