@@ -544,6 +544,214 @@ static __global__ void __launch_bounds__(128) k_finalize_tc(FinalizeArgs a) {
   if (a.power) a.power[b] = power;
 }
 
+// k_finalize_tcw<N, PARTS>: the same epilogue with ONE WARP per env and no block-level barrier (round 2; the
+// block-per-env k_finalize_tc above takes 122 us for the 5x5 detector at 4096 envs = 21 % of a configs[1] step, and a
+// first warp-per-env form with plain loads 106 us: the kernel is bound by the LATENCY of fetching the env's 28.8 KB of
+// column partial sums, not by its arithmetic).  So the partial sums stream through shared memory: every warp keeps a
+// double-buffered ring of tiles (8 XS pupil columns = ~6 KB each, 16-byte cp.async, one commit group per tile) in
+// flight ahead of its arithmetic -- 16 warps per SM x 6-12 KB outstanding.
+// Lane (xs, b) = (lane / N, lane % N) owns column b of the column sums and the pupil columns x = xs, xs + XS, ...
+// (XS = 32 / N): per x it adds the PARTS partial sums of R[x][b] in FP64 and multiplies them with the N table
+// entries m[a][x] (broadcast loads), i.e. N complex accumulators per lane instead of N^2 -- no lane computes anything
+// twice.  The XS partial results per detector pixel meet in shared memory, summed in a fixed order by the lane that owns
+// the pixel.  Slot sums (fibre projections, Strehl) are loaded before the contraction and reduced after it.
+// Summation order depends on the env's data only: a batched env equals its single-env twin bit for bit.
+constexpr int FIN_WARPS = 8;
+template <int N, int PARTS> struct FinCfg {
+  static constexpr int XS = 32 / N, LANES = XS * N, N2 = N * N, N2P = N2 < 7 ? 7 : N2;
+  static constexpr int ITER = N >= 6 ? 4 : 8, TILE_X = XS * ITER, ROW = PARTS * N /* float2 per pupil column */;
+  static constexpr int TAB_MAX = N * 256 * 16;           // the [N][Np] table, Np <= 256 on the tensor / fused paths
+  static constexpr int TILE_BYTES = TILE_X * ROW * 8, WARP_BYTES = 2 * TILE_BYTES, SMEM = FIN_WARPS * WARP_BYTES;
+  static constexpr int RED_LD = 33;
+  static_assert(TILE_BYTES % 16 == 0, "tile size");
+  static_assert((2 * N * RED_LD + 2 * N2P) * 8 <= WARP_BYTES, "the reduction scratch aliases the tile ring");
+};
+template <int N, int PARTS>
+static __global__ void __launch_bounds__(FIN_WARPS * 32, 2) k_finalize_tcw(FinalizeArgs a, int num_envs) {
+  using Cfg = FinCfg<N, PARTS>;
+  constexpr int XS = Cfg::XS, LANES = Cfg::LANES, N2 = Cfg::N2, ITER = Cfg::ITER, TILE_X = Cfg::TILE_X, ROW = Cfg::ROW;
+  extern __shared__ __align__(16) unsigned char fin_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * FIN_WARPS + warp;
+  unsigned char* wbase = fin_smem + warp * Cfg::WARP_BYTES;
+  double2* tab_s = reinterpret_cast<double2*>(fin_smem + FIN_WARPS * Cfg::WARP_BYTES);   // [N][Np] second obs-arm table
+  constexpr unsigned FULL = 0xffffffffu;
+  const int ntiles = (a.Np + TILE_X - 1) / TILE_X;
+  const float2* r4 = a.R4 + (size_t)b * a.Np * ROW;
+  auto issue = [&](int t, int buf) {
+    const int cols = min(TILE_X, a.Np - t * TILE_X);
+    const int nchunks = cols * ROW / 2;                                // 16-byte pieces (cols is even)
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(r4 + (size_t)t * TILE_X * ROW);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(wbase + buf * Cfg::TILE_BYTES);
+    for (int c = lane; c < nchunks; c += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + c * 16), "l"(src + (size_t)c * 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (b < num_envs) {
+    issue(0, 0);
+    if (ntiles > 1) issue(1, 1);
+  }
+  // the table is read N times per (pupil column, lane): from global memory those loads were the kernel's stall
+  // (L1 hit rate 39 % next to 184 KB of shared memory; ncu: long scoreboard 6 of 14 warp-cycles per issue)
+  for (int i = threadIdx.x; i < N * a.Np; i += FIN_WARPS * 32) tab_s[i] = __ldg(a.m1o + i);
+  __syncthreads();
+  if (b >= num_envs) return;                            // warps are independent from here on
+  if (a.act) {
+    int bad = 0;
+    for (int k = lane; k < a.K; k += 32) bad |= isfinite(a.act[(size_t)b * a.K + k]) ? 0 : 1;   // inf: exp(i inf) = NaN too
+    if (__any_sync(FULL, bad)) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int t = lane; t < N2; t += 32) {
+        if (a.obs64) a.obs64[(size_t)b * N2 + t] = qnan;
+        if (a.obs16) a.obs16[(size_t)b * N2 + t] = 0x7e00;
+      }
+      if (lane == 0 && a.compute_reward) {
+        if (a.reward) a.reward[b] = qnan;
+        if (a.power) a.power[b] = qnan;
+        if (a.strehl) a.strehl[b] = qnan;
+        if (a.ssim) a.ssim[b] = qnan;
+      }
+      return;
+    }
+  }
+  // per-lane partial slot sums (reduced after the contraction)
+  double2 cj[AOG_MAX_LP];
+  double2 sp = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int j = 0; j < AOG_MAX_LP; ++j) cj[j] = make_double2(0.0, 0.0);
+  if (a.compute_reward) {
+    const int eb = b >> 7;
+    const int nslots = ((eb + 1) * a.slot_items - 1) / a.slot_ipc - (eb * a.slot_items) / a.slot_ipc + 1;
+    if (a.coef_is_raw == 2) {
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < AOG_MAX_LP; ++j)
+          if (j < a.J) {
+            const double* c4 = a.coef4 + ((size_t)b * a.J + j) * 4;
+            cj[j] = make_double2(c4[0] + c4[1], c4[2] + c4[3]);
+          }
+      }
+    } else {
+      const double2* fp = a.fib_part + (size_t)b * a.fib_slots * a.fib_stride;
+      for (int i = lane; i < nslots; i += 32) {
+#pragma unroll
+        for (int j = 0; j < AOG_MAX_LP; ++j)
+          if (j < a.J) { const double2 v = fp[i * a.fib_stride + j]; cj[j].x += v.x; cj[j].y += v.y; }
+      }
+    }
+    if (a.rew_type == AOG_REW_STREHL_RATIO) {
+      const double2* spp = a.strehl_part + (size_t)b * a.strehl_blocks;
+      for (int i = lane; i < nslots; i += 32) { const double2 v = spp[i]; sp.x += v.x; sp.y += v.y; }
+    }
+  }
+  // contraction over the pupil columns
+  const int xs = lane / N, bb = lane - xs * N;
+  double are[N], aim[N];
+#pragma unroll
+  for (int v = 0; v < N; ++v) are[v] = aim[v] = 0.0;
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else                asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const float2* tile = reinterpret_cast<const float2*>(wbase + (t & 1) * Cfg::TILE_BYTES);
+    if (lane < LANES) {
+#pragma unroll
+      for (int i = 0; i < ITER; ++i) {
+        const int xl = xs + XS * i, x = t * TILE_X + xl;
+        if (x < a.Np) {
+          double ex = 0.0, ey = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < PARTS; ++qq) {
+            const float2 t4 = tile[(xl * PARTS + qq) * N + bb];
+            ex += (double)t4.x;
+            ey += (double)t4.y;
+          }
+#pragma unroll
+          for (int v = 0; v < N; ++v) {
+            const double2 m = tab_s[v * a.Np + x];
+            are[v] = fma(m.x, ex, fma(-m.y, ey, are[v]));
+            aim[v] = fma(m.x, ey, fma(m.y, ex, aim[v]));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (t + 2 < ntiles) issue(t + 2, t & 1);
+  }
+  double* red = reinterpret_cast<double*>(wbase);               // [2 N][RED_LD]; the tile ring is drained
+  double* obs_s = red + 2 * N * Cfg::RED_LD;
+  double* win_s = obs_s + Cfg::N2P;
+#pragma unroll
+  for (int v = 0; v < N; ++v) { red[(2 * v) * Cfg::RED_LD + lane] = are[v]; red[(2 * v + 1) * Cfg::RED_LD + lane] = aim[v]; }
+  __syncwarp();
+  for (int t = lane; t < N2; t += 32) {
+    const int v = t / N, u = t - v * N;
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int s = 0; s < XS; ++s) { re += red[(2 * v) * Cfg::RED_LD + s * N + u]; im += red[(2 * v + 1) * Cfg::RED_LD + s * N + u]; }
+    const double fr = re * a.norm.x - im * a.norm.y, fi = re * a.norm.y + im * a.norm.x;
+    const double pw = (fr * fr + fi * fi) * a.obs_weight;
+    const int to = a.transpose_out ? (u * N + v) : t;
+    obs_s[to] = pw;
+    if (a.obs64) a.obs64[(size_t)b * N2 + to] = pw;
+    if (a.obs16) a.obs16[(size_t)b * N2 + to] = __half_as_ushort(__double2half(pw));
+  }
+  __syncwarp();
+  if (!a.compute_reward) return;
+  // fibre: out = M (c e^{i beta L});  total power = c'^H G c'
+  double2 c[AOG_MAX_LP];
+#pragma unroll
+  for (int j = 0; j < AOG_MAX_LP; ++j) {
+    if (j < a.J) {
+      double2 s = make_double2(warp_sum(cj[j].x), warp_sum(cj[j].y));
+      s = make_double2(s.x * a.coef_scale.x - s.y * a.coef_scale.y, s.x * a.coef_scale.y + s.y * a.coef_scale.x);
+      const double2 ph = a.lpphase[j];
+      c[j] = make_double2(s.x * ph.x - s.y * ph.y, s.x * ph.y + s.y * ph.x);
+    } else {
+      c[j] = make_double2(0.0, 0.0);
+    }
+  }
+  double power = 0.0;
+#pragma unroll
+  for (int j = 0; j < AOG_MAX_LP; ++j)
+#pragma unroll
+    for (int k = 0; k < AOG_MAX_LP; ++k)
+      if (j < a.J && k < a.J) power += a.lpgram[j * a.J + k] * (c[j].x * c[k].x + c[j].y * c[k].y);
+  double reward;
+  if (a.rew_type == AOG_REW_STREHL_RATIO) {
+    const double sr = warp_sum(sp.x), si = warp_sum(sp.y);
+    const double strehl = a.strehl_scale * (sr * sr + si * si);
+    if (lane == 0 && a.strehl) a.strehl[b] = strehl;
+    reward = -(100.0 - strehl);
+  } else {
+    // skimage SSIM on 1-D data (ssim_1d above), one window per lane, summed in window order
+    const double peak = a.ssim_peak, C1 = (0.01 * peak) * (0.01 * peak), C2 = (0.03 * peak) * (0.03 * peak);
+    const double cov_norm = 7.0 / 6.0;
+    constexpr int ref_idx = N2 / 2;
+    for (int cw = 3 + lane; cw < N2 - 3; cw += 32) {
+      double sx = 0, sxx = 0, sy = 0, syy = 0, sxy = 0;
+      for (int i = cw - 3; i <= cw + 3; ++i) {
+        const double x = obs_s[i], r = (i == ref_idx) ? peak : 0.0;
+        sx += x; sxx += x * x; sy += r; syy += r * r; sxy += x * r;
+      }
+      const double ux = sx / 7, uy = sy / 7, uxx = sxx / 7, uyy = syy / 7, uxy = sxy / 7;
+      const double vx = cov_norm * (uxx - ux * ux), vy = cov_norm * (uyy - uy * uy), vxy = cov_norm * (uxy - ux * uy);
+      win_s[cw] = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+    }
+    __syncwarp();
+    double tot = 0.0;
+    for (int cw = 3; cw < N2 - 3; ++cw) tot += win_s[cw];      // same summation order as ssim_1d
+    const double sv = tot / (double)(N2 - 6);
+    if (lane == 0 && a.ssim) a.ssim[b] = sv;
+    reward = 0.8 * power + (1.0 - 0.8) * sv;
+  }
+  if (lane != 0) return;
+  if (a.has_thr && reward < a.thr) reward = -1.0;
+  if (a.reward) a.reward[b] = reward;
+  if (a.power) a.power[b] = power;
+}
+
 // --------------------------------------------------------------------------------------
 // Autoregressive column extrusion (hcipy InfiniteAtmosphericLayer._extrude; AO_env.py:125).
 // gather: Z[b] = [ screen[stencil] (on the 180-degree rotated screen when moving +x) ,

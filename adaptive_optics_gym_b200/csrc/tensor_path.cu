@@ -2107,6 +2107,22 @@ int launch_phase_n(aog_env* env, TensorState* ts, const FieldParams& p, int n, i
   }
   AOG_FAIL(AOG_ERR_UNSUPPORTED, "obs_dim");
 }
+// k_finalize_tcw<n, FK_PARTS>: one warp per env, dynamic shared memory above 48 KB (opt-in once per device)
+template <int N>
+cudaError_t launch_finalize(int device, const FinalizeArgs& a, int nB, cudaStream_t st) {
+  using Cfg = FinCfg<N, FK_PARTS>;
+  static std::atomic<bool> configured_on[64];
+  std::atomic<bool>& configured = configured_on[device & 63];
+  if (!configured.load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(k_finalize_tcw<N, FK_PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               Cfg::SMEM + Cfg::TAB_MAX);
+    if (e != cudaSuccess) return e;
+    configured.store(true, std::memory_order_release);
+  }
+  if (a.Np > 256) return cudaErrorInvalidValue;
+  k_finalize_tcw<N, FK_PARTS><<<cdiv(nB, FIN_WARPS), FIN_WARPS * 32, Cfg::SMEM + N * a.Np * 16, st>>>(a, nB);
+  return cudaSuccess;
+}
 }  // namespace
 
 int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_outputs& out, cudaStream_t st) {
@@ -2215,7 +2231,18 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
     a.power = out.power ? out.power + e0 : nullptr;
     a.strehl = out.strehl ? out.strehl + e0 : nullptr;
     a.ssim = out.ssim ? out.ssim + e0 : nullptr;
-    k_finalize_tc<<<nB, 128, (size_t)Np * n * sizeof(double2), st>>>(a);
+    static const bool fin_block = getenv("AOG_FINALIZE_BLOCK") != nullptr;     // A/B switch: the block-per-env form
+    if (fin_block || n > 8) k_finalize_tc<<<nB, 128, (size_t)Np * n * sizeof(double2), st>>>(a);
+    else switch (n) {
+      case 1: AOG_CUDA(launch_finalize<1>(c.device, a, nB, st)); break;
+      case 2: AOG_CUDA(launch_finalize<2>(c.device, a, nB, st)); break;
+      case 3: AOG_CUDA(launch_finalize<3>(c.device, a, nB, st)); break;
+      case 4: AOG_CUDA(launch_finalize<4>(c.device, a, nB, st)); break;
+      case 5: AOG_CUDA(launch_finalize<5>(c.device, a, nB, st)); break;
+      case 6: AOG_CUDA(launch_finalize<6>(c.device, a, nB, st)); break;
+      case 7: AOG_CUDA(launch_finalize<7>(c.device, a, nB, st)); break;
+      default: AOG_CUDA(launch_finalize<8>(c.device, a, nB, st)); break;
+    }
     AOG_LAUNCH_CHECK();
   }
   return AOG_OK;
