@@ -55,7 +55,8 @@ int dmma_configure(aog_env* env) {
   static std::atomic<bool> done_on[64];    // function attributes are per device: one flag per device ordinal
   std::atomic<bool>& done = done_on[env->cfg.device & 63];
   if (done.load(std::memory_order_acquire)) return AOG_OK;
-  AOG_CUDA(cudaFuncSetAttribute(k_ar_step, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM));
+  AOG_CUDA(cudaFuncSetAttribute(k_ar_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM));
+  AOG_CUDA(cudaFuncSetAttribute(k_ar_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM + 4096 * 4));
   AOG_CUDA(cudaFuncSetAttribute(k_dgemm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
   done.store(true, std::memory_order_release);
   return AOG_OK;
@@ -88,8 +89,8 @@ int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long
     // GEMM with the scatter into the ring slot (and the phase-tile refresh of the tensor / fused paths) in its epilogue
     dim3 g2(cdiv(Np, 64), cdiv(nB, AR_TM));
     { int rc = dmma_configure(env); if (rc) return rc; }
-    k_ar_step<<<g2, AR_THREADS, AR_SMEM, st>>>(env->arZ, env->t_arW, env->screens, env->phase_tiles, nB, Np, Ns + Np, env->P, e0, phys,
-                                  flipped, 1.0 / (c.wavelength_wfs * 3.14159265358979323846), env->phase_tiles_unit);
+    k_ar_step<false><<<g2, AR_THREADS, AR_SMEM, st>>>(env->arZ, env->t_arW, env->screens, env->phase_tiles, nB, Np, Ns + Np, env->P, e0, phys,
+                                  flipped, 1.0 / (c.wavelength_wfs * 3.14159265358979323846), env->phase_tiles_unit, ArDirect{});
     AOG_LAUNCH_CHECK();
   }
   if (getenv("AOG_AR_SPLIT") != nullptr && c.precision != AOG_PRECISION_F64) {
@@ -101,11 +102,56 @@ int extrude_once(aog_env* env, bool positive, const double* noise_dev, long long
   return AOG_OK;
 }
 
+// ---- all the column extrusions of one step, the stencil read in place (k_ar_step<DIRECT>) --------------------
+// Envs are independent, so the loop runs chunk by chunk: one k_ar_noise launch makes the scaled normals of the chunk's
+// n extrusions, then n GEMM launches (no gather pass, no gathered copy).  Same draws and the same sums as extrude_once.
+int extrude_direct(aog_env* env, bool positive, int n, const double* noise_dev, cudaStream_t st) {
+  const aog_config& c = env->cfg;
+  const int Np = c.num_pupil_pixels, Ns = c.num_stencil, B = c.num_envs;
+  const int flipped = positive ? 1 : 0;
+  { int rc = dmma_configure(env); if (rc) return rc; }
+  if (n > env->arNZ_cap) {
+    int rc = dev_alloc(env, &env->arNZ, (size_t)n * env->chunk * Np);
+    if (rc) return rc;
+    env->arNZ_cap = n;
+  }
+  int org = (int)env->cnt.column_origin;
+  for (int e0 = 0; e0 < B; e0 += env->chunk) {
+    const int nB = std::min(env->chunk, B - e0);
+    dim3 gn(cdiv(Np / 2, 128), nB, n);
+    k_ar_noise<<<gn, 128, 0, st>>>(noise_dev, env->arNZ, Np, nB, n, e0, c.sqrt_cn2, (long long)n * Np, c.seed,
+                                   (unsigned long long)c.env_id_base, (unsigned long long)env->cnt.extrusions);
+    AOG_LAUNCH_CHECK();
+    org = (int)env->cnt.column_origin;
+    for (int i = 0; i < n; ++i) {
+      const int phys = positive ? org : (org - 1 + Np) % Np;
+      ArDirect dr{};
+      dr.nz = env->arNZ + (size_t)i * nB * Np;
+      dr.tail = env->t_ar_tail;
+      // stencil column x (logical, on the rotated screen when flipped) -> physical column
+      dr.pc0 = ((flipped ? Np - 1 : 0) + org) % Np;
+      dr.pc1 = ((flipped ? Np - 2 : 1) + org) % Np;
+      dr.org = org; dr.Ns = Ns;
+      dim3 g2(cdiv(Np, 64), cdiv(nB, AR_TM));
+      k_ar_step<true><<<g2, AR_THREADS, AR_SMEM + (Ns - 2 * Np) * (int)sizeof(int), st>>>(nullptr, flipped ? env->t_arW_rev : env->t_arW, env->screens, env->phase_tiles,
+                                                      nB, Np, Ns + Np, env->P, e0, phys, flipped,
+                                                      1.0 / (c.wavelength_wfs * 3.14159265358979323846), env->phase_tiles_unit, dr);
+      AOG_LAUNCH_CHECK();
+      org = positive ? (org + 1) % Np : phys;
+    }
+  }
+  env->cnt.column_origin = org;
+  env->cnt.extrusions += n;
+  return AOG_OK;
+}
+
 int evolve_to(aog_env* env, int64_t new_timestep, int64_t old_timestep, const double* noise_dev, cudaStream_t st) {
   if (env->cfg.velocity == 0.0) return AOG_OK;
   const int64_t d = center_px(env, new_timestep) - center_px(env, old_timestep);
   const int Np = env->cfg.num_pupil_pixels;
   const int64_t n = d < 0 ? -d : d;
+  if (n == 0) return AOG_OK;
+  if (env->ar_direct && getenv("AOG_AR_SPLIT") == nullptr && n <= 4096) return extrude_direct(env, d > 0, (int)n, noise_dev, st);
   for (int64_t i = 0; i < n; ++i) {
     const double* nz = noise_dev ? noise_dev + (size_t)i * Np : nullptr;
     int rc = extrude_once(env, d > 0, nz, (long long)n * Np, st);
@@ -302,6 +348,7 @@ int aog_create(const aog_config* cfg, aog_env** out) {
     A(dev_alloc(env, &env->t_arA, (size_t)Np * c.num_stencil));
     A(dev_alloc(env, &env->t_arB, (size_t)Np * Np));
     A(dev_alloc(env, &env->t_arW, (size_t)(c.num_stencil + Np) * Np));
+    A(dev_alloc(env, &env->t_arW_rev, (size_t)(c.num_stencil + Np) * Np));
   }
   if (c.num_screen_fine > 0) {
     const size_t N2 = c.num_screen_fine;
@@ -360,7 +407,7 @@ void aog_destroy(aog_env* env) {
   aog_tensor_destroy(env);
   void* ptrs[] = {env->t_aperture, env->t_modes, env->t_gram, env->t_m1f, env->t_m2f, env->t_m1o, env->t_m2o,
                   env->t_lpw, env->t_lpphase, env->t_lpgram, env->t_stencil, env->t_stencil_perm, env->t_arA, env->t_arB, env->t_arW,
-                  env->t_scrC1, env->t_scrW1, env->t_scrW1T, env->t_scrC2, env->t_scrW2, env->t_scrW2T,
+                  env->t_arW_rev, env->t_ar_tail, env->arNZ, env->t_scrC1, env->t_scrW1, env->t_scrW1T, env->t_scrC2, env->t_scrW2, env->t_scrW2T,
                   env->screens, env->act, env->bufA, env->bufB, env->bufC, env->bufR, env->coef,
                   env->strehl_part, env->arZ, env->arNew, env->act_in, env->noise_in, env->o_pack,
                   env->t_sh_mla, env->t_sh_C, env->t_sh_CT,
@@ -443,6 +490,21 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
     if (rc) return rc;
     AOG_CUDA(cudaMemcpy(env->t_stencil_perm, perm.data(), Ns * sizeof(int), cudaMemcpyHostToDevice));
     AOG_CUDA(cudaMemcpy(dst, sorted.data(), Ns * sizeof(int), cudaMemcpyHostToDevice));
+    // hcipy's stencil (two full columns + one pixel per row further back) lets k_ar_step read the screens in place
+    bool direct = Np % 2 == 0 && Ns > 2 * Np && Ns - 2 * Np <= 4096 && getenv("AOG_AR_GATHER") == nullptr;
+    for (size_t k = 0; direct && k < 2 * Np; ++k) direct = sorted[k] == (int)((k % Np) * Np + k / Np);
+    std::vector<int> tail(Ns > 2 * Np ? Ns - 2 * Np : 0);
+    for (size_t k = 2 * Np; direct && k < Ns; ++k) {
+      const int x = sorted[k] % (int)Np, y = sorted[k] / (int)Np;
+      direct = x >= 2 && x <= (int)Np - 2;            // never the column an extrusion overwrites (logical Np - 1)
+      tail[k - 2 * Np] = x | (y << 16);
+    }
+    env->ar_direct = direct;
+    if (direct) {
+      rc = dev_alloc(env, &env->t_ar_tail, tail.size());
+      if (rc) return rc;
+      AOG_CUDA(cudaMemcpy(env->t_ar_tail, tail.data(), tail.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
   } else {
     AOG_CUDA(cudaMemcpy(dst, host, want * esz, cudaMemcpyHostToDevice));
   }
@@ -451,7 +513,9 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
   if ((which == AOG_TABLE_AR_A || which == AOG_TABLE_AR_B || which == AOG_TABLE_AR_STENCIL) && env->have[AOG_TABLE_AR_A] &&
       env->have[AOG_TABLE_AR_B] && env->have[AOG_TABLE_AR_STENCIL]) {
     const int tot = (int)((Ns + Np) * Np);
-    k_build_arW<<<cdiv(tot, 256), 256>>>(env->t_arA, env->t_arB, env->t_stencil_perm, env->t_arW, (int)Np, (int)Ns);
+    k_build_arW<<<cdiv(tot, 256), 256>>>(env->t_arA, env->t_arB, env->t_stencil_perm, env->t_arW, (int)Np, (int)Ns, 0);
+    AOG_LAUNCH_CHECK();
+    k_build_arW<<<cdiv(tot, 256), 256>>>(env->t_arA, env->t_arB, env->t_stencil_perm, env->t_arW_rev, (int)Np, (int)Ns, 1);
     AOG_LAUNCH_CHECK();
   }
   if (which == AOG_TABLE_SCR_W1) {

@@ -31,6 +31,9 @@ struct aog_env {
   double* t_arA = nullptr;         // [Np][Ns] as uploaded
   double* t_arB = nullptr;         // [Np][Np] as uploaded
   double* t_arW = nullptr;         // [(Ns+Np)][Np] = [A^T ; B^T]  (GEMM operand)
+  double* t_arW_rev = nullptr;     // the same with the rows of the two full stencil columns reversed (k_ar_step<DIRECT>, +x)
+  int* t_ar_tail = nullptr;        // [Ns - 2 Np] (x | y << 16) of the stencil's tail pixels, gather order
+  bool ar_direct = false;          // the stencil is [column 0 | column 1 | tail]: k_ar_step reads the screens in place
   double* t_scrC1 = nullptr;       // [Np][Np]
   double2* t_scrW1 = nullptr;      // [Np][Np]
   double2* t_scrW1T = nullptr;     // transpose
@@ -85,6 +88,8 @@ struct aog_env {
   int strehl_blocks = 0;
   double* arZ = nullptr;           // [chunk][Ns+Np]
   double* arNew = nullptr;         // [chunk][Np]
+  double* arNZ = nullptr;          // [arNZ_cap extrusions][chunk][Np] scaled normals of one step (k_ar_noise)
+  int arNZ_cap = 0;
   void* act_in = nullptr;          // [B][K] staging of raw actions (f64-sized)
   double* noise_in = nullptr;      // staging for injected noise
   size_t noise_in_cap = 0;

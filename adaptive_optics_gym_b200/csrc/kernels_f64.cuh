@@ -789,6 +789,29 @@ static __global__ void k_ar_gather(const double* __restrict__ screens, const int
   Z[(size_t)b * (Ns + Np) + j] = v;
 }
 
+// sqrt(Cn2) xi for ALL the extrusions of a step in one launch (the DIRECT form of k_ar_step reads it in place):
+// NZ[(e nB + b) Np + i], e < next;  the same Philox draws as k_ar_gather (extrusion e uses draw index draw0 + e), one
+// block per pair of normals, or the injected normals noise[(env0 + b) noise_stride + e Np + i].
+static __global__ void k_ar_noise(const double* __restrict__ noise, double* __restrict__ NZ, int Np, int nB, int next,
+                                  int env0, double sqrt_cn2, long long noise_stride, unsigned long long seed,
+                                  unsigned long long env_id_base, unsigned long long draw0) {
+  const int b = blockIdx.y, e = blockIdx.z;
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= Np) return;
+  double2 z;
+  if (noise) {
+    const double* src = noise + (size_t)(env0 + b) * noise_stride + (size_t)e * Np + i;
+    z = make_double2(src[0], i + 1 < Np ? src[1] : 0.0);
+  } else {
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, env_id_base + env0 + b, ((draw0 + e) * (unsigned long long)Np + (unsigned long long)i) * 4ull, &st);
+    z = curand_normal2_double(&st);
+  }
+  double* dst = NZ + ((size_t)e * nB + b) * Np + i;
+  dst[0] = sqrt_cn2 * z.x;
+  if (i + 1 < Np) dst[1] = sqrt_cn2 * z.y;
+}
+
 // new column = Z . W (hcipy _extrude: A z + B xi for every env) on the FP64 tensor cores, with the scatter into the
 // ring-buffered screens -- and, for the tensor / fused paths, the refresh of that column's fixed-point phase tiles --
 // in the epilogue.  mma.sync.m8n8k4.f64 (DMMA) sustains 36 TFLOP/s on B200 with 4-8 warps per SM where scalar DFMA
@@ -933,23 +956,83 @@ k_dgemm_mma(const double* __restrict__ A, const double* __restrict__ B, double* 
 // are 37 x 4 = 148 such tiles -- one per SM of a B200 in a single wave (the shared 128 x 64 tile gave 128 blocks).
 constexpr int AR_TM = 112, AR_THREADS = 224, AR_LDA = 8 + 4, AR_A_STAGE = AR_TM * AR_LDA, AR_B_STAGE = 8 * DMMA_LDB;
 constexpr int AR_SMEM = DMMA_STAGES * (AR_A_STAGE + AR_B_STAGE) * (int)sizeof(double);
+// DIRECT (round 2): the A operand is read where it lives instead of from a gathered copy Z (k_ar_gather: 24 us per
+// extrusion, launch-shape bound).  In gather order the stencil is [column 0 | column 1 | one pixel per row further
+// back | noise]: the two newest columns are contiguous runs of the column-major screens (16-byte cp.async, in MEMORY
+// order -- for the rotated screen of a +x extrusion that is the reversed row order, so W has a second copy with
+// those rows reversed), the Np tail pixels are single doubles (8-byte cp.async at the geometric offsets), and the
+// scaled normals of ALL extrusions of a step come from one k_ar_noise launch.  The column this launch overwrites is
+// the oldest one (logical column Np - 1), which the upload code checks is not in the stencil.
+struct ArDirect {
+  const double* nz;      // [nB][Np] sqrt(Cn2) xi of this extrusion (chunk-relative rows)
+  const int* tail;       // [Ns - 2 Np] (x | y << 16) logical coordinates of the tail pixels, gather order
+  int pc0, pc1;          // physical columns of stencil columns 0 and 1
+  int org, Ns;
+};
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+template <bool DIRECT>
 static __global__ void __launch_bounds__(AR_THREADS)
 k_ar_step(const double* __restrict__ Z, const double* __restrict__ W, double* __restrict__ screens,
           int32_t* __restrict__ tiles, int nB, int Np, int Kd, int P, int env0, int phys_col, int flipped,
-          double inv_w, double phi_one) {
+          double inv_w, double phi_one, ArDirect dr) {
   extern __shared__ __align__(16) double dmma_smem[];
   double* As = dmma_smem;                                      // [stage][112][AR_LDA]
   double* Bs = dmma_smem + DMMA_STAGES * AR_A_STAGE;           // [stage][8][DMMA_LDB]
   const int m0 = blockIdx.y * AR_TM, n0 = blockIdx.x * 64;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, gid = lane >> 2, tig = lane & 3;
   const int wm = warp * 16;
+  // DIRECT loader: this thread's two A rows (t / 4 and t / 4 + 56) and its k pair inside a K step
+  const int lrow = t >> 2, lkc = (t & 3) * 2;
+  const bool ok0 = m0 + lrow < nB, ok1 = m0 + lrow + AR_THREADS / 4 < nB;
+  const double* scr0 = screens + (size_t)(env0 + (ok0 ? m0 + lrow : 0)) * P;
+  const double* scr1 = screens + (size_t)(env0 + (ok1 ? m0 + lrow + AR_THREADS / 4 : 0)) * P;
+  const double* nz0 = DIRECT ? dr.nz + (size_t)(ok0 ? m0 + lrow : 0) * Np : nullptr;
+  const double* nz1 = DIRECT ? dr.nz + (size_t)(ok1 ? m0 + lrow + AR_THREADS / 4 : 0) * Np : nullptr;
+  int* tail_off = reinterpret_cast<int*>(dmma_smem + DMMA_STAGES * (AR_A_STAGE + AR_B_STAGE));   // [Ns - 2 Np] offsets into an env's screen
+  if constexpr (DIRECT) {
+    for (int j = t; j < dr.Ns - 2 * Np; j += AR_THREADS) {
+      const int xy = __ldg(dr.tail + j);
+      int x = xy & 0xffff, y = xy >> 16;
+      if (flipped) { x = Np - 1 - x; y = Np - 1 - y; }
+      x += dr.org;
+      if (x >= Np) x -= Np;
+      tail_off[j] = x * Np + y;
+    }
+    __syncthreads();
+  }
   auto issue = [&](int ks) {                                   // K step ks (8 deep) -> ring slot ks % DMMA_STAGES
     const int k0 = ks * 8, st = ks % DMMA_STAGES;
+    if constexpr (DIRECT) {
+      const int k = k0 + lkc;
+      double* d0 = As + st * AR_A_STAGE + lrow * AR_LDA + lkc;
+      double* d1 = d0 + (AR_THREADS / 4) * AR_LDA;
+      const bool kok = k < Kd;
+      if (k < 2 * Np) {                                        // the two newest columns, memory order
+        const int off = k < Np ? dr.pc0 * Np + k : dr.pc1 * Np + (k - Np);
+        cp_async16(d0, scr0 + off, ok0);
+        cp_async16(d1, scr1 + off, ok1);
+      } else if (k < dr.Ns) {                                  // tail pixels: one double each
+        const int2 off = *reinterpret_cast<const int2*>(tail_off + (k - 2 * Np));
+        cp_async8(d0, scr0 + off.x, ok0);
+        cp_async8(d0 + 1, scr0 + off.y, ok0);
+        cp_async8(d1, scr1 + off.x, ok1);
+        cp_async8(d1 + 1, scr1 + off.y, ok1);
+      } else {                                                 // noise
+        const int off = kok ? k - dr.Ns : 0;
+        cp_async16(d0, nz0 + off, ok0 && kok);
+        cp_async16(d1, nz1 + off, ok1 && kok);
+      }
+    } else {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {                              // A: 112 rows x 4 chunks of 2 doubles
       const int c = t + AR_THREADS * i, row = c >> 2, kc = (c & 3) * 2;
       const bool ok = m0 + row < nB && k0 + kc < Kd;
       cp_async16(As + st * AR_A_STAGE + row * AR_LDA + kc, Z + (size_t)(ok ? m0 + row : 0) * Kd + (ok ? k0 + kc : 0), ok);
+    }
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {                              // B: 8 rows x 32 chunks of 2 doubles
@@ -1333,12 +1416,15 @@ static __global__ void k_transpose_z(const double2* __restrict__ in, double2* __
 }
 
 static __global__ void k_build_arW(const double* __restrict__ A, const double* __restrict__ Bm, const int* __restrict__ perm,
-                            double* __restrict__ W, int Np, int Ns) {
+                            double* __restrict__ W, int Np, int Ns, int reverse_cols) {
   // W[j][y] = A[y][perm[j]] (j < Ns: stencil point j of the gather order);  W[Ns + j][y] = B[y][j]
+  // reverse_cols: the rows of the two full stencil columns in reversed order (k_ar_step<DIRECT> on the rotated screen)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (Ns + Np) * Np) return;
   int j = i / Np, y = i - j * Np;
-  W[i] = (j < Ns) ? A[(size_t)y * Ns + perm[j]] : Bm[(size_t)y * Np + (j - Ns)];
+  int js = j;
+  if (reverse_cols && j < 2 * Np) js = (j / Np) * Np + (Np - 1 - j % Np);
+  W[i] = (j < Ns) ? A[(size_t)y * Ns + perm[js]] : Bm[(size_t)y * Np + (j - Ns)];
 }
 
 static __global__ void k_focal_power(const double2* __restrict__ F, double* __restrict__ out, int n, double2 norm, double w) {

@@ -861,3 +861,33 @@ def test_other_grid_sizes_fused_against_oracle(Np, Nf, obs_dim, act_type, K, rew
         assert vr[0].item() == r and vinfo['power'][0].item() == info['power']
         assert np.array_equal(vo[0].cpu().numpy().view(np.uint16), o.view(np.uint16))
     env.close(), vec.close()
+
+
+@pytest.mark.parametrize('vel', [20, -20])
+def test_direct_extrusion_equals_gathered_form(vel, monkeypatch):
+    """k_ar_step<DIRECT> (stencil read in place, one k_ar_noise launch per step) against the gather + GEMM form it
+    replaces (AOG_AR_GATHER=1): same Philox draws, same products; only the order of the sum over the stencil differs
+    (memory order instead of gather order on the rotated screen), so the screens agree to FP64 rounding, both drift
+    directions, a ragged env count."""
+    import torch
+    from adaptive_optics_gym_b200 import AOVecEnv
+    kw = dict(atm_type='dynamic', atm_vel=vel, atm_fried=0.10, act_dim=64, obs_dim=2, rew_type='strehl_ratio',
+              timesteps_per_episode=4, seed=5, precision='fused')
+    out = []
+    for gathered in (False, True):
+        if gathered:
+            monkeypatch.setenv('AOG_AR_GATHER', '1')
+        env = AOVecEnv(37, **kw)
+        env.reset()
+        g = torch.Generator(device='cpu').manual_seed(3)
+        for t in range(4):
+            a = (torch.rand((37, 64), generator=g) * 2 - 1).to(env.device)
+            obs, rew, *_ = env.step(a)
+        st = env.get_state()
+        out.append((np.array(st['screens']), obs.cpu().numpy().copy(), rew.cpu().numpy().copy(),
+                    env._h.counters().extrusions))
+        env.close()
+    assert out[0][3] == out[1][3] and out[0][3] >= 36
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=0, atol=1e-12 * np.abs(out[1][0]).max())
+    np.testing.assert_allclose(out[0][1].astype(np.float64), out[1][1].astype(np.float64), rtol=2e-3)   # float16 obs
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-7)
