@@ -1113,6 +1113,166 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
   }
 }
 
+// ----------------------------------------------------------------------------- fused optics, tiny batches
+// k_small_fused: the fused optics chain (k_dm_phase_tc MODE 2: same tables, same fixed-point phase, same sums) for
+// batches of at most SMALL_MAX envs -- BASELINE configs[0] is literally ONE env.  The tensor-core kernel gives a
+// 128-env block to every pupil column and one env to every thread, so for a single env 127 of 128 lanes idle through
+// 240 x 15 chunks (26 us); here a THREAD IS A PIXEL: a CTA takes `ipc` pupil columns, thread y forms the DM phase of
+// pixel (x, y) for every env as an FP32 dot product over the split-fp16 operands the tensor cores would read (a_hi +
+// a_lo and m_hi + m_lo are exact in FP32), adds the atmosphere tile, takes sin / cos on the SFU and multiplies with
+// its record; the column sums are reduced in FP64 (warp shuffles, then the 8 warps through shared memory).  Outputs
+// have the layout k_finalize_tcw reads: R4[env][x][part 0] (parts 1, 2 zero) and one Strehl / fibre slot per CTA.
+constexpr int SMALL_MAX = 8;
+struct SmallParams {
+  int B, Np, kpad, ipc, col_origin, env0;
+  uint32_t sci_ratio_q32;
+  const int32_t* hwt; const uint16_t* apmask; const float* gfib;
+  const __half* act_hi; const __half* act_lo; const __half* m_hi; const __half* m_lo;
+  float2* R4; double2* strehl_part; double2* fib_part;
+};
+template <bool STREHL, int NOBS>
+__global__ void __launch_bounds__(256) k_small_fused(const SmallParams p) {
+  constexpr int NP2 = NOBS / 2, NC = NOBS & 1, NF = FK_NF(NOBS);
+  constexpr int NO = 4 * NP2 + 2 * NC, NV = NO + 2 * FK_JT + 2;      // obs products | fibre (re, im) | Strehl (re, im)
+  __shared__ float act_s[SMALL_MAX][128];
+  __shared__ double red_s[8][SMALL_MAX][NV];
+  __shared__ double fin_s[SMALL_MAX][NV];
+  __shared__ double slot_s[SMALL_MAX][2 * FK_JT + 2];
+  const int Np = p.Np, y = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < SMALL_MAX * 128; i += 256) {
+    const int b = i >> 7, k = i & 127;
+    act_s[b][k] = (b < p.B && k < p.kpad)
+                      ? __half2float(p.act_hi[(size_t)b * p.kpad + k]) + __half2float(p.act_lo[(size_t)b * p.kpad + k]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < SMALL_MAX * (2 * FK_JT + 2); i += 256) (&slot_s[0][0])[i] = 0.0;
+  __syncthreads();
+  constexpr int kmask = 0x7FFFFF, kexp = 0x4B000000;
+  const int32_t q31 = (int32_t)(p.sci_ratio_q32 >> 1);
+  const int32_t sci_bias = (1 << 22) - 2 * (int32_t)(((long long)(1 << 22) * (long long)q31) >> 32);
+  for (int xi = 0; xi < p.ipc; ++xi) {
+    const int x = blockIdx.x * p.ipc + xi;
+    if (x >= Np) break;
+    const bool lit = y < Np && ((p.apmask[x * (Np / 16) + (y >> 4)] >> (y & 15)) & 1);
+    float d[SMALL_MAX];
+#pragma unroll
+    for (int b = 0; b < SMALL_MAX; ++b) d[b] = 0.f;
+    float rec[NF];
+    if (lit) {
+      const size_t pix = (size_t)x * Np + y;
+      for (int kb = 0; kb < p.kpad; kb += 64) {
+        float m[64];
+        const uint4* mh = reinterpret_cast<const uint4*>(p.m_hi + pix * p.kpad + kb);
+        const uint4* ml = reinterpret_cast<const uint4*>(p.m_lo + pix * p.kpad + kb);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 h = __ldg(mh + c), l = __ldg(ml + c);
+          const __half2* hh = reinterpret_cast<const __half2*>(&h);
+          const __half2* ll = reinterpret_cast<const __half2*>(&l);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fh = __half22float2(hh[e]), fl = __half22float2(ll[e]);
+            m[8 * c + 2 * e] = fh.x + fl.x;
+            m[8 * c + 2 * e + 1] = fh.y + fl.y;
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < SMALL_MAX; ++b) {
+          if (b < p.B) {
+            float acc = d[b];
+#pragma unroll
+            for (int k4 = 0; k4 < 16; ++k4) {
+              const float4 a = *reinterpret_cast<const float4*>(&act_s[b][kb + 4 * k4]);
+              acc = fmaf(a.x, m[4 * k4], acc); acc = fmaf(a.y, m[4 * k4 + 1], acc);
+              acc = fmaf(a.z, m[4 * k4 + 2], acc); acc = fmaf(a.w, m[4 * k4 + 3], acc);
+            }
+            d[b] = acc;
+          }
+        }
+      }
+      const float4* rp = reinterpret_cast<const float4*>(p.gfib + pix * NF);
+#pragma unroll
+      for (int r = 0; r < NF / 4; ++r) {
+        const float4 v = __ldg(rp + r);
+        rec[4 * r] = v.x; rec[4 * r + 1] = v.y; rec[4 * r + 2] = v.z; rec[4 * r + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < NF; ++r) rec[r] = 0.f;
+    }
+    int xp = x + p.col_origin;
+    if (xp >= Np) xp -= Np;
+#pragma unroll
+    for (int b = 0; b < SMALL_MAX; ++b) {
+      if (b >= p.B) break;                                          // uniform
+      double vals[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) vals[v] = 0.0;
+      if (lit) {
+        const int env = p.env0 + b, l = env & 31;
+        const size_t ti = (((size_t)(env >> 5) * Np + xp) * (Np / 16) + (y >> 4)) * 512 + (size_t)l * 16 +
+                          ((((y >> 2) & 3) ^ ((l >> 1) & 3)) << 2) + (y & 3);
+        const int32_t tb = __ldg(p.hwt + ti) + __float2int_rn(d[b] * PHI_ONE) + (1 << 22);
+        float c0, s0;
+        sincos_biased_fma(tb, kmask, kexp, &s0, &c0);
+#pragma unroll
+        for (int v = 0; v < NP2; ++v) {
+          vals[4 * v + 0] = (double)(rec[2 * v] * c0);
+          vals[4 * v + 1] = (double)(rec[2 * v + 1] * s0);
+          vals[4 * v + 2] = (double)(rec[2 * v] * s0);
+          vals[4 * v + 3] = (double)(rec[2 * v + 1] * c0);
+        }
+        if (NC) { vals[4 * NP2] = (double)(rec[2 * NP2] * c0); vals[4 * NP2 + 1] = (double)(rec[2 * NP2] * s0); }
+#pragma unroll
+        for (int k = 0; k < FK_JT; ++k) {
+          vals[NO + 2 * k] = (double)(rec[2 * NP2 + NC + k] * c0);
+          vals[NO + 2 * k + 1] = (double)(rec[2 * NP2 + NC + k] * s0);
+        }
+        if (STREHL) {
+          const int32_t ts = 2 * __mulhi(tb, q31) + sci_bias;
+          float cs, ss;
+          sincos_biased_fma(ts, kmask, kexp, &ss, &cs);
+          vals[NO + 2 * FK_JT] = (double)(rec[2 * NP2 + NC + FK_JT] * cs);
+          vals[NO + 2 * FK_JT + 1] = (double)(rec[2 * NP2 + NC + FK_JT] * ss);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double sum = warp_sum(vals[v]);
+        if (lane == 0) red_s[warp][b][v] = sum;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.B * NV; i += 256) {
+      const int b = i / NV, v = i - b * NV;
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red_s[w][b][v];
+      fin_s[b][v] = sum;
+      if (v >= NO) slot_s[b][v - NO] += sum;                       // the same thread owns (b, v) for every column
+    }
+    __syncthreads();
+    // column sums of the obs arm: pair v -> rows v and n-1-v, as k_dm_phase_tc MODE 2 forms them
+    for (int i = threadIdx.x; i < p.B * NOBS * FK_PARTS; i += 256) {
+      const int b = i / (NOBS * FK_PARTS), r = i - b * (NOBS * FK_PARTS), q = r / NOBS, v = r - q * NOBS;
+      float2 out = make_float2(0.f, 0.f);
+      if (q == 0) {
+        const double* f = fin_s[b];
+        if (NC && v == NP2) out = make_float2((float)f[4 * NP2], (float)f[4 * NP2 + 1]);
+        else if (v < NP2) out = make_float2((float)(f[4 * v] - f[4 * v + 1]), (float)(f[4 * v + 2] + f[4 * v + 3]));
+        else { const int w = NOBS - 1 - v; out = make_float2((float)(f[4 * w] + f[4 * w + 1]), (float)(f[4 * w + 2] - f[4 * w + 3])); }
+      }
+      p.R4[(((size_t)b * Np + x) * FK_PARTS + q) * NOBS + v] = out;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.B * (FK_JT + 1); i += 256) {
+    const int b = i / (FK_JT + 1), j = i - b * (FK_JT + 1);
+    const double2 v = make_double2(slot_s[b][2 * j], slot_s[b][2 * j + 1]);
+    if (j < FK_JT) p.fib_part[((size_t)b * FK_SLOTS + blockIdx.x) * FK_JT + j] = v;
+    else if (STREHL) p.strehl_part[(size_t)b * FK_SLOTS + blockIdx.x] = v;
+  }
+}
+
 // ----------------------------------------------------------------------------- field + MFT stage 1
 // k_field_mft1: the pupil field is formed ON CHIP and fed straight into the stage-1 pair MMA
 // (reference AO_env.py:132-135 field, :138 first MFT product):
@@ -2107,6 +2267,23 @@ int launch_phase_n(aog_env* env, TensorState* ts, const FieldParams& p, int n, i
   }
   AOG_FAIL(AOG_ERR_UNSUPPORTED, "obs_dim");
 }
+template <bool STREHL>
+int launch_small(aog_env* env, const SmallParams& sp, int n, cudaStream_t st) {
+  const int grid = cdiv(sp.Np, sp.ipc);
+  switch (n) {
+    case 1: k_small_fused<STREHL, 1><<<grid, 256, 0, st>>>(sp); break;
+    case 2: k_small_fused<STREHL, 2><<<grid, 256, 0, st>>>(sp); break;
+    case 3: k_small_fused<STREHL, 3><<<grid, 256, 0, st>>>(sp); break;
+    case 4: k_small_fused<STREHL, 4><<<grid, 256, 0, st>>>(sp); break;
+    case 5: k_small_fused<STREHL, 5><<<grid, 256, 0, st>>>(sp); break;
+    case 6: k_small_fused<STREHL, 6><<<grid, 256, 0, st>>>(sp); break;
+    case 7: k_small_fused<STREHL, 7><<<grid, 256, 0, st>>>(sp); break;
+    case 8: k_small_fused<STREHL, 8><<<grid, 256, 0, st>>>(sp); break;
+    default: AOG_FAIL(AOG_ERR_UNSUPPORTED, "obs_dim");
+  }
+  AOG_LAUNCH_CHECK();
+  return AOG_OK;
+}
 // k_finalize_tcw<n, FK_PARTS>: one warp per env, dynamic shared memory above 48 KB (opt-in once per device)
 template <int N>
 cudaError_t launch_finalize(int device, const FinalizeArgs& a, int nB, cudaStream_t st) {
@@ -2165,6 +2342,18 @@ int aog_tensor_optics(aog_env* env, bool flat_dm, bool with_reward, const aog_ou
       const int grid = cdiv(fp.num_items, fp.items_per_cta);
       int rc;
       slot_ipc = fp.items_per_cta;            // k_finalize_tc sums exactly the slots this launch writes
+      const bool no_small = getenv("AOG_NO_SMALL") != nullptr;             // A/B switch and test hook: tensor cores for every batch size
+      if (fused && ts->sym && B <= SMALL_MAX && !no_small && ts->kpad <= 128 && Np <= 256 && !fp.dbg) {
+        SmallParams sp{};
+        sp.B = nB; sp.Np = Np; sp.kpad = ts->kpad; sp.col_origin = fp.col_origin; sp.env0 = e0;
+        sp.ipc = cdiv(Np, std::min(ts->num_sms, FK_SLOTS));
+        sp.sci_ratio_q32 = fp.sci_ratio_q32;
+        sp.hwt = ts->hwt; sp.apmask = ts->apmask; sp.gfib = reinterpret_cast<const float*>(ts->gfib);
+        sp.act_hi = ts->act_hi; sp.act_lo = ts->act_lo; sp.m_hi = ts->modesK_hi; sp.m_lo = ts->modesK_lo;
+        sp.R4 = ts->R4; sp.strehl_part = env->strehl_part; sp.fib_part = ts->fib_part;
+        slot_ipc = sp.ipc;
+        rc = strehl ? launch_small<true>(env, sp, n, st) : launch_small<false>(env, sp, n, st);
+      } else
       if (fused && ts->sym) rc = strehl ? launch_phase_n<true, 2>(env, ts, fp, n, grid, st) : launch_phase_n<false, 2>(env, ts, fp, n, grid, st);
       else if (fused)       rc = strehl ? launch_phase_n<true, 1>(env, ts, fp, n, grid, st) : launch_phase_n<false, 1>(env, ts, fp, n, grid, st);
       else                  rc = strehl ? launch_phase_n<true, 0>(env, ts, fp, n, grid, st) : launch_phase_n<false, 0>(env, ts, fp, n, grid, st);
