@@ -58,6 +58,8 @@ int dmma_configure(aog_env* env) {
   AOG_CUDA(cudaFuncSetAttribute(k_ar_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM));
   AOG_CUDA(cudaFuncSetAttribute(k_ar_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM + 4096 * 4));
   AOG_CUDA(cudaFuncSetAttribute(k_dgemm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, DmmaCfg<1>::SMEM));
+  AOG_CUDA(cudaFuncSetAttribute(k_scr_fft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM));
+  AOG_CUDA(cudaFuncSetAttribute(k_scr_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, FFT_SMEM));
   done.store(true, std::memory_order_release);
   return AOG_OK;
 }
@@ -407,7 +409,7 @@ void aog_destroy(aog_env* env) {
   aog_tensor_destroy(env);
   void* ptrs[] = {env->t_aperture, env->t_modes, env->t_gram, env->t_m1f, env->t_m2f, env->t_m1o, env->t_m2o,
                   env->t_lpw, env->t_lpphase, env->t_lpgram, env->t_stencil, env->t_stencil_perm, env->t_arA, env->t_arB, env->t_arW,
-                  env->t_arW_rev, env->t_ar_tail, env->arNZ, env->t_scrC1, env->t_scrW1, env->t_scrW1T, env->t_scrC2, env->t_scrW2, env->t_scrW2T,
+                  env->t_arW_rev, env->t_ar_tail, env->arNZ, env->t_scr_sh, env->t_scr_tw, env->t_scrC1, env->t_scrW1, env->t_scrW1T, env->t_scrC2, env->t_scrW2, env->t_scrW2T,
                   env->screens, env->act, env->bufA, env->bufB, env->bufC, env->bufR, env->coef,
                   env->strehl_part, env->arZ, env->arNew, env->act_in, env->noise_in, env->o_pack,
                   env->t_sh_mla, env->t_sh_C, env->t_sh_CT,
@@ -521,6 +523,33 @@ int aog_set_table(aog_env* env, int which, const void* host, size_t count) {
   if (which == AOG_TABLE_SCR_W1) {
     k_transpose_z<<<cdiv((int)P, 256), 256>>>(env->t_scrW1, env->t_scrW1T, (int)Np, (int)Np);
     AOG_LAUNCH_CHECK();
+  }
+  if (which == AOG_TABLE_SCR_W1) {
+    // a shifted DFT matrix of the reference size?  W1[x][k] = W1[0][k] exp(2 pi i x k / N)  ->  FFT synthesis
+    const double* m = static_cast<const double*>(host);
+    const size_t N = Np;
+    bool fft = N == 240 && getenv("AOG_SCR_GEMM") == nullptr && getenv("AOG_SCR_COMPLEX") == nullptr;
+    std::vector<double> tw(2 * 240);
+    for (int j = 0; j < 240; ++j) {
+      tw[2 * j] = std::cos(2.0 * 3.14159265358979323846 * j / 240.0);
+      tw[2 * j + 1] = std::sin(2.0 * 3.14159265358979323846 * j / 240.0);
+    }
+    double res = 0.0;
+    for (size_t x = 0; fft && x < N; ++x)
+      for (size_t k = 0; k < N; ++k) {
+        const size_t j = (x * k) % N;
+        const double sr = m[2 * k], si = m[2 * k + 1];
+        const double er = sr * tw[2 * j] - si * tw[2 * j + 1], ei = sr * tw[2 * j + 1] + si * tw[2 * j];
+        res = std::max(res, std::max(std::fabs(m[2 * (x * N + k)] - er), std::fabs(m[2 * (x * N + k) + 1] - ei)));
+      }
+    env->scr_fft = fft && res <= 1e-11;
+    if (env->scr_fft) {
+      int rc;
+      if ((rc = dev_alloc(env, &env->t_scr_sh, N))) return rc;
+      if ((rc = dev_alloc(env, &env->t_scr_tw, (size_t)240))) return rc;
+      AOG_CUDA(cudaMemcpy(env->t_scr_sh, m, N * sizeof(double2), cudaMemcpyHostToDevice));       // row x = 0
+      AOG_CUDA(cudaMemcpy(env->t_scr_tw, tw.data(), 240 * sizeof(double2), cudaMemcpyHostToDevice));
+    }
   }
   if (which == AOG_TABLE_SCR_W1 || which == AOG_TABLE_SCR_W2) {
     // conjugate-paired rows -> real-arithmetic synthesis tables (common.cuh: t_scrWst)
@@ -674,6 +703,8 @@ int aog_generate_screens(aog_env* env, void* stream) {
   // real-arithmetic form on the FP64 tensor cores (common.cuh: t_scrWst), one scale at a time:
   //   out1 = [Re W_top ; Im W_top] . [Xr | Xi]   (N x 2 Nk)  ->  U = rows < N/2, V = rows >= N/2
   //   P1 = Ur WrT, P2 = Vi WrT, P3 = Ui WiT, P4 = Vr WiT   (N/2 x N/2 each)  ->  k_scr_combine4
+  const bool fft_form = env->scr_fft && Np == 240 && env->scr_sym[0] && env->scr_sym[1] && N2 % 2 == 0;
+  bool tiles_done = fft_form && env->phase_tiles != nullptr;       // k_scr_fft_cols refreshes the phase tiles itself
   auto synth_real = [&](int sidx, int Nk, const double* Ctab, unsigned long long draw_base, int e0, int nB,
                         int accumulate) -> int {
     const int Nh = Np / 2, Q = Nh * Nh;
@@ -681,10 +712,23 @@ int aog_generate_screens(aog_env* env, void* stream) {
     double* O = reinterpret_cast<double*>(env->bufB);
     double* Pq = reinterpret_cast<double*>(env->bufC);
     const long long sX = 2LL * P, sO = 2 * sB, sP = 2 * sC;
-    k_scr_noise_planes<<<dim3(cdiv(Nk * Nk, 256), nB), 256, 0, st>>>(Ctab, X, Nk, sX, e0, seed,
-                                                                      (unsigned long long)c.env_id_base, draw_base);
-    AOG_LAUNCH_CHECK();
     { int rc = dmma_configure(env); if (rc) return rc; }
+    if (sidx == 0 && fft_form) {
+      // the fine scale is a 240 x 240 inverse DFT: rows (normals drawn in the kernel), then columns straight into
+      // the screens, on top of the coarse scale, with the phase tiles of the tensor / fused paths (fft240.cuh)
+      double2* T = env->bufB;
+      k_scr_fft_rows<<<dim3(240 / FFT_LINES, nB), FFT_THREADS, FFT_SMEM, st>>>(Ctab, env->t_scr_sh, env->t_scr_tw, T, sB, e0, seed,
+                                                                       (unsigned long long)c.env_id_base, draw_base);
+      AOG_LAUNCH_CHECK();
+      k_scr_fft_cols<<<dim3(240 / FFT_LINES, nB), FFT_THREADS, FFT_SMEM, st>>>(T, sB, env->t_scr_tw, env->screens, P, e0, c.sqrt_cn2, accumulate,
+                                                                       env->phase_tiles, 1.0 / (c.wavelength_wfs * 3.14159265358979323846),
+                                                                       env->phase_tiles_unit);
+      AOG_LAUNCH_CHECK();
+      return AOG_OK;
+    }
+    k_scr_noise_planes<<<dim3(cdiv(Nk * Nk / 2, 256), nB), 256, 0, st>>>(Ctab, X, Nk, sX, e0, seed,
+                                                                          (unsigned long long)c.env_id_base, draw_base);
+    AOG_LAUNCH_CHECK();
     k_dgemm_mma<<<dim3(cdiv(2 * Nk, 64), cdiv(Np, 128), nB), 256, DmmaCfg<1>::SMEM, st>>>(env->t_scrWst[sidx], X, O, Np, 2 * Nk, Nk, Nk,
                                                                            2 * Nk, 2 * Nk, 0, sX, sO);
     AOG_LAUNCH_CHECK();
@@ -702,14 +746,16 @@ int aog_generate_screens(aog_env* env, void* stream) {
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     const int nB = std::min(env->chunk, B - e0);
     if (env->scr_sym[0] && env->scr_sym[1]) {
-      int rc = synth_real(0, Np, env->t_scrC1, base, e0, nB, 0);
+      // (with the FFT form the coarse scale goes first: the column kernel finishes the screen and writes its tiles)
+      int rc = synth_real(fft_form ? 1 : 0, fft_form ? N2 : Np, fft_form ? env->t_scrC2 : env->t_scrC1, fft_form ? base + P : base, e0, nB, 0);
       if (rc) return rc;
-      rc = synth_real(1, N2, env->t_scrC2, base + P, e0, nB, 1);
+      rc = synth_real(fft_form ? 0 : 1, fft_form ? Np : N2, fft_form ? env->t_scrC1 : env->t_scrC2, fft_form ? base : base + P, e0, nB, 1);
       if (rc) return rc;
       continue;
     }
+    tiles_done = false;
     // scale 1: X1 [Np x Np] -> W1 X1 W1^T
-    k_scr_noise<<<dim3(cdiv(P, 256), nB), 256, 0, st>>>(env->t_scrC1, env->bufA, P, (long long)P, e0, seed,
+    k_scr_noise<<<dim3(cdiv(P / 2, 256), nB), 256, 0, st>>>(env->t_scrC1, env->bufA, P, (long long)P, e0, seed,
                                                         (unsigned long long)c.env_id_base, base);
     AOG_LAUNCH_CHECK();
     k_zgemm<<<dim3(cdiv(Np, 64), cdiv(Np, 64), nB), 256, 0, st>>>(env->t_scrW1, env->bufA, env->bufB, Np, Np, Np, Np,
@@ -721,7 +767,7 @@ int aog_generate_screens(aog_env* env, void* stream) {
     k_scr_combine<<<dim3(cdiv(P, 256), nB), 256, 0, st>>>(env->screens, env->bufC, P, sC, e0, c.sqrt_cn2, 0);
     AOG_LAUNCH_CHECK();
     // scale 2: X2 [N2 x N2] -> W2 X2 W2^T
-    k_scr_noise<<<dim3(cdiv(N2 * N2, 256), nB), 256, 0, st>>>(env->t_scrC2, env->bufA, N2 * N2, (long long)P, e0, seed,
+    k_scr_noise<<<dim3(cdiv(N2 * N2 / 2, 256), nB), 256, 0, st>>>(env->t_scrC2, env->bufA, N2 * N2, (long long)P, e0, seed,
                                                               (unsigned long long)c.env_id_base, base + P);
     AOG_LAUNCH_CHECK();
     k_zgemm<<<dim3(cdiv(N2, 64), cdiv(Np, 64), nB), 256, 0, st>>>(env->t_scrW2, env->bufA, env->bufB, Np, N2, N2, N2,
@@ -734,7 +780,7 @@ int aog_generate_screens(aog_env* env, void* stream) {
     AOG_LAUNCH_CHECK();
   }
   env->cnt.column_origin = 0;
-  if (c.precision != AOG_PRECISION_F64) return aog_tensor_screens_updated(env);
+  if (c.precision != AOG_PRECISION_F64 && !tiles_done) return aog_tensor_screens_updated(env);
   return AOG_OK;
 }
 

@@ -40,6 +40,9 @@ struct aog_env {
   double* t_scrC2 = nullptr;       // [N2][N2]
   double2* t_scrW2 = nullptr;      // [Np][N2]
   double2* t_scrW2T = nullptr;     // [N2][Np]
+  double2* t_scr_sh = nullptr;     // [Np] W1[0][k]: W1[x][k] = sh[k] w^(x k) (a shifted DFT matrix) -> FFT synthesis (fft240.cuh)
+  double2* t_scr_tw = nullptr;     // [240] w^j = exp(2 pi i j / 240)
+  bool scr_fft = false;
 
   // ---- Shack-Hartmann tables / state ----
   int sh_num_sub = 0, sh_num_pix = 0;

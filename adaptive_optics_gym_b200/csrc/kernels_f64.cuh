@@ -1,6 +1,7 @@
 // FP64 (exact) kernels of the AO-v0 step path.  This is the guaranteed-parity arithmetic
 // (AOG_PRECISION_F64) and the on-device checker for the tensor-core path.
 #pragma once
+#include "fft240.cuh"
 #include "common.cuh"
 #include <curand_kernel.h>
 
@@ -1117,17 +1118,136 @@ static __global__ void k_ar_scatter(double* __restrict__ screens, const double* 
 // von-Karman screen synthesis (semi_dynamic reset; AO_env.py:76-77): spectral noise
 // X = C . (xi_r + i xi_i), then screen = Re[W X W^T] through the batched complex GEMM.
 // --------------------------------------------------------------------------------------
+// Spectral normals of the synthesis: ONE Philox-4x32-10 block (counter = element pair, env; key = seed) makes the two
+// complex normals of elements 2 j and 2 j + 1 by two Box-Muller transforms in FP32 on the SFU (24-bit uniforms,
+// lg2 / sqrt / sin / cos approximations: a normal deviate good to ~1e-6, |z| <= 5.9) -- the screens are random draws,
+// equivalent to the reference's only statistically, and curand's FP64 Box-Muller (log, sqrt, sincospi in double, one
+// curand_init per element) was 2.6 ms of a 10.7 ms reset of 4096 envs.
+__device__ __forceinline__ uint4 aog_philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(h1 ^ c.y ^ k.x, l1, h0 ^ c.w ^ k.y, l0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// z[0..3]: (re, im) of element 2 j, (re, im) of element 2 j + 1;  pair = (draw_base + i) / 2 for even i
+__device__ __forceinline__ void scr_normals4(unsigned long long seed, unsigned long long env_id, unsigned long long pair,
+                                             float (&z)[4]) {
+  const uint4 r = aog_philox4x32_10(make_uint4((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)env_id, (uint32_t)(env_id >> 32)),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float u0 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float ra = sqrtf(-2.f * __logf(u0)), rb = sqrtf(-2.f * __logf(u2));
+  float sn, cs;
+  __sincosf(6.28318530718f * u1, &sn, &cs);
+  z[0] = ra * cs; z[1] = ra * sn;
+  __sincosf(6.28318530718f * u3, &sn, &cs);
+  z[2] = rb * cs; z[3] = rb * sn;
+}
 static __global__ void k_scr_noise(const double* __restrict__ C, double2* __restrict__ X, int count, long long strideX,
                             int env0, unsigned long long seed, unsigned long long env_id_base,
                             unsigned long long draw_base) {
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);                // count and draw_base are even
   if (i >= count) return;
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, env_id_base + env0 + b, (draw_base + (unsigned long long)i) * 4ull, &st);
-  const double2 z = curand_normal2_double(&st);
-  const double c = C[i];
-  X[(size_t)b * strideX + i] = make_double2(c * z.x, c * z.y);
+  float z[4];
+  scr_normals4(seed, env_id_base + env0 + b, (draw_base + (unsigned long long)i) >> 1, z);
+  const double c0 = C[i], c1 = C[i + 1];
+  X[(size_t)b * strideX + i] = make_double2(c0 * (double)z[0], c0 * (double)z[1]);
+  X[(size_t)b * strideX + i + 1] = make_double2(c1 * (double)z[2], c1 * (double)z[3]);
+}
+
+// FFT form of the fine scale (fft240.cuh): S1 = Re IDFT2(X sh sh^T) for Np = 240, W1[x][k] = sh[k] w^(x k).
+//   k_scr_fft_rows: T[ky][x] = sum_kx X'[ky][kx] w^(x kx),  X' = (Xr + i Xi) sh[ky] sh[kx]     (FFT_LINES rows per block)
+//   k_scr_fft_cols: screens[x][y] (+)= scale Re sum_ky T[ky][x] w^(y ky)                        (FFT_LINES columns per block)
+// X is generated inside the row kernel (the Philox draws of k_scr_noise_planes, so the GEMM forms give the same
+// screens); the column kernel adds the coarse scale already in the screens and writes the fixed-point phase tiles of
+// the tensor / fused paths.  256 threads: stage 1 on 16 x 15 threads, stage 2 on 16 x 16; the 240-slot line buffers
+// sit in shared memory (rows padded for the column kernel's transposing stores).
+#ifndef AOG_FFT_LINES
+#define AOG_FFT_LINES 16
+#endif
+constexpr int FFT_LINES = AOG_FFT_LINES, FFT_THREADS = 16 * FFT_LINES, FFT_LD = 241;
+constexpr int FFT_SMEM = (FFT_LINES * FFT_LD + 2 * 240) * (int)sizeof(double2);
+static __global__ void __launch_bounds__(FFT_THREADS)
+k_scr_fft_rows(const double* __restrict__ C, const double2* __restrict__ sh, const double2* __restrict__ tw,
+               double2* __restrict__ T, long long sT, int env0, unsigned long long seed, unsigned long long env_id_base,
+               unsigned long long draw_base) {
+  constexpr int N = 240;
+  extern __shared__ __align__(16) double2 fft_smem[];
+  double2* buf = fft_smem;                       // [16][FFT_LD]
+  double2* tw_s = fft_smem + FFT_LINES * FFT_LD; // [240]
+  double2* sh_s = tw_s + N;                      // [240]
+  const int b = blockIdx.y, ky0 = blockIdx.x * FFT_LINES, t = threadIdx.x;
+  for (int i = t; i < N; i += FFT_THREADS) { tw_s[i] = tw[i]; sh_s[i] = sh[i]; }
+  __syncthreads();
+  // X = C . xi: the draws of k_scr_noise_planes (element i = ky N + kx, pairs of elements per Philox block), never stored
+  for (int pi = t; pi < FFT_LINES * (N / 2); pi += FFT_THREADS) {
+    const int r = pi / (N / 2), kx = 2 * (pi - r * (N / 2)), ky = ky0 + r, i = ky * N + kx;
+    float z[4];
+    scr_normals4(seed, env_id_base + env0 + b, (draw_base + (unsigned long long)i) >> 1, z);
+    const double c0 = C[i], c1 = C[i + 1];
+    const double2 s0 = fft240::cmul(sh_s[ky], sh_s[kx]), s1 = fft240::cmul(sh_s[ky], sh_s[kx + 1]);
+    buf[r * FFT_LD + kx] = fft240::cmul(make_double2(c0 * (double)z[0], c0 * (double)z[1]), s0);
+    buf[r * FFT_LD + kx + 1] = fft240::cmul(make_double2(c1 * (double)z[2], c1 * (double)z[3]), s1);
+  }
+  __syncthreads();
+  if (t < FFT_LINES * 15) fft240::stage1(buf + (t / 15) * FFT_LD, 1, t % 15, tw_s);
+  __syncthreads();
+  {
+    // T is stored [ky / 16][x][ky % 16]: this block's 16 rows are the 16 contiguous entries of every x, so the column
+    // kernel reads 4 KB runs (a plain [ky][x] layout made it gather 256-byte pieces at a 3840-byte stride: 3.2 ms)
+    static_assert(FFT_LINES == 16, "T layout");
+    const int r = t & 15, k1 = t >> 4;
+    double2 a[15];
+    fft240::stage2(buf + r * FFT_LD, 1, k1, a);
+    double2* out = T + (size_t)b * sT + ((size_t)blockIdx.x * N + k1) * 16 + r;
+#pragma unroll
+    for (int k2 = 0; k2 < 15; ++k2) out[(size_t)16 * k2 * 16] = a[k2];
+  }
+}
+static __global__ void __launch_bounds__(FFT_THREADS)
+k_scr_fft_cols(const double2* __restrict__ T, long long sT, const double2* __restrict__ tw, double* __restrict__ screens,
+               int P, int env0, double scale, int accumulate, int32_t* __restrict__ tiles, double inv_w, double phi_one) {
+  constexpr int N = 240;
+  extern __shared__ __align__(16) double2 fft_smem[];
+  double2* buf = fft_smem;                       // [16 columns][FFT_LD]
+  double2* tw_s = fft_smem + FFT_LINES * FFT_LD;
+  const int b = blockIdx.y, x0 = blockIdx.x * FFT_LINES, t = threadIdx.x;
+  for (int i = t; i < N; i += FFT_THREADS) tw_s[i] = tw[i];
+  const double2* tb = T + (size_t)b * sT;
+#pragma unroll
+  for (int kb = 0; kb < N / 16; ++kb)                  // T is [ky / 16][x][ky % 16]: 16 columns x 16 rows = one 4 KB run
+    buf[(t >> 4) * FFT_LD + kb * 16 + (t & 15)] = tb[((size_t)kb * N + x0) * 16 + t];
+  __syncthreads();
+  if (t < FFT_LINES * 15) fft240::stage1(buf + (t / 15) * FFT_LD, 1, t % 15, tw_s);
+  __syncthreads();
+  {
+    const int c = t >> 4, k1 = t & 15;
+    double2 a[15];
+    fft240::stage2(buf + c * FFT_LD, 1, k1, a);
+    double* out = screens + (size_t)(env0 + b) * P + (size_t)(x0 + c) * N + k1;     // screens are [x][y]
+    // the finished screen's fixed-point phase tile (TensorState::hwt, as k_ar_step's epilogue writes it): y = k1 + 16 k2
+    // is element k1 of chunk k2, column origin 0 after a synthesis
+    const size_t env = (size_t)env0 + b;
+    const int l = (int)(env & 31), piece = ((k1 >> 2) & 3) ^ ((l >> 1) & 3), e = k1 & 3;
+    int32_t* trow = tiles ? tiles + (((env >> 5) * N + (x0 + c)) * (size_t)(N / 16)) * 512 + (size_t)l * 16 + piece * 4 + e : nullptr;
+#pragma unroll
+    for (int k2 = 0; k2 < 15; ++k2) {
+      double v = scale * a[k2].x;
+      if (accumulate) v += out[16 * k2];
+      out[16 * k2] = v;
+      if (tiles) {
+        double f = v * inv_w * phi_one;
+        f = fmin(fmax(f, -2147483000.0), 2147483000.0);
+        trow[(size_t)k2 * 512] = (int32_t)__double2ll_rn(f);
+      }
+    }
+  }
 }
 
 // real-arithmetic synthesis (common.cuh: t_scrWst): the same draws as k_scr_noise, written as two real planes
@@ -1136,16 +1256,17 @@ static __global__ void k_scr_noise_planes(const double* __restrict__ C, double* 
                                           int env0, unsigned long long seed, unsigned long long env_id_base,
                                           unsigned long long draw_base) {
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);                // Nk and draw_base are even
   if (i >= Nk * Nk) return;
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, env_id_base + env0 + b, (draw_base + (unsigned long long)i) * 4ull, &st);
-  const double2 z = curand_normal2_double(&st);
-  const double c = C[i];
-  const int k = i / Nk, l = i - k * Nk;
+  float z[4];
+  scr_normals4(seed, env_id_base + env0 + b, (draw_base + (unsigned long long)i) >> 1, z);
+  const double c0 = C[i], c1 = C[i + 1];
+  const int k = i / Nk, l = i - k * Nk;                                     // i + 1 is in the same row
   double* x = X + (size_t)b * strideX + (size_t)k * 2 * Nk + l;
-  x[0] = c * z.x;
-  x[Nk] = c * z.y;
+  x[0] = c0 * (double)z[0];
+  x[Nk] = c0 * (double)z[1];
+  x[1] = c1 * (double)z[2];
+  x[Nk + 1] = c1 * (double)z[3];
 }
 
 // S at the four mirror images of (y, x), y, x < N/2, from P1 = Ur Wr^T, P2 = Vi Wr^T, P3 = Ui Wi^T, P4 = Vr Wi^T

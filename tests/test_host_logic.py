@@ -154,3 +154,19 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['higher_is_better'] is True and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
     assert line['cpu_baseline']['cores'] == 2 and line['e2e']['h2d_bytes_per_step'] == 0
     assert 'quasi_static' in line['config']['workload']
+
+
+def test_fft240_index_maps_on_the_cpu(tmp_path):
+    """csrc/fft240.cuh (the 16 x 15 Cooley-Tukey transform of the FFT screen synthesis) compiled for the host against a
+    direct O(N^2) DFT: the radix-2 DFT-16, the Good-Thomas DFT-15 and the twiddle / slot maps agree to 1e-13."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not found')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'fft240_host')
+    subprocess.run([nvcc, '-O2', '-std=c++17', '-Wno-deprecated-gpu-targets', '-o', exe,
+                    os.path.join(root, 'tools', 'micro', 'fft240_host.cu')], check=True, capture_output=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert float(out.strip()) < 1e-13

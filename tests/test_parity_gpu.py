@@ -555,21 +555,28 @@ def test_device_poisson_sampler_statistics():
 
 
 def test_real_arithmetic_screen_synthesis_matches_complex_form(monkeypatch):
-    """von-Karman synthesis Re(W X W^T): the real-arithmetic tensor-core form (conjugate-paired rows of W) draws the
-    same Philox normals and must reproduce the two-complex-GEMM form to rounding."""
+    """von-Karman synthesis Re(W X W^T): the FFT form of the fine scale (fft240.cuh: W1 is a shifted 240-point DFT
+    matrix; default) and the real-arithmetic tensor-core form (conjugate-paired rows of W; AOG_SCR_GEMM=1) draw the
+    same Philox normals and must reproduce the two-complex-GEMM form (AOG_SCR_COMPLEX=1) to rounding."""
     from adaptive_optics_gym_b200 import AOVecEnv
     kw = dict(atm_type='semi_dynamic', atm_fried=0.15, seed=11)
-    env = AOVecEnv(7, **kw)
-    env.reset()
-    fast = env._h.get_screens()
-    env.close()
+
+    def screens():
+        env = AOVecEnv(7, **kw)
+        env.reset()
+        out = env._h.get_screens()
+        env.close()
+        return out
+
+    fft = screens()
+    monkeypatch.setenv('AOG_SCR_GEMM', '1')
+    gemm = screens()
     monkeypatch.setenv('AOG_SCR_COMPLEX', '1')
-    ref = AOVecEnv(7, **kw)
-    ref.reset()
-    slow = ref._h.get_screens()
-    ref.close()
+    slow = screens()
     assert np.abs(slow).max() > 0
-    assert np.abs(fast - slow).max() <= 1e-11 * np.abs(slow).max()
+    assert np.abs(gemm - slow).max() <= 1e-11 * np.abs(slow).max()
+    assert np.abs(fft - slow).max() <= 1e-11 * np.abs(slow).max()
+    assert not np.array_equal(fft, gemm)          # (the switch did select another kernel)
 
 
 @pytest.mark.parametrize('precision', ['fused', 'tensor'])
