@@ -120,8 +120,8 @@ int extrude_direct(aog_env* env, bool positive, int n, const double* noise_dev, 
   int org = (int)env->cnt.column_origin;
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     const int nB = std::min(env->chunk, B - e0);
-    dim3 gn(cdiv(Np / 2, 128), nB, n);
-    k_ar_noise<<<gn, 128, 0, st>>>(noise_dev, env->arNZ, Np, nB, n, e0, c.sqrt_cn2, (long long)n * Np, c.seed,
+    dim3 gn(cdiv(cdiv(Np, 4), 64), nB, n);
+    k_ar_noise<<<gn, 64, 0, st>>>(noise_dev, env->arNZ, Np, nB, n, e0, c.sqrt_cn2, (long long)n * Np, c.seed,
                                    (unsigned long long)c.env_id_base, (unsigned long long)env->cnt.extrusions);
     AOG_LAUNCH_CHECK();
     org = (int)env->cnt.column_origin;

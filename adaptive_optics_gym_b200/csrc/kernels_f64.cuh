@@ -758,6 +758,38 @@ static __global__ void __launch_bounds__(FIN_WARPS * 32, 2) k_finalize_tcw(Final
 // gather: Z[b] = [ screen[stencil] (on the 180-degree rotated screen when moving +x) ,
 //                  sqrt(Cn2) xi ];  GEMM: new = Z . [A^T ; B^T];  scatter: ring slot.
 // --------------------------------------------------------------------------------------
+// Philox-4x32-10 (Salmon et al. 2011), one counter block per call
+__device__ __forceinline__ uint4 aog_philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(h1 ^ c.y ^ k.x, l1, h0 ^ c.w ^ k.y, l0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// four standard normals from one block: two Box-Muller transforms in FP32 on the SFU (24-bit uniforms; a deviate good
+// to ~1e-6, |z| <= 5.9).  The draws only have to be normal and reproducible from (seed, env, index) -- parity with the
+// reference is through injected noise -- and curand's FP64 Box-Muller cost 58 us per step of 4096 envs at 20 m/s.
+__device__ __forceinline__ void aog_normals4(uint4 r, float (&z)[4]) {
+  const float u0 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float ra = sqrtf(-2.f * __logf(u0)), rb = sqrtf(-2.f * __logf(u2));
+  float sn, cs;
+  __sincosf(6.28318530718f * u1, &sn, &cs);
+  z[0] = ra * cs; z[1] = ra * sn;
+  __sincosf(6.28318530718f * u3, &sn, &cs);
+  z[2] = rb * cs; z[3] = rb * sn;
+}
+// extrusion noise: normals 4 j .. 4 j + 3 of extrusion `draw` of env `env_id`
+__device__ __forceinline__ void ar_normals4(unsigned long long seed, unsigned long long env_id, unsigned long long draw,
+                                            int j, float (&z)[4]) {
+  aog_normals4(aog_philox4x32_10(make_uint4((uint32_t)j, (uint32_t)draw, (uint32_t)(draw >> 32), (uint32_t)env_id),
+                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(env_id >> 32))), z);
+}
+
 static __global__ void k_ar_gather(const double* __restrict__ screens, const int* __restrict__ stencil,
                             const double* __restrict__ noise, double* __restrict__ Z, int P, int Np, int Ns,
                             int env0, int col_origin, int flipped, double sqrt_cn2, long long noise_stride,
@@ -779,11 +811,10 @@ static __global__ void k_ar_gather(const double* __restrict__ screens, const int
     if (noise) {
       xi = noise[(size_t)(env0 + b) * noise_stride + i];
     } else {
-      // one Philox block (4 words) makes TWO normals: neighbouring threads (i, i ^ 1) share the draw of pair i / 2
-      curandStatePhilox4_32_10_t st;
-      curand_init(seed, env_id_base + env0 + b, (draw_index * (unsigned long long)Np + (unsigned long long)(i & ~1)) * 4ull, &st);
-      const double2 z = curand_normal2_double(&st);
-      xi = (i & 1) ? z.y : z.x;
+      // one Philox block makes four normals: threads i, i ^ 1, i ^ 2, i ^ 3 share the block i / 4 (as k_ar_noise draws them)
+      float z[4];
+      ar_normals4(seed, env_id_base + env0 + b, draw_index, i >> 2, z);
+      xi = (double)z[i & 3];
     }
     v = sqrt_cn2 * xi;
   }
@@ -792,25 +823,28 @@ static __global__ void k_ar_gather(const double* __restrict__ screens, const int
 
 // sqrt(Cn2) xi for ALL the extrusions of a step in one launch (the DIRECT form of k_ar_step reads it in place):
 // NZ[(e nB + b) Np + i], e < next;  the same Philox draws as k_ar_gather (extrusion e uses draw index draw0 + e), one
-// block per pair of normals, or the injected normals noise[(env0 + b) noise_stride + e Np + i].
+// block per four normals, or the injected normals noise[(env0 + b) noise_stride + e Np + i].
 static __global__ void k_ar_noise(const double* __restrict__ noise, double* __restrict__ NZ, int Np, int nB, int next,
                                   int env0, double sqrt_cn2, long long noise_stride, unsigned long long seed,
                                   unsigned long long env_id_base, unsigned long long draw0) {
   const int b = blockIdx.y, e = blockIdx.z;
-  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = 4 * j;
   if (i >= Np) return;
-  double2 z;
+  double v[4];
   if (noise) {
     const double* src = noise + (size_t)(env0 + b) * noise_stride + (size_t)e * Np + i;
-    z = make_double2(src[0], i + 1 < Np ? src[1] : 0.0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i + k < Np ? src[k] : 0.0;
   } else {
-    curandStatePhilox4_32_10_t st;
-    curand_init(seed, env_id_base + env0 + b, ((draw0 + e) * (unsigned long long)Np + (unsigned long long)i) * 4ull, &st);
-    z = curand_normal2_double(&st);
+    float z[4];
+    ar_normals4(seed, env_id_base + env0 + b, draw0 + e, j, z);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (double)z[k];
   }
   double* dst = NZ + ((size_t)e * nB + b) * Np + i;
-  dst[0] = sqrt_cn2 * z.x;
-  if (i + 1 < Np) dst[1] = sqrt_cn2 * z.y;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (i + k < Np) dst[k] = sqrt_cn2 * v[k];
 }
 
 // new column = Z . W (hcipy _extrude: A z + B xi for every env) on the FP64 tensor cores, with the scatter into the
@@ -1123,30 +1157,11 @@ static __global__ void k_ar_scatter(double* __restrict__ screens, const double* 
 // lg2 / sqrt / sin / cos approximations: a normal deviate good to ~1e-6, |z| <= 5.9) -- the screens are random draws,
 // equivalent to the reference's only statistically, and curand's FP64 Box-Muller (log, sqrt, sincospi in double, one
 // curand_init per element) was 2.6 ms of a 10.7 ms reset of 4096 envs.
-__device__ __forceinline__ uint4 aog_philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
-    const uint32_t h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(h1 ^ c.y ^ k.x, l1, h0 ^ c.w ^ k.y, l0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
 // z[0..3]: (re, im) of element 2 j, (re, im) of element 2 j + 1;  pair = (draw_base + i) / 2 for even i
 __device__ __forceinline__ void scr_normals4(unsigned long long seed, unsigned long long env_id, unsigned long long pair,
                                              float (&z)[4]) {
-  const uint4 r = aog_philox4x32_10(make_uint4((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)env_id, (uint32_t)(env_id >> 32)),
-                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float u0 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float ra = sqrtf(-2.f * __logf(u0)), rb = sqrtf(-2.f * __logf(u2));
-  float sn, cs;
-  __sincosf(6.28318530718f * u1, &sn, &cs);
-  z[0] = ra * cs; z[1] = ra * sn;
-  __sincosf(6.28318530718f * u3, &sn, &cs);
-  z[2] = rb * cs; z[3] = rb * sn;
+  aog_normals4(aog_philox4x32_10(make_uint4((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)env_id, (uint32_t)(env_id >> 32)),
+                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), z);
 }
 static __global__ void k_scr_noise(const double* __restrict__ C, double2* __restrict__ X, int count, long long strideX,
                             int env0, unsigned long long seed, unsigned long long env_id_base,
