@@ -721,8 +721,7 @@ int aog_generate_screens(aog_env* env, void* stream) {
                                                                        (unsigned long long)c.env_id_base, draw_base);
       AOG_LAUNCH_CHECK();
       k_scr_fft_cols<<<dim3(240 / FFT_LINES, nB), FFT_THREADS, FFT_SMEM, st>>>(T, sB, env->t_scr_tw, env->screens, P, e0, c.sqrt_cn2, accumulate,
-                                                                       env->phase_tiles, 1.0 / (c.wavelength_wfs * 3.14159265358979323846),
-                                                                       env->phase_tiles_unit);
+                                                                       nullptr, 0.0, 0.0);
       AOG_LAUNCH_CHECK();
       return AOG_OK;
     }
@@ -739,17 +738,20 @@ int aog_generate_screens(aog_env* env, void* stream) {
                                                                          2 * Nk, Nh, Nh, sO, 0, sP);
       AOG_LAUNCH_CHECK();
     }
-    k_scr_combine4<<<dim3(cdiv(Q, 256), nB), 256, 0, st>>>(env->screens, Pq, Np, sP, e0, c.sqrt_cn2, accumulate);
+    // with the FFT form this is the last writer of the screens: it also refreshes the phase tiles
+    const bool wt = fft_form && accumulate && env->phase_tiles != nullptr;
+    k_scr_combine4<<<dim3(cdiv(Q, 256), nB), 256, 0, st>>>(env->screens, Pq, Np, sP, e0, c.sqrt_cn2, accumulate,
+                                                           wt ? env->phase_tiles : nullptr,
+                                                           1.0 / (c.wavelength_wfs * 3.14159265358979323846), env->phase_tiles_unit);
     AOG_LAUNCH_CHECK();
     return AOG_OK;
   };
   for (int e0 = 0; e0 < B; e0 += env->chunk) {
     const int nB = std::min(env->chunk, B - e0);
     if (env->scr_sym[0] && env->scr_sym[1]) {
-      // (with the FFT form the coarse scale goes first: the column kernel finishes the screen and writes its tiles)
-      int rc = synth_real(fft_form ? 1 : 0, fft_form ? N2 : Np, fft_form ? env->t_scrC2 : env->t_scrC1, fft_form ? base + P : base, e0, nB, 0);
+      int rc = synth_real(0, Np, env->t_scrC1, base, e0, nB, 0);
       if (rc) return rc;
-      rc = synth_real(fft_form ? 0 : 1, fft_form ? Np : N2, fft_form ? env->t_scrC1 : env->t_scrC2, fft_form ? base : base + P, e0, nB, 1);
+      rc = synth_real(1, N2, env->t_scrC2, base + P, e0, nB, 1);
       if (rc) return rc;
       continue;
     }

@@ -1180,8 +1180,9 @@ static __global__ void k_scr_noise(const double* __restrict__ C, double2* __rest
 //   k_scr_fft_rows: T[ky][x] = sum_kx X'[ky][kx] w^(x kx),  X' = (Xr + i Xi) sh[ky] sh[kx]     (FFT_LINES rows per block)
 //   k_scr_fft_cols: screens[x][y] (+)= scale Re sum_ky T[ky][x] w^(y ky)                        (FFT_LINES columns per block)
 // X is generated inside the row kernel (the Philox draws of k_scr_noise_planes, so the GEMM forms give the same
-// screens); the column kernel adds the coarse scale already in the screens and writes the fixed-point phase tiles of
-// the tensor / fused paths.  256 threads: stage 1 on 16 x 15 threads, stage 2 on 16 x 16; the 240-slot line buffers
+// screens); the column kernel writes the screens, and the coarse scale's k_scr_combine4 then adds its part and writes
+// the fixed-point phase tiles of the tensor / fused paths (the column kernel can do both itself -- `accumulate`,
+// `tiles` -- but its few warps hide the read-modify-write badly: 2.6 ms against 1.9 + 0.4 in the element-wise kernel).  256 threads: stage 1 on 16 x 15 threads, stage 2 on 16 x 16; the 240-slot line buffers
 // sit in shared memory (rows padded for the column kernel's transposing stores).
 #ifndef AOG_FFT_LINES
 #define AOG_FFT_LINES 16
@@ -1235,9 +1236,13 @@ k_scr_fft_cols(const double2* __restrict__ T, long long sT, const double2* __res
   const int b = blockIdx.y, x0 = blockIdx.x * FFT_LINES, t = threadIdx.x;
   for (int i = t; i < N; i += FFT_THREADS) tw_s[i] = tw[i];
   const double2* tb = T + (size_t)b * sT;
+  {
+    double2 v[N / 16];                                 // all 15 loads in flight before the first store
 #pragma unroll
-  for (int kb = 0; kb < N / 16; ++kb)                  // T is [ky / 16][x][ky % 16]: 16 columns x 16 rows = one 4 KB run
-    buf[(t >> 4) * FFT_LD + kb * 16 + (t & 15)] = tb[((size_t)kb * N + x0) * 16 + t];
+    for (int kb = 0; kb < N / 16; ++kb) v[kb] = tb[((size_t)kb * N + x0) * 16 + t];   // T is [ky / 16][x][ky % 16]: 16 columns x 16 rows = one 4 KB run
+#pragma unroll
+    for (int kb = 0; kb < N / 16; ++kb) buf[(t >> 4) * FFT_LD + kb * 16 + (t & 15)] = v[kb];
+  }
   __syncthreads();
   if (t < FFT_LINES * 15) fft240::stage1(buf + (t / 15) * FFT_LD, 1, t % 15, tw_s);
   __syncthreads();
@@ -1286,8 +1291,11 @@ static __global__ void k_scr_noise_planes(const double* __restrict__ C, double* 
 
 // S at the four mirror images of (y, x), y, x < N/2, from P1 = Ur Wr^T, P2 = Vi Wr^T, P3 = Ui Wi^T, P4 = Vr Wi^T
 // (U = Re W_top X, V = Im W_top X): (P1 -+ P2) -+ (P3 +- P4)
+// tiles != null (the last writer of a synthesis): also the fixed-point phase tiles of the tensor / fused paths
+// (TensorState::hwt, as k_ar_step's epilogue writes them; column origin 0)
 static __global__ void k_scr_combine4(double* __restrict__ screens, const double* __restrict__ Pq, int Np,
-                                      long long strideP, int env0, double scale, int accumulate) {
+                                      long long strideP, int env0, double scale, int accumulate,
+                                      int32_t* __restrict__ tiles, double inv_w, double phi_one) {
   const int Nh = Np / 2, Q = Nh * Nh;
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1299,8 +1307,20 @@ static __global__ void k_scr_combine4(double* __restrict__ screens, const double
   const double v[4] = {(p1 - p2) - (p3 + p4), (p1 - p2) + (p3 + p4), (p1 + p2) - (p3 - p4), (p1 + p2) + (p3 - p4)};
   const size_t idx[4] = {(size_t)x * Np + y, (size_t)(Np - 1 - x) * Np + y, (size_t)x * Np + (Np - 1 - y),
                          (size_t)(Np - 1 - x) * Np + (Np - 1 - y)};
+  const size_t env = (size_t)env0 + b;
+  const int l = (int)(env & 31);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) s[idx[c]] = accumulate ? (s[idx[c]] + scale * v[c]) : scale * v[c];
+  for (int c = 0; c < 4; ++c) {
+    const double out = accumulate ? (s[idx[c]] + scale * v[c]) : scale * v[c];
+    s[idx[c]] = out;
+    if (tiles) {
+      const int xx = (int)(idx[c] / Np), yy = (int)(idx[c] - (size_t)xx * Np);
+      double f = out * inv_w * phi_one;
+      f = fmin(fmax(f, -2147483000.0), 2147483000.0);
+      tiles[(((env >> 5) * Np + xx) * (size_t)(Np / 16) + (yy >> 4)) * 512 + (size_t)l * 16 +
+            ((((yy >> 2) & 3) ^ ((l >> 1) & 3)) << 2) + (yy & 3)] = (int32_t)__double2ll_rn(f);
+    }
+  }
 }
 
 static __global__ void k_scr_combine(double* __restrict__ screens, const double2* __restrict__ Y, int P, long long strideY,

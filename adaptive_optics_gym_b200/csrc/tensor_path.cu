@@ -1630,9 +1630,17 @@ k_actuators_pack(const ActT* __restrict__ actions, const double* __restrict__ gr
     if (!sh_operation) {
       double part = 0.0;
       for (int i = lane; i < K; i += 32) {
-        double r = 0.0;
-        for (int j = 0; j < K; ++j) r += sh_g[(size_t)j * K + i] * A[j];
-        part += A[i] * r;
+        // four independent chains: the 64-term dot product was one dependent FP64 FMA chain per lane (latency bound)
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+        int j = 0;
+        for (; j + 3 < K; j += 4) {
+          r0 = fma(sh_g[(size_t)j * K + i], A[j], r0);
+          r1 = fma(sh_g[(size_t)(j + 1) * K + i], A[j + 1], r1);
+          r2 = fma(sh_g[(size_t)(j + 2) * K + i], A[j + 2], r2);
+          r3 = fma(sh_g[(size_t)(j + 3) * K + i], A[j + 3], r3);
+        }
+        for (; j < K; ++j) r0 = fma(sh_g[(size_t)j * K + i], A[j], r0);
+        part += A[i] * ((r0 + r1) + (r2 + r3));
       }
       scale = target_rms / sqrt(fmax(warp_sum(part), 0.0));   // var == 0 -> inf -> 0 * inf = NaN (reference semantics); never sqrt(-eps)
     }

@@ -435,7 +435,8 @@ def main():
             return mft_roofline(r, prec)
         _, km, tm = kernel_times(r, prec)
         lc = last_chunk_of(r)
-        cands = {'optics': km['field']}
+        n_chunks = -(-r.B // min(r.env._h.chunk_size(), r.B))
+        cands = {'optics': km['field'] * n_chunks}          # km: the last chunk's launch; a step launches one per chunk
         if tm['extrusions'] > 0:
             cands['extrusion'] = tm['extrusions_ms']
         sh = {k: tm[k] for k in ('sh_phase', 'sh_fold', 'sh_gemm1', 'sh_gemm2', 'sh_camera') if tm[k] > 0}
@@ -451,16 +452,19 @@ def main():
         if top == 'optics':
             rl = fused_roofline(r, km)
         elif top == 'reset_per_step':
-            N2 = int(r.env.tables['scr_C2'].shape[0])
-            syn = lambda Nk: 2.0 * Np * (2 * Nk) * Nk + 4 * 2.0 * (Np // 2) ** 2 * Nk      # real-form synthesis
-            flop = syn(Np) + syn(N2)
+            # the reset = von-Karman synthesis (the fine scale as a 240 x 240 inverse FFT whose row kernel
+            # draws its normals and whose column kernel writes screens + phase tiles; the coarse scale as five small FP64
+            # tensor-core GEMMs) + one optics pass.  HBM-bound by design; algorithmic bytes per env: the FFT intermediate
+            # written and read (2 x 16 P), the screen written by the coarse scale, read and rewritten by the column
+            # kernel (3 x 8 P), the phase tiles (4 P), the optics pass (4 P)
+            alg = (32.0 + 24.0 + 4.0 + 4.0) * Np * Np
             ms_reset = cands[top] * r.T
-            ach = flop * r.B / (ms_reset * 1e-3) / 1e12
-            rl = {'bound': 'tensor', 'achieved': ach, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s', 'frac': ach / FP64_PEAK_TFLOPS,
-                  'traffic': None, 'kernel': 'reset: von-Karman screen synthesis S = Re(W X W^T) (k_scr_noise_planes + 10 x '
-                                             'k_dgemm_mma on the FP64 tensor cores + k_scr_combine4) + the optics chain',
-                  'ms_per_launch': ms_reset, 'envs_per_launch': r.B, 'algorithmic_flop_per_env': flop,
-                  'peak_source': 'nominal B200 FP64 37 TFLOP/s (no measured FP64 peak in MEASURED_PEAKS.json)'}
+            ach = alg * r.B / (ms_reset * 1e-3) / 1e9
+            rl = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                  'traffic': None, 'kernel': 'reset: von-Karman screen synthesis (k_scr_fft_rows + k_scr_fft_cols, coarse scale '
+                                             'on the FP64 tensor cores) + the optics chain',
+                  'ms_per_launch': ms_reset, 'envs_per_launch': r.B, 'algorithmic_bytes_per_env': alg,
+                  'peak_source': hbm_note}
         elif top == 'extrusion':
             n_ext = tm['extrusions']
             per = tm['extrusions_ms'] / n_ext
@@ -468,7 +472,7 @@ def main():
             ach = EXTRUSION_FLOP(Np, Ns) * r.B / (per * 1e-3) / 1e12     # every chunk is inside the timed span
             rl = {'bound': 'tensor', 'achieved': ach, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s',
                   'frac': ach / FP64_PEAK_TFLOPS, 'traffic': None,
-                  'kernel': 'k_ar_gather + k_ar_step: one column extrusion new = A z + B xi for every env (FP64 tensor cores)',
+                  'kernel': 'k_ar_step<DIRECT>: one column extrusion new = A z + B xi for every env, stencil read in place (FP64 tensor cores)',
                   'ms_per_launch': per, 'launches_per_step': n_ext, 'envs_per_launch': r.B,
                   'algorithmic_flop_per_env': EXTRUSION_FLOP(Np, Ns),
                   'peak_source': 'nominal B200 FP64 37 TFLOP/s (no measured FP64 peak in MEASURED_PEAKS.json)'}
