@@ -567,6 +567,7 @@ __device__ __forceinline__ int fk_column(int item_in_block) {
   return (MODE == 0 || MODE == 3) ? item_in_block : (item_in_block * FK_COL_STRIDE) % NP;   // 53 is prime: coprime with every NP
 }
 constexpr int FK_THREADS = (2 + FK_EPI_WARPS) * 32;     // 448
+
 constexpr int FK_SLOTS = 128;                           // Strehl / fibre partial slots per env (>= CTAs touching an env block)
 constexpr int FK_MIN_ITEMS = 2;                         // items per CTA at least (bounds the slots: 240 / 2 + 1 = 121 <= FK_SLOTS); small batches spread over more SMs
 constexpr int FK_PF_TILE = 32 * 16 * 4;                 // 2 KB: 32 envs x 16 pixels of phase (one bulk copy)
@@ -667,6 +668,9 @@ struct FieldParams {
 // NP = pupil pixels per side: 240 (the reference, AO_env.py:216) for every mode; 128 and 256 for the fused modes
 // (BASELINE configs[4], the pupil-grid axis).  Any multiple of 16 up to 256 fits the tiles (N of the MMA, TMEM columns).
 template <bool STREHL, int NOBS, int MODE, int NP = TC_NP>
+// (448 threads x 144 registers would fit the register file on paper, but warps are allocated in groups of four: a
+// build with __maxnreg__(144) fails to launch every variant above 128 registers.  The Strehl + 5x5-detector variant
+// therefore spills 16 bytes at the 128-register cap: 0.53 ms against 0.41 for either feature alone.)
 __global__ void __launch_bounds__(FK_THREADS, 1)
 k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constant__ CUtensorMap tmAct_lo,
               const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
