@@ -670,7 +670,7 @@ struct FieldParams {
 template <bool STREHL, int NOBS, int MODE, int NP = TC_NP>
 // (448 threads x 144 registers would fit the register file on paper, but warps are allocated in groups of four: a
 // build with __maxnreg__(144) fails to launch every variant above 128 registers.  The Strehl + 5x5-detector variant
-// therefore spills 16 bytes at the 128-register cap: 0.53 ms against 0.41 for either feature alone.)
+// sits at that cap: it spilled 16 bytes (0.53 ms against 0.41 for either feature alone) until LATE_TILE below: 0.51.)
 __global__ void __launch_bounds__(FK_THREADS, 1)
 k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constant__ CUtensorMap tmAct_lo,
               const __grid_constant__ CUtensorMap tmM_hi, const __grid_constant__ CUtensorMap tmM_lo,
@@ -925,9 +925,12 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
         buf ^= 1;
         const uint8_t* tile = pf_warp_ptr + cb * PF_SLOT + lane * 64;
         const int sw = (lane >> 1) & 3;                                   // pieces were stored at j ^ ((env >> 1) & 3)
+        // The Strehl + wide-detector variants sit at the 128-register cap of a 448-thread block: they fetch the second
+        // half of the phase tile after the first eight pixels instead of holding all 16 values through the loop.
+        constexpr bool LATE_TILE = SYM && STREHL && NOBS >= 5;
         int32_t t[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < (LATE_TILE ? 2 : 4); ++j) {
           const int4 h = *reinterpret_cast<const int4*>(tile + ((j ^ sw) << 4));
           t[4 * j] = h.x; t[4 * j + 1] = h.y; t[4 * j + 2] = h.z; t[4 * j + 3] = h.w;
         }
@@ -945,6 +948,13 @@ k_dm_phase_tc(const __grid_constant__ CUtensorMap tmAct_hi, const __grid_constan
           for (int k = 0; k < FK_JT; ++k) fre[k] = fim[k] = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
+            if (LATE_TILE && j == 8) {
+#pragma unroll
+              for (int jj = 2; jj < 4; ++jj) {
+                const int4 h = *reinterpret_cast<const int4*>(tile + ((jj ^ sw) << 4));
+                t[4 * jj] = h.x; t[4 * jj + 1] = h.y; t[4 * jj + 2] = h.z; t[4 * jj + 3] = h.w;
+              }
+            }
             const int32_t tb = t[j] + __float2int_rn(d[j] * PHI_ONE) + (1 << 22);
             float c0, s0;
             sincos_biased_fma(tb, kmask, kexp, &s0, &c0);

@@ -903,10 +903,15 @@ def test_direct_extrusion_equals_gathered_form(vel, monkeypatch):
 def test_single_env_on_the_tensor_core_kernel_against_oracle(monkeypatch):
     """Batches of up to 8 envs run the fused optics on k_small_fused (a thread per pixel); AOG_NO_SMALL=1 sends them
     through the tcgen05 kernel like every larger batch: BASELINE configs[0] / configs[1] against the oracle on that
-    kernel too."""
+    kernel too (this is also what covers the register-capped Strehl + 5x5 variant of k_dm_phase_tc at one env)."""
     monkeypatch.setenv('AOG_NO_SMALL', '1')
     test_config1_quasi_static_strehl('fused')
     test_config2_zernike_smf_ssim('fused')
+    # ... and the committed goldens, which include the Strehl + 5x5-detector variant (dynamic, 5 m/s) and the closed
+    # Shack-Hartmann loop
+    from tests.test_golden import NAMES, test_cuda_path_matches_golden
+    for name in NAMES:
+        test_cuda_path_matches_golden(name, 'fused')
 
 
 @pytest.mark.parametrize('obs_dim,act_type,K,rew_type', [(2, 'num_actuators', 64, 'strehl_ratio'), (5, 'zernike', 6, 'smf_ssim')])
