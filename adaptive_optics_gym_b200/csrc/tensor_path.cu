@@ -6,7 +6,8 @@
 //                   phase (atmosphere + DM) and, from it, every output of the step as sums over the pupil: obs-arm
 //                   column sums, Strehl sum, fibre-coupling coefficients as inner products with the fibre modes
 //                   propagated back to the pupil (G_j = M1^T (mode_j w) M2^T).  Nothing but partial sums leaves the SM.
-//   k_finalize_tc   detector powers, fibre power, Strehl, SSIM, reward
+//   k_small_fused   the same optics chain with a thread per pixel for batches of at most 8 envs (one env = configs[0])
+//   k_finalize_tcw  detector powers, fibre power, Strehl, SSIM, reward: one warp per env (kernels_f64.cuh)
 //
 // AOG_PRECISION_TENSOR -- the fibre arm through the matrix Fourier transform, three kernels per chunk:
 //   k_dm_phase_tc   DM surface as a tcgen05 GEMM over blocks of 128 envs; epilogue = total wavefront phase
